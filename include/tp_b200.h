@@ -1,0 +1,241 @@
+/* tp_b200.h — C ABI of the B200-native batched trajectory-optimisation engine.
+ *
+ * This is the drop-in boundary for the ViGO B-spline solve path of hanyujin02/trajectory_planner.
+ * The reference has no FFI / plugin interface: the boundary is the public C++ surface of
+ * trajPlanner::bsplineTraj (include/trajectory_planner/bsplineTraj.h:87-181), trajPlanner::bspline
+ * (bspline.h:22-35) and the four mapManager::occMap calls that path makes.  Each entry point below
+ * cites the reference member it replaces; INTEGRATION.md shows the shim a maintainer adds on the
+ * reference side (a ROS-free `trajPlanner::bsplineTraj` whose methods forward here).
+ *
+ * Conventions: plain pointers and sizes, caller-owned buffers, `int` return codes (0 = TP_OK,
+ * negative = error, see tp_last_error()), no exceptions cross the boundary.  An engine handle is
+ * bound to ONE GPU; use one engine per GPU (one process per GPU under torchrun, or one host thread
+ * per engine).  Calls on one engine are serialised by the caller.  There is NO CPU fallback:
+ * every compute entry point fails with TP_ERR_NO_DEVICE when no CUDA device is usable.
+ *
+ * Memory spaces: every batch entry point takes `mem` = TP_MEM_HOST (pointers are host memory; the
+ * call does H2D, compute, D2H and returns when results are in the host buffers) or TP_MEM_DEVICE
+ * (pointers are device memory on the engine's GPU; the call enqueues on `stream` and returns
+ * without synchronising unless noted).
+ */
+#ifndef TP_B200_H
+#define TP_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TP_OK 0
+#define TP_ERR_INVALID_ARG (-1)
+#define TP_ERR_NO_DEVICE (-2)
+#define TP_ERR_CUDA (-3)
+#define TP_ERR_IO (-4)
+#define TP_ERR_NO_MAP (-5)
+#define TP_ERR_CAPACITY (-6)
+
+#define TP_MEM_HOST 0
+#define TP_MEM_DEVICE 1
+
+/* per-trajectory solve status (tp_vigo_result.status) */
+#define TP_STATUS_SUCCESS 1        /* makePlan() returned true                                  */
+#define TP_STATUS_FAIL_ASTAR 0     /* "Fail because of A* failure"      (bsplineTraj.cpp:345-349) */
+#define TP_STATUS_FAIL_OPTIMIZE (-1) /* optimizeTrajectory() false: failCount>=8 or round cap (:633,:650) */
+#define TP_STATUS_FAIL_CAPACITY (-2) /* an engine capacity (segments / guide pairs / A* heap) overflowed */
+#define TP_STATUS_INVALID (-3)     /* fewer than 7 control points etc.                          */
+
+typedef struct tp_map tp_map_t;       /* host-side occupancy map (the occMap contract)          */
+typedef struct tp_engine tp_engine_t; /* one GPU: device map replica, streams, scratch          */
+
+/* ViGO parameters: the 16 rosparam keys of bsplineTraj::initParam (bsplineTraj.cpp:24-172), the
+ * compile-time constants of bsplineTraj.h:46-47,58, the L-BFGS settings of bsplineTraj.cpp:695-699
+ * and deterministic caps that replace the reference's wall-clock exits. */
+typedef struct tp_vigo_params {
+  double ts;                   /* bspline_traj/timestep                                  0.1 */
+  double dthresh;              /* bspline_traj/distance_threshold                        0.5 */
+  double max_vel, max_acc;     /* updateMaxVel / updateMaxAcc (bsplineTraj.cpp:197-205)       */
+  double w_distance, w_smooth, w_feas, w_dyn; /* weight_* keys                               */
+  double min_height, max_height;
+  double uncertain_factor;     /* uncertain_aware_factor                                     */
+  double pred_horizon;         /* prediction_horizon                                         */
+  double dthresh_dyn;          /* distance_threshold_dynamic                                 */
+  double max_path_length;
+  double max_obstacle_size[3];
+  double ctrl_pt_dist;         /* controlPointDistance_ (bsplineTraj.h:46)              0.25 */
+  double ctrl_pt_ts;           /* controlPointsTs_      (bsplineTraj.h:47)               0.2 */
+  double not_check_ratio;      /* notCheckRatio_        (bsplineTraj.h:58)               0.0 */
+  double lbfgs_g_eps;          /* solverParams.g_epsilon (bsplineTraj.cpp:699)          0.01 */
+  int32_t plan_in_z;           /* plan_in_z_axis                                             */
+  int32_t lbfgs_m;             /* mem_size (:697)                                         16 */
+  int32_t lbfgs_max_iter;      /* max_iterations (:698)                                  200 */
+  int32_t lbfgs_max_linesearch;/* lbfgs.hpp:948                                           40 */
+  int32_t max_outer_rounds;    /* replaces the 0.03 s exit of bsplineTraj.cpp:633         24 */
+  int32_t astar_max_expansions;/* replaces the 0.2 s exit of astarOcc.cpp:231         200000 */
+  int32_t strict_order;        /* 1: serial-order reductions (bit-reproduces the CPU sums)   */
+  int32_t reserved;
+} tp_vigo_params;
+
+/* per-trajectory outcome of tp_vigo_make_plan_batch */
+typedef struct tp_vigo_result {
+  int32_t status;          /* TP_STATUS_*                                                    */
+  int32_t outer_rounds;    /* iterations of the optimise/check/re-guide loop (:619-681)      */
+  int32_t fail_count;      /* failCount of bsplineTraj.cpp:615                               */
+  int32_t lbfgs_runs;      /* number of optimize() calls                                     */
+  int32_t lbfgs_iters;     /* total L-BFGS iterations (k of lbfgs.hpp:1165,1287)             */
+  int32_t lbfgs_evals;     /* total cost-function evaluations                                */
+  int32_t astar_searches;
+  int32_t astar_expansions;
+  int32_t n_guide_pairs;
+  int32_t last_lbfgs_ret;  /* lbfgs status code of the last run (lbfgs.hpp:20-80 numbering)  */
+  double final_cost;       /* fx of the last run                                             */
+  double linear_factor;    /* linearFeasibilityReparam() (bsplineTraj.cpp:1116-1137)         */
+} tp_vigo_result;
+
+typedef struct tp_lbfgs_result {
+  int32_t ret, iters, evals, reserved;
+  double fx;
+} tp_lbfgs_result;
+
+typedef struct tp_map_info {
+  double res;
+  double origin[3];
+  int32_t dims[3];
+  int32_t inflate[3];
+  int64_t n_occupied, n_inflated, n_known;
+  int64_t packed_bytes; /* bytes of one bit-packed grid as laid out in HBM */
+} tp_map_info;
+
+typedef struct tp_engine_cfg {
+  int32_t astar_workers;      /* concurrent A* searches (0 = auto from astar_mem_gb)          */
+  int32_t max_segments;       /* collision segments per trajectory (default 32)              */
+  int32_t max_guide_pairs;    /* guide (point,direction) pairs per trajectory (default 256)  */
+  int32_t astar_heap_cap;     /* open-set capacity per search (0 = auto)                      */
+  int32_t max_path_cells;     /* A* path length cap (default 4096)                            */
+  int32_t lbfgs_threads;      /* threads per trajectory block: 64 | 128 (default 128)        */
+  double astar_mem_gb;        /* HBM budget for A* node pools (default 48)                   */
+  int32_t reserved[4];
+} tp_engine_cfg;
+
+const char* tp_last_error(void);
+int tp_version(void);
+int tp_device_count(void);
+
+/* ------------------------------------------------------------------------------------ maps
+ * The occMap contract (mapManager::occMap is an external, unpinned package; this header is the
+ * definition both oracle and product share — SURVEY.md §8c):
+ *   index = floor((p - origin)/res) per axis; inside iff 0 <= index < dims;
+ *   isInflatedOccupied(p): outside -> true, else inflated bit;   (bsplineTraj.h:199,319; astarOcc.h:58)
+ *   isUnknown(p):          outside -> true, else !known bit;     (bsplineTraj.cpp:841)
+ *   isInflatedOccupiedLine(a,b): either endpoint hit, else samples a + i*res*unit(b-a),
+ *                                i = 1 .. int(|b-a|/res)-1       (bsplineTraj.cpp:435)
+ *   prebuilt insertion: a point marks its cell occupied+known and sets the inflated bit in the
+ *   index box +-inflate[] around it.                                                        */
+tp_map_t* tp_map_create(double res, const double origin[3], const int32_t dims[3], const int32_t inflate[3]);
+void tp_map_destroy(tp_map_t* m);
+int tp_map_add_points(tp_map_t* m, const double* xyz, int64_t n);
+int tp_map_add_cells(tp_map_t* m, const int32_t* ijk, int64_t n, int occupied);
+/* ASCII .pcd (the reference's map/square_static_map.pcd) through the prebuilt insertion */
+int tp_map_load_pcd(tp_map_t* m, const char* path);
+/* OctoMap .bt (the map/ directory .bt files): occupied leaves -> occupied cells, free leaves -> known cells; leaf keys
+ * are mapped to cells by their centre.  The tree's res must equal the map's res. */
+int tp_map_load_bt(tp_map_t* m, const char* path);
+/* this repo's compact raster format (.tpm: header + bit-packed occupied/known grids) */
+int tp_map_save_tpm(const tp_map_t* m, const char* path);
+tp_map_t* tp_map_load_tpm(const char* path, const int32_t inflate[3]);
+int tp_map_info_get(const tp_map_t* m, tp_map_info* info);
+/* which: 0 occupied, 1 known, 2 inflated; out = dims[0]*dims[1]*dims[2] bytes, z fastest */
+int tp_map_get_grid(const tp_map_t* m, int which, uint8_t* out);
+/* .bt helper: metric bounding box of all known leaves (octomap getMetricMin/Max; polyTrajOctomap.cpp:573-574) */
+int tp_bt_bbox(const char* path, double* res, double mn[3], double mx[3], int occupied_only);
+
+/* ------------------------------------------------------------------------------------ engine */
+void tp_engine_default_cfg(tp_engine_cfg* cfg);
+tp_engine_t* tp_engine_create(int device, const tp_engine_cfg* cfg);
+void tp_engine_destroy(tp_engine_t* e);
+/* replicate the bit-packed map into this GPU's HBM (bsplineTraj::setMap, bsplineTraj.cpp:187) */
+int tp_engine_set_map(tp_engine_t* e, const tp_map_t* m);
+int tp_engine_synchronize(tp_engine_t* e);
+/* number of kernels this engine has launched since creation (bench.py's gpu_launches) */
+int64_t tp_engine_launch_count(const tp_engine_t* e);
+/* the CUDA stream the engine enqueues on when `stream` arguments are NULL */
+void* tp_engine_stream(tp_engine_t* e);
+
+void tp_vigo_default_params(tp_vigo_params* p);
+
+/* ------------------------------------------------------------------------------------ map queries
+ * occMap::isInflatedOccupied / isUnknown / isInflatedOccupiedLine over n points (xyz = n x 3 FP64). */
+int tp_query_points(tp_engine_t* e, int64_t n, const double* xyz, uint8_t* hit, int mem, void* stream);
+int tp_query_unknown(tp_engine_t* e, int64_t n, const double* xyz, uint8_t* unknown, int mem, void* stream);
+int tp_query_lines(tp_engine_t* e, int64_t n, const double* a, const double* b, uint8_t* hit, int mem, void* stream);
+
+/* ------------------------------------------------------------------------------------ ViGO pieces
+ * Batches are ragged: trajectory b owns control points offsets[b] .. offsets[b+1]-1 of the
+ * 3 x sum(N) column-major FP64 array `ctrl` (xyz contiguous per point == optData_.controlPoints,
+ * bsplineTraj.h:22).  Guide pairs are passed as a flat list sorted by trajectory:
+ * g_offsets[B+1], g_cp[G] (control point index inside its trajectory), g_p[3G], g_v[3G]; within
+ * one control point their order is the order of optData_.guidePoints[i] (bsplineTraj.h:23-24). */
+
+/* bsplineTraj::costFunction (bsplineTraj.cpp:802-821) at the given control points:
+ * f[B], grad[3 x sum(N-6)] (gradient of the optimised columns 3..N-4, ragged by offsets[b]-6b).
+ * w_override (may be NULL): per-trajectory {weightDistance_, weightDynamicObstacle_}.        */
+int tp_vigo_cost_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, const int32_t* offsets,
+                       const double* ctrl, const int32_t* g_offsets, const int32_t* g_cp, const double* g_p,
+                       const double* g_v, const double* w_override, double* f, double* grad, int mem, void* stream);
+
+/* bsplineTraj::optimize (bsplineTraj.cpp:687-718): one fused cost+L-BFGS run per trajectory.
+ * ctrl is updated in place (it keeps the last evaluated point, as the reference's callback
+ * leaves it); x_final (may be NULL, 3 x sum(N-6)) receives the solver's own x.              */
+int tp_vigo_optimize_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, const int32_t* offsets, double* ctrl,
+                           const int32_t* g_offsets, const int32_t* g_cp, const double* g_p, const double* g_v,
+                           const double* w_override, tp_lbfgs_result* res, double* x_final, int mem, void* stream);
+
+/* bsplineTraj::hasCollisionTrajectory (bsplineTraj.h:307-325): hit[B] */
+int tp_vigo_has_collision_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, const int32_t* offsets,
+                                const double* ctrl, uint8_t* hit, int mem, void* stream);
+
+/* bsplineTraj::findCollisionSeg (bsplineTraj.cpp:403-445): nseg[B], segs[B x max_segments x 2] */
+int tp_vigo_find_collision_seg_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, const int32_t* offsets,
+                                     const double* ctrl, int32_t* nseg, int32_t* segs, int mem, void* stream);
+
+/* AStar::AstarSearch + getPath (astarOcc.cpp:119-254) for S independent (start,end) pairs:
+ * path_len[S] (-1 = failure), paths[S x max_path_cells x 3], expansions[S] */
+int tp_astar_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t S, const double* starts, const double* ends,
+                   int32_t* path_len, double* paths, int32_t* expansions, int mem, void* stream);
+
+/* first three steps of makePlan (bsplineTraj.cpp:341-352): findCollisionSeg + pathSearch +
+ * assignGuidePointsSemiCircle.  Outputs: ok[B], nseg/segs (collisionSeg_ after the merge step),
+ * guide pairs in the flat layout above (g_offsets[B+1], capacity g_cap per trajectory =
+ * engine max_guide_pairs, rows b*g_cap ..). Host memory only. */
+int tp_vigo_init_guides_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, const int32_t* offsets,
+                              const double* ctrl, uint8_t* ok, int32_t* nseg, int32_t* segs, int32_t* g_count,
+                              int32_t* g_cp, double* g_p, double* g_v);
+
+/* ------------------------------------------------------------------------------------ the batched entry point
+ * bsplineTraj::makePlan (bsplineTraj.cpp:333-385) for B independent problems that share the map
+ * and parameters: findCollisionSeg -> A* detours -> guide points -> [L-BFGS -> collision check ->
+ * re-guide / weight doubling]* -> linear time re-parameterisation.  ctrl_in / ctrl_out may alias.
+ * dyn_* (may be NULL / 0): dynamic obstacles shared by the whole batch
+ * (bsplineTraj::updateDynamicObstacles, bsplineTraj.cpp:326-330). */
+int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, const int32_t* offsets,
+                            const double* ctrl_in, double* ctrl_out, tp_vigo_result* results, int32_t n_dyn,
+                            const double* dyn_pos, const double* dyn_vel, const double* dyn_size, int mem, void* stream);
+
+/* ------------------------------------------------------------------------------------ front end (host side)
+ * What src/bspline_node.cpp:332-371 does before makePlan, for B (start, goal) pairs: seed 1-segment
+ * min-snap polynomial (exact KKT solve of the QP polyTrajSolver.cpp builds) -> resample until
+ * consecutive points are <= 1.5 * ctrl_pt_dist apart (bsplineTraj::inputPathCheck, :207-245) ->
+ * updatePath (:290-323: goal check, adjustPathLengthDirect, fillPath, parameterizeToBspline).
+ * offsets_out[B+1]; ctrl_out capacity = ctrl_cap points; valid[b] = 0 when updatePath would
+ * return false (that trajectory gets zero control points).  Returns total points or <0. */
+int64_t tp_vigo_frontend_batch(const tp_map_t* m, const tp_vigo_params* p, int32_t B, const double* starts,
+                               const double* goals, int32_t* offsets_out, double* ctrl_out, int64_t ctrl_cap,
+                               uint8_t* valid);
+/* bspline::parameterizeToBspline (bspline.cpp:74-138): K points (+ v0,v1,a0,a1) -> K+2 control points */
+int tp_bspline_fit(double ts, int32_t K, const double* points, const double* start_end4, double* ctrl_out);
+/* bspline::at / getDerivative().at (bspline.cpp:32-72), host side (pose-at-time queries stay on the host) */
+int tp_bspline_eval(int32_t N, const double* ctrl, double ts, int32_t deriv, int32_t nt, const double* t, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TP_B200_H */

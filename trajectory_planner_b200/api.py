@@ -1,0 +1,432 @@
+"""Host-side mirror of the reference interface for the ViGO B-spline path, on top of the C ABI.
+
+`OccMap` stands in for mapManager::occMap (prebuilt-map loading + the query contract), `Engine`
+owns one GPU, and `BsplineTraj` keeps the method names of trajPlanner::bsplineTraj
+(include/trajectory_planner/bsplineTraj.h:87-181): setMap / updateMaxVel / updateMaxAcc /
+updatePath / updateDynamicObstacles / makePlan / getControlPoints / getPose / getDuration /
+getLinearFactor / isCurrTrajValid, each a batch-of-one call into the same CUDA kernels the
+batched entry point (`Engine.make_plan_batch`) uses.  Nothing here computes on the CPU except the
+front end (path -> control points) and pose-at-time queries, which the design keeps on the host.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import (EngineCfg, MapInfo, VigoParams, RESULT_DTYPE, LBFGS_DTYPE, TP_MEM_DEVICE, TP_MEM_HOST, check, ptr)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def default_params():
+    p = VigoParams()
+    _capi.load().tp_vigo_default_params(C.byref(p))
+    return p
+
+
+class OccMap:
+    """Host occupancy map honouring the occMap contract of include/tp_b200.h."""
+
+    def __init__(self, res=0.1, origin=(-20.0, -20.0, -0.1), dims=(400, 400, 30), inflate=(4, 4, 2), _handle=None):
+        self.L = _capi.load()
+        if _handle is not None:
+            self.h = _handle
+        else:
+            o, d, i = _f64(origin), _i32(dims), _i32(inflate)
+            self.h = self.L.tp_map_create(float(res), o.ctypes.data_as(_capi._dp), d.ctypes.data_as(_capi._ip),
+                                          i.ctypes.data_as(_capi._ip))
+            if not self.h:
+                check(-1, "tp_map_create")
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.L.tp_map_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    @staticmethod
+    def inflate_cells(robot_size=(0.8, 0.8, 0.3), res=0.1):
+        """ceil(robot_size / (2 res)) per axis (cfg/bspline_interactive/occupancy_map.yaml:9,36)."""
+        return tuple(int(np.ceil(s / (2.0 * res))) for s in robot_size)
+
+    @classmethod
+    def from_pcd(cls, path, res=0.1, map_size=(40.0, 40.0, 3.0), ground_height=-0.1, robot_size=(0.8, 0.8, 0.3)):
+        """The reference's prebuilt-map set-up (occupancy_map.yaml:36-38,50)."""
+        origin = (-map_size[0] / 2.0, -map_size[1] / 2.0, ground_height)
+        dims = tuple(int(np.ceil(s / res)) for s in map_size)
+        m = cls(res, origin, dims, cls.inflate_cells(robot_size, res))
+        check(m.L.tp_map_load_pcd(m.h, str(path).encode()), "tp_map_load_pcd")
+        return m
+
+    @classmethod
+    def from_bt(cls, path, robot_size=(0.8, 0.8, 0.3), pad=1.0, occupied_only_bbox=True):
+        """Rasterise an OctoMap .bt at its native resolution into the occMap contract."""
+        L = _capi.load()
+        res = C.c_double(0)
+        mn, mx = np.zeros(3), np.zeros(3)
+        check(L.tp_bt_bbox(str(path).encode(), C.byref(res), mn.ctypes.data_as(_capi._dp), mx.ctypes.data_as(_capi._dp),
+                           1 if occupied_only_bbox else 0), "tp_bt_bbox")
+        r = res.value
+        lo = np.floor((mn - pad) / r) * r
+        dims = np.ceil((mx + pad - lo) / r).astype(int)
+        m = cls(r, tuple(lo), tuple(int(v) for v in dims), cls.inflate_cells(robot_size, r))
+        check(L.tp_map_load_bt(m.h, str(path).encode()), "tp_map_load_bt")
+        return m
+
+    @classmethod
+    def from_tpm(cls, path, robot_size=(0.8, 0.8, 0.3), inflate=None):
+        L = _capi.load()
+        if inflate is None:
+            # res is in the file: peek at it
+            with open(path, "rb") as f:
+                hdr = f.read(16)
+            res = float(np.frombuffer(hdr[8:16], dtype=np.float64)[0])
+            inflate = cls.inflate_cells(robot_size, res)
+        inf = _i32(inflate)
+        h = L.tp_map_load_tpm(str(path).encode(), inf.ctypes.data_as(_capi._ip))
+        if not h:
+            check(-1, "tp_map_load_tpm")
+        return cls(_handle=h)
+
+    def save_tpm(self, path):
+        check(self.L.tp_map_save_tpm(self.h, str(path).encode()), "tp_map_save_tpm")
+
+    def add_points(self, xyz):
+        xyz = _f64(xyz).reshape(-1, 3)
+        check(self.L.tp_map_add_points(self.h, xyz.ctypes.data_as(_capi._dp), len(xyz)), "tp_map_add_points")
+
+    def add_cells(self, ijk, occupied=True):
+        ijk = _i32(ijk).reshape(-1, 3)
+        check(self.L.tp_map_add_cells(self.h, ijk.ctypes.data_as(_capi._ip), len(ijk), 1 if occupied else 0),
+              "tp_map_add_cells")
+
+    def info(self):
+        mi = MapInfo()
+        check(self.L.tp_map_info_get(self.h, C.byref(mi)), "tp_map_info_get")
+        return dict(res=mi.res, origin=tuple(mi.origin), dims=tuple(mi.dims), inflate=tuple(mi.inflate),
+                    n_occupied=mi.n_occupied, n_inflated=mi.n_inflated, n_known=mi.n_known,
+                    packed_bytes=mi.packed_bytes)
+
+    def grid(self, which="inflated"):
+        w = {"occupied": 0, "known": 1, "inflated": 2}[which]
+        d = self.info()["dims"]
+        out = np.zeros(int(np.prod(d)), np.uint8)
+        check(self.L.tp_map_get_grid(self.h, w, out.ctypes.data_as(_capi._u8p)), "tp_map_get_grid")
+        return out.reshape(d)
+
+
+def frontend_batch(omap, params, starts, goals):
+    """start/goal pairs -> (offsets[B+1], ctrl[sum N, 3], valid[B]) — src/bspline_node.cpp:332-371."""
+    L = _capi.load()
+    starts, goals = _f64(starts).reshape(-1, 3), _f64(goals).reshape(-1, 3)
+    B = len(starts)
+    cap = 1024 * max(B, 1)
+    off = np.zeros(B + 1, np.int32)
+    ctrl = np.zeros((cap, 3))
+    valid = np.zeros(B, np.uint8)
+    n = L.tp_vigo_frontend_batch(omap.h, C.byref(params), B, ptr(starts), ptr(goals), ptr(off), ptr(ctrl), cap, ptr(valid))
+    check(int(n), "tp_vigo_frontend_batch")
+    return off, ctrl[:n].copy(), valid
+
+
+def bspline_fit(ts, points, start_end=None):
+    pts = _f64(points).reshape(-1, 3)
+    se = _f64(np.zeros((4, 3)) if start_end is None else start_end).reshape(4, 3)
+    out = np.zeros((len(pts) + 2, 3))
+    check(_capi.load().tp_bspline_fit(float(ts), len(pts), ptr(pts), ptr(se), ptr(out)), "tp_bspline_fit")
+    return out
+
+
+def bspline_eval(ctrl, t, ts=0.2, deriv=0):
+    ctrl = _f64(ctrl).reshape(-1, 3)
+    t = _f64(np.atleast_1d(t))
+    out = np.zeros((len(t), 3))
+    check(_capi.load().tp_bspline_eval(len(ctrl), ptr(ctrl), float(ts), int(deriv), len(t), ptr(t), ptr(out)),
+          "tp_bspline_eval")
+    return out
+
+
+class Engine:
+    """One GPU: bit-packed map replica in HBM, A* node pools, streams and scratch."""
+
+    def __init__(self, device=0, cfg=None, **cfg_kw):
+        self.L = _capi.load()
+        c = EngineCfg()
+        self.L.tp_engine_default_cfg(C.byref(c))
+        if cfg is not None:
+            c = cfg
+        for k, v in cfg_kw.items():
+            setattr(c, k, v)
+        self.cfg = c
+        self.h = self.L.tp_engine_create(int(device), C.byref(c))
+        if not self.h:
+            check(-1, "tp_engine_create")
+        self.device = int(device)
+        self.map = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.tp_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_map(self, omap):
+        check(self.L.tp_engine_set_map(self.h, omap.h), "tp_engine_set_map")
+        self.map = omap
+
+    def synchronize(self):
+        check(self.L.tp_engine_synchronize(self.h), "tp_engine_synchronize")
+
+    @property
+    def launch_count(self):
+        return int(self.L.tp_engine_launch_count(self.h))
+
+    @property
+    def stream(self):
+        return self.L.tp_engine_stream(self.h)
+
+    # ---- map queries
+    def query_points(self, xyz):
+        xyz = _f64(xyz).reshape(-1, 3)
+        out = np.zeros(len(xyz), np.uint8)
+        check(self.L.tp_query_points(self.h, len(xyz), ptr(xyz), ptr(out), TP_MEM_HOST, None), "tp_query_points")
+        return out
+
+    def query_unknown(self, xyz):
+        xyz = _f64(xyz).reshape(-1, 3)
+        out = np.zeros(len(xyz), np.uint8)
+        check(self.L.tp_query_unknown(self.h, len(xyz), ptr(xyz), ptr(out), TP_MEM_HOST, None), "tp_query_unknown")
+        return out
+
+    def query_lines(self, a, b):
+        a, b = _f64(a).reshape(-1, 3), _f64(b).reshape(-1, 3)
+        out = np.zeros(len(a), np.uint8)
+        check(self.L.tp_query_lines(self.h, len(a), ptr(a), ptr(b), ptr(out), TP_MEM_HOST, None), "tp_query_lines")
+        return out
+
+    def query_points_device(self, n, xyz_ptr, out_ptr, stream=None):
+        """Device pointers (e.g. torch tensors' data_ptr()); enqueues one kernel on `stream`."""
+        check(self.L.tp_query_points(self.h, int(n), C.c_void_p(xyz_ptr), C.c_void_p(out_ptr), TP_MEM_DEVICE,
+                                     C.c_void_p(stream) if stream else None), "tp_query_points")
+
+    # ---- ViGO pieces
+    @staticmethod
+    def _guides(guides, B):
+        if guides is None:
+            return None, None, None, None
+        g_off, g_cp, g_p, g_v = guides
+        return _i32(g_off), _i32(g_cp), _f64(g_p).reshape(-1, 3), _f64(g_v).reshape(-1, 3)
+
+    def cost_batch(self, params, offsets, ctrl, guides=None, weights=None):
+        offsets, ctrl = _i32(offsets), _f64(ctrl).reshape(-1, 3)
+        B = len(offsets) - 1
+        g_off, g_cp, g_p, g_v = self._guides(guides, B)
+        w = None if weights is None else _f64(weights).reshape(B, 2)
+        f = np.zeros(B)
+        nvar = max(3 * (len(ctrl) - 6 * B), 1)
+        grad = np.zeros(nvar)
+        check(self.L.tp_vigo_cost_batch(self.h, C.byref(params), B, ptr(offsets), ptr(ctrl), ptr(g_off), ptr(g_cp),
+                                        ptr(g_p), ptr(g_v), ptr(w), ptr(f), ptr(grad), TP_MEM_HOST, None),
+              "tp_vigo_cost_batch")
+        return f, grad
+
+    def optimize_batch(self, params, offsets, ctrl, guides=None, weights=None, want_x=True):
+        offsets, ctrl = _i32(offsets), _f64(ctrl).reshape(-1, 3).copy()
+        B = len(offsets) - 1
+        g_off, g_cp, g_p, g_v = self._guides(guides, B)
+        w = None if weights is None else _f64(weights).reshape(B, 2)
+        res = np.zeros(B, LBFGS_DTYPE)
+        nvar = max(3 * (len(ctrl) - 6 * B), 1)
+        xf = np.zeros(nvar) if want_x else None
+        check(self.L.tp_vigo_optimize_batch(self.h, C.byref(params), B, ptr(offsets), ptr(ctrl), ptr(g_off), ptr(g_cp),
+                                            ptr(g_p), ptr(g_v), ptr(w), ptr(res), ptr(xf), TP_MEM_HOST, None),
+              "tp_vigo_optimize_batch")
+        return ctrl, res, xf
+
+    def has_collision_batch(self, params, offsets, ctrl):
+        offsets, ctrl = _i32(offsets), _f64(ctrl).reshape(-1, 3)
+        B = len(offsets) - 1
+        hit = np.zeros(B, np.uint8)
+        check(self.L.tp_vigo_has_collision_batch(self.h, C.byref(params), B, ptr(offsets), ptr(ctrl), ptr(hit),
+                                                 TP_MEM_HOST, None), "tp_vigo_has_collision_batch")
+        return hit
+
+    def find_collision_seg_batch(self, params, offsets, ctrl):
+        offsets, ctrl = _i32(offsets), _f64(ctrl).reshape(-1, 3)
+        B = len(offsets) - 1
+        ms = self.cfg.max_segments
+        nseg = np.zeros(B, np.int32)
+        segs = np.zeros((B, ms, 2), np.int32)
+        check(self.L.tp_vigo_find_collision_seg_batch(self.h, C.byref(params), B, ptr(offsets), ptr(ctrl), ptr(nseg),
+                                                      ptr(segs), TP_MEM_HOST, None), "tp_vigo_find_collision_seg_batch")
+        return [segs[b, :nseg[b]].copy() for b in range(B)]
+
+    def astar_batch(self, params, starts, ends):
+        starts, ends = _f64(starts).reshape(-1, 3), _f64(ends).reshape(-1, 3)
+        S = len(starts)
+        pc = self.cfg.max_path_cells
+        plen = np.zeros(S, np.int32)
+        paths = np.zeros((S, pc, 3))
+        ex = np.zeros(S, np.int32)
+        check(self.L.tp_astar_batch(self.h, C.byref(params), S, ptr(starts), ptr(ends), ptr(plen), ptr(paths), ptr(ex),
+                                    TP_MEM_HOST, None), "tp_astar_batch")
+        return [None if plen[s] < 0 else paths[s, :plen[s]].copy() for s in range(S)], ex
+
+    def init_guides_batch(self, params, offsets, ctrl):
+        offsets, ctrl = _i32(offsets), _f64(ctrl).reshape(-1, 3)
+        B = len(offsets) - 1
+        ms, gc = self.cfg.max_segments, self.cfg.max_guide_pairs
+        ok = np.zeros(B, np.uint8)
+        nseg = np.zeros(B, np.int32)
+        segs = np.zeros((B, ms, 2), np.int32)
+        gcount = np.zeros(B, np.int32)
+        g_cp = np.zeros((B, gc), np.int32)
+        g_p = np.zeros((B, gc, 3))
+        g_v = np.zeros((B, gc, 3))
+        check(self.L.tp_vigo_init_guides_batch(self.h, C.byref(params), B, ptr(offsets), ptr(ctrl), ptr(ok), ptr(nseg),
+                                               ptr(segs), ptr(gcount), ptr(g_cp), ptr(g_p), ptr(g_v)),
+              "tp_vigo_init_guides_batch")
+        out = []
+        for b in range(B):
+            n = gcount[b]
+            out.append(dict(ok=bool(ok[b]), segs=segs[b, :nseg[b]].copy(), cp=g_cp[b, :n].copy(), p=g_p[b, :n].copy(),
+                            v=g_v[b, :n].copy()))
+        return out
+
+    # ---- the batched entry point
+    def make_plan_batch(self, params, offsets, ctrl, dyn=None):
+        """Host buffers in, host buffers out (H2D + solve + D2H inside the call)."""
+        offsets, ctrl = _i32(offsets), _f64(ctrl).reshape(-1, 3)
+        B = len(offsets) - 1
+        out = np.empty_like(ctrl)
+        res = np.zeros(B, RESULT_DTYPE)
+        n_dyn, dp, dv, ds = 0, None, None, None
+        if dyn is not None:
+            dp, dv, ds = (_f64(a).reshape(-1, 3) for a in dyn)
+            n_dyn = len(dp)
+        check(self.L.tp_vigo_make_plan_batch(self.h, C.byref(params), B, ptr(offsets), ptr(ctrl), ptr(out), ptr(res),
+                                             n_dyn, ptr(dp), ptr(dv), ptr(ds), TP_MEM_HOST, None),
+              "tp_vigo_make_plan_batch")
+        return out, res
+
+    def make_plan_batch_device(self, params, B, offsets_ptr, ctrl_in_ptr, ctrl_out_ptr, results_ptr, stream=None):
+        """Device pointers (inputs already resident in HBM); results stay on the device."""
+        check(self.L.tp_vigo_make_plan_batch(self.h, C.byref(params), int(B), C.c_void_p(offsets_ptr),
+                                             C.c_void_p(ctrl_in_ptr), C.c_void_p(ctrl_out_ptr), C.c_void_p(results_ptr),
+                                             0, None, None, None, TP_MEM_DEVICE, C.c_void_p(stream) if stream else None),
+              "tp_vigo_make_plan_batch")
+
+
+class BsplineTraj:
+    """Method-for-method stand-in for trajPlanner::bsplineTraj (bsplineTraj.h:87-181) for one
+    trajectory: the planner state lives on the host, every heavy step runs on the GPU engine."""
+
+    def __init__(self, engine, params=None):
+        self.engine = engine
+        self.params = params if params is not None else default_params()
+        self.ctrl = None
+        self.init_ = False
+        self.linear_factor = 1.0
+        self.dyn = None
+        self.last_result = None
+
+    def setMap(self, omap):
+        self.engine.set_map(omap)
+
+    def updateMaxVel(self, v):
+        self.params.max_vel = float(v)
+
+    def updateMaxAcc(self, a):
+        self.params.max_acc = float(a)
+
+    def getInitTs(self):
+        return self.params.ctrl_pt_dist / self.params.max_vel
+
+    def getControlPointTs(self):
+        return self.params.ctrl_pt_ts
+
+    def getControlPointDist(self):
+        return self.params.ctrl_pt_dist
+
+    def updateControlPoints(self, ctrl):
+        """Directly set optData_.controlPoints (what updatePath leaves behind, bsplineTraj.cpp:315-319)."""
+        self.ctrl = _f64(ctrl).reshape(-1, 3).copy()
+        self.dyn = None
+        self.init_ = True
+        return True
+
+    def updatePathFromStartGoal(self, start, goal):
+        """src/bspline_node.cpp:332-371: seed min-snap path, inputPathCheck loop, updatePath."""
+        off, ctrl, valid = frontend_batch(self.engine.map, self.params, [start], [goal])
+        if not valid[0]:
+            return False
+        return self.updateControlPoints(ctrl)
+
+    def updatePath(self, path, start_end_conditions=None):
+        """bsplineTraj::updatePath for an already resampled path (>= 4 points): goal check + B-spline fit.
+        (adjustPathLengthDirect/fillPath are applied by updatePathFromStartGoal's front end.)"""
+        path = _f64(path).reshape(-1, 3)
+        if self.engine.map is None:
+            raise _capi.TpError("setMap first")
+        if self.engine.query_points(path[-1:])[0]:
+            return False
+        if len(path) < 4:
+            return False
+        return self.updateControlPoints(bspline_fit(self.params.ctrl_pt_ts, path, start_end_conditions))
+
+    def updateDynamicObstacles(self, pos, vel, size):
+        self.dyn = (pos, vel, size)
+
+    def makePlan(self):
+        if not self.init_:
+            return False
+        off = np.array([0, len(self.ctrl)], np.int32)
+        out, res = self.engine.make_plan_batch(self.params, off, self.ctrl, self.dyn)
+        self.last_result = res[0]
+        self.ctrl = out
+        if res[0]["status"] == _capi.TP_STATUS_SUCCESS:
+            self.linear_factor = float(res[0]["linear_factor"])
+            return True
+        return False
+
+    def getControlPoints(self):
+        return self.ctrl.T.copy()  # 3 x N like the reference's Eigen::MatrixXd
+
+    def getDuration(self):
+        return (len(self.ctrl) - 3) * self.params.ctrl_pt_ts
+
+    def getTimestep(self):
+        return self.params.ts
+
+    def getLinearFactor(self):
+        return self.linear_factor
+
+    def getLinearReparamTime(self, t):
+        return self.linear_factor * t
+
+    def getPose(self, t, yaw=True):
+        """-> (x, y, z, yaw) — bsplineTraj.cpp:1402-1419 (pose-at-time stays on the host)."""
+        p = bspline_eval(self.ctrl, [t], self.params.ctrl_pt_ts, 0)[0]
+        if not yaw:
+            return p[0], p[1], p[2], 0.0
+        v = bspline_eval(self.ctrl, [t], self.params.ctrl_pt_ts, 1)[0]
+        return p[0], p[1], p[2], float(np.arctan2(v[1], v[0]))
+
+    def isCurrTrajValid(self):
+        if not self.init_:
+            return False
+        off = np.array([0, len(self.ctrl)], np.int32)
+        return not bool(self.engine.has_collision_batch(self.params, off, self.ctrl)[0])

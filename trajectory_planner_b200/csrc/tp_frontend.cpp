@@ -1,0 +1,357 @@
+// Host-side front end of the ViGO solve: what src/bspline_node.cpp:332-371 does between the two
+// RViz clicks and bsplineTraj::makePlan().  Stays on the host (SURVEY.md §8f-2 marks a device
+// version as a later row); it produces the control points that are the input of the GPU path.
+//
+//   seed:   1-segment min-snap polynomial start->goal, rest to rest
+//           (polyTrajOccMap::makePlan(false), polyTrajOccMap.cpp:326-399; QP of
+//           polyTrajSolver.cpp:241-271 (P), :314-584 (A), :587-813 (bounds), time allocation
+//           :125-138, de-normalisation :870-879).  The reference hands the QP to OSQP
+//           (eps 1e-3); we solve the same equality-constrained QP exactly via its KKT system.
+//   sample: polyTrajOccMap::getTrajectory(dt) (polyTrajOccMap.cpp:434-446) + polyTrajSolver::getPos
+//           (polyTrajSolver.cpp:1051-1071)
+//   check:  bsplineTraj::inputPathCheck (bsplineTraj.cpp:207-245), dt *= 0.8 loop of
+//           src/bspline_node.cpp:355-366 (its 0.05 s wall clock -> a 60-iteration cap)
+//   update: bsplineTraj::updatePath (bsplineTraj.cpp:290-323): goal check, adjustPathLengthDirect
+//           (:754-793; the function-static prevPathLength is an explicit 0.0 per problem), fillPath
+//           (:247-288), bspline::parameterizeToBspline (bspline.cpp:74-138).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../../include/tp_b200.h"
+#include "tp_map.h"
+
+namespace {
+
+struct P3 {
+  double x, y, z;
+};
+inline P3 sub(const P3& a, const P3& b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline double norm(const P3& a) { return std::sqrt((a.x * a.x + a.y * a.y) + a.z * a.z); }
+
+// dense solve A x = b (n x n, row-major) with partial pivoting; returns false if singular
+bool solve_dense(std::vector<double>& A, std::vector<double>& b, int n) {
+  for (int c = 0; c < n; ++c) {
+    int piv = c;
+    double best = std::fabs(A[(size_t)c * n + c]);
+    for (int r = c + 1; r < n; ++r)
+      if (std::fabs(A[(size_t)r * n + c]) > best) {
+        best = std::fabs(A[(size_t)r * n + c]);
+        piv = r;
+      }
+    if (best < 1e-300) return false;
+    if (piv != c) {
+      for (int k = 0; k < n; ++k) std::swap(A[(size_t)piv * n + k], A[(size_t)c * n + k]);
+      std::swap(b[piv], b[c]);
+    }
+    for (int r = c + 1; r < n; ++r) {
+      double f = A[(size_t)r * n + c] / A[(size_t)c * n + c];
+      if (f == 0) continue;
+      for (int k = c; k < n; ++k) A[(size_t)r * n + k] -= f * A[(size_t)c * n + k];
+      b[r] -= f * b[c];
+    }
+  }
+  for (int r = n - 1; r >= 0; --r) {
+    double s = b[r];
+    for (int k = r + 1; k < n; ++k) s -= A[(size_t)r * n + k] * b[k];
+    b[r] = s / A[(size_t)r * n + r];
+  }
+  return true;
+}
+
+// one-segment min-snap, degree 7, normalised time; rows: p(0), p(1), v(0), v(1), a(0), a(1)
+// (constructA order for K = 1).  Endpoint velocity/acceleration bounds are NOT scaled by the
+// duration in the reference (constructBound); with the rest-to-rest conditions used here that is
+// immaterial.  coef[3][8] returned in real time (c_d /= T^d).
+bool seed_minsnap(const P3& s, const P3& g, double desired_vel, double coef[3][8], double& T) {
+  const int n = 8, m = 6, diff = 4;
+  T = norm(sub(g, s)) / desired_vel;
+  double P[8][8];
+  std::memset(P, 0, sizeof(P));
+  for (int i = diff; i < n; ++i)
+    for (int j = diff; j < n; ++j) {
+      double f = 1.0;
+      for (int d = 0; d < diff; ++d) f *= (double)((i - d) * (j - d));
+      f /= (double)(i + j - diff * 2 + 1);
+      P[i][j] = f;
+    }
+  double A[6][8];
+  std::memset(A, 0, sizeof(A));
+  A[0][0] = 1.0;
+  for (int d = 0; d < n; ++d) A[1][d] = 1.0;
+  A[2][1] = 1.0;
+  for (int d = 1; d < n; ++d) A[3][d] = (double)d;
+  A[4][2] = 2.0;
+  for (int d = 2; d < n; ++d) A[5][d] = (double)(d * (d - 1));
+  const double rhs[3][6] = {{s.x, g.x, 0, 0, 0, 0}, {s.y, g.y, 0, 0, 0, 0}, {s.z, g.z, 0, 0, 0, 0}};
+  for (int ax = 0; ax < 3; ++ax) {
+    const int N = n + m;
+    std::vector<double> K((size_t)N * N, 0.0), b(N, 0.0);
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) K[(size_t)i * N + j] = P[i][j];
+    for (int r = 0; r < m; ++r)
+      for (int j = 0; j < n; ++j) {
+        K[(size_t)(n + r) * N + j] = A[r][j];
+        K[(size_t)j * N + n + r] = A[r][j];
+      }
+    for (int r = 0; r < m; ++r) b[n + r] = rhs[ax][r];
+    if (!solve_dense(K, b, N)) return false;
+    for (int d = 0; d < n; ++d) coef[ax][d] = b[d] / std::pow(T, d);
+  }
+  return true;
+}
+
+P3 poly_pos(const double coef[3][8], double t) {
+  double x = 0, y = 0, z = 0;
+  for (int d = 0; d < 8; ++d) {
+    const double pw = std::pow(t, d);
+    x += coef[0][d] * pw;
+    y += coef[1][d] * pw;
+    z += coef[2][d] * pw;
+  }
+  return {x, y, z};
+}
+
+bool line_occ(const tp_map* m, const P3& a, const P3& b) {
+  const double pa[3] = {a.x, a.y, a.z}, pb[3] = {b.x, b.y, b.z};
+  return m->is_inflated_occupied_line(pa, pb);
+}
+
+// bsplineTraj::adjustPathLengthDirect with prevPathLength = 0
+void adjust_path_length_direct(const tp_map* m, const std::vector<P3>& path, double max_len, std::vector<P3>& out) {
+  out.clear();
+  bool exceed = false;
+  double min_len = 0.0;
+  const P3 p0 = path[0];
+  for (size_t i = 0; i + 1 < path.size(); ++i) {
+    const P3 p1 = path[i], p2 = path[i + 1];
+    const double total = norm(sub(p2, p0));
+    if (total >= std::max(0.0, max_len)) exceed = true;
+    out.push_back(p1);
+    if (exceed) {
+      const bool free_ = !line_occ(m, p1, p2);
+      if (free_ && min_len >= 1.5) {
+        out.push_back(p2);
+        return;
+      }
+    }
+    if (line_occ(m, p1, p2))
+      min_len = 0.0;
+    else
+      min_len += norm(sub(p2, p1));
+  }
+  out.push_back(path.back());
+}
+
+// bsplineTraj::inputPathCheck
+bool input_path_check(const tp_map* m, const std::vector<P3>& path, double cp_dist, double max_len,
+                      std::vector<P3>& adjusted) {
+  if (path.empty()) return true;
+  std::vector<P3> adj;
+  adjust_path_length_direct(m, path, max_len, adj);
+  for (size_t i = 0; i + 1 < adj.size(); ++i)
+    if (norm(sub(adj[i], adj[i + 1])) > cp_dist * 1.5) return false;
+  adjusted.clear();
+  P3 prev = adj[0];
+  for (size_t i = 0; i < adj.size(); ++i) {
+    if (i == 0) {
+      adjusted.push_back(adj[i]);
+      prev = adj[i];
+    } else if (norm(sub(adj[i], prev)) >= cp_dist * 0.8) {
+      adjusted.push_back(adj[i]);
+      prev = adj[i];
+    }
+  }
+  adjusted.push_back(adjusted.back());
+  return true;
+}
+
+bool fill_path(const std::vector<P3>& p, std::vector<P3>& out) {
+  if (p.size() <= 1) return false;
+  if (p.size() == 2) {
+    const P3 d = sub(p[1], p[0]);
+    out = {p[0],
+           {d.x / 3.0 + p[0].x, d.y / 3.0 + p[0].y, d.z / 3.0 + p[0].z},
+           {2.0 * d.x / 3.0 + p[0].x, 2.0 * d.y / 3.0 + p[0].y, 2.0 * d.z / 3.0 + p[0].z},
+           p[1]};
+  } else if (p.size() == 3) {
+    out = {p[0],
+           {(p[0].x + p[1].x) / 2.0, (p[0].y + p[1].y) / 2.0, (p[0].z + p[1].z) / 2.0},
+           p[1],
+           {(p[1].x + p[2].x) / 2.0, (p[1].y + p[2].y) / 2.0, (p[1].z + p[2].z) / 2.0},
+           p[2]};
+  } else
+    out = p;
+  return true;
+}
+
+// least squares min |A x - b| for 3 right-hand sides via Householder QR (A: rows x cols, row-major)
+void lstsq3(std::vector<double>& A, std::vector<double>& B, int rows, int cols, std::vector<double>& X) {
+  for (int c = 0; c < cols; ++c) {
+    double nrm = 0;
+    for (int r = c; r < rows; ++r) nrm += A[(size_t)r * cols + c] * A[(size_t)r * cols + c];
+    nrm = std::sqrt(nrm);
+    if (nrm == 0) continue;
+    const double alpha = A[(size_t)c * cols + c] > 0 ? -nrm : nrm;
+    std::vector<double> v(rows - c);
+    for (int r = c; r < rows; ++r) v[r - c] = A[(size_t)r * cols + c];
+    v[0] -= alpha;
+    double vn = 0;
+    for (double t : v) vn += t * t;
+    if (vn == 0) continue;
+    for (int k = c; k < cols; ++k) {
+      double s = 0;
+      for (int r = c; r < rows; ++r) s += v[r - c] * A[(size_t)r * cols + k];
+      s = 2 * s / vn;
+      for (int r = c; r < rows; ++r) A[(size_t)r * cols + k] -= s * v[r - c];
+    }
+    for (int k = 0; k < 3; ++k) {
+      double s = 0;
+      for (int r = c; r < rows; ++r) s += v[r - c] * B[(size_t)r * 3 + k];
+      s = 2 * s / vn;
+      for (int r = c; r < rows; ++r) B[(size_t)r * 3 + k] -= s * v[r - c];
+    }
+  }
+  X.assign((size_t)cols * 3, 0.0);
+  for (int k = 0; k < 3; ++k)
+    for (int r = cols - 1; r >= 0; --r) {
+      double s = B[(size_t)r * 3 + k];
+      for (int j = r + 1; j < cols; ++j) s -= A[(size_t)r * cols + j] * X[(size_t)j * 3 + k];
+      X[(size_t)r * 3 + k] = s / A[(size_t)r * cols + r];
+    }
+}
+
+// bspline::parameterizeToBspline
+void fit_bspline(double ts, const std::vector<P3>& pts, const double se[12], std::vector<double>& ctrl) {
+  const int K = (int)pts.size(), rows = K + 4, cols = K + 2;
+  std::vector<double> A((size_t)rows * cols, 0.0), B((size_t)rows * 3, 0.0);
+  const double pr[3] = {1, 4, 1}, vr[3] = {-1, 0, 1}, ar[3] = {1, -2, 1};
+  for (int i = 0; i < K; ++i)
+    for (int k = 0; k < 3; ++k) A[(size_t)i * cols + i + k] = (1 / 6.0) * pr[k];
+  for (int k = 0; k < 3; ++k) {
+    A[(size_t)K * cols + k] = (1 / 2.0 / ts) * vr[k];
+    A[(size_t)(K + 1) * cols + K - 1 + k] = (1 / 2.0 / ts) * vr[k];
+    A[(size_t)(K + 2) * cols + k] = (1 / ts / ts) * ar[k];
+    A[(size_t)(K + 3) * cols + K - 1 + k] = (1 / ts / ts) * ar[k];
+  }
+  for (int i = 0; i < K; ++i) {
+    B[(size_t)i * 3] = pts[i].x;
+    B[(size_t)i * 3 + 1] = pts[i].y;
+    B[(size_t)i * 3 + 2] = pts[i].z;
+  }
+  for (int i = 0; i < 4; ++i)
+    for (int k = 0; k < 3; ++k) B[(size_t)(K + i) * 3 + k] = se[3 * i + k];
+  lstsq3(A, B, rows, cols, ctrl);
+}
+
+// bspline::at for a degree-p uniform spline given as packed control points
+void bspline_at(const std::vector<double>& cp, int n, int degree, double ts, double t, double out[3]) {
+  const double duration = (double)((n - 1 + degree + 1 + 1) - degree - 1 - degree) * ts;
+  const double tb = std::min(std::max(0.0, t), duration);
+  int k = degree;
+  while ((double)(k + 1 - degree) * ts < tb) ++k;
+  double d[4][3];
+  for (int i = 0; i <= degree; ++i)
+    for (int a = 0; a < 3; ++a) d[i][a] = cp[(size_t)3 * (k - degree + i) + a];
+  for (int r = 1; r <= degree; ++r)
+    for (int i = degree; i >= r; --i) {
+      const double ka = (double)(i + k - degree - degree) * ts;
+      const double kb = (double)(i + 1 + k - r - degree) * ts;
+      const double alpha = (tb - ka) / (kb - ka);
+      for (int a = 0; a < 3; ++a) d[i][a] = (1 - alpha) * d[i - 1][a] + alpha * d[i][a];
+    }
+  for (int a = 0; a < 3; ++a) out[a] = d[degree][a];
+}
+
+}  // namespace
+
+extern "C" {
+
+int tp_bspline_fit(double ts, int32_t K, const double* points, const double* start_end4, double* ctrl_out) {
+  if (!(ts > 0) || K < 4 || !points || !start_end4 || !ctrl_out) {
+    tp_set_error("tp_bspline_fit: need ts > 0, >= 4 points and 4 boundary vectors (bspline.cpp:78-93)");
+    return TP_ERR_INVALID_ARG;
+  }
+  std::vector<P3> pts(K);
+  for (int i = 0; i < K; ++i) pts[i] = {points[3 * i], points[3 * i + 1], points[3 * i + 2]};
+  std::vector<double> c;
+  fit_bspline(ts, pts, start_end4, c);
+  std::memcpy(ctrl_out, c.data(), sizeof(double) * 3 * (K + 2));
+  return TP_OK;
+}
+
+int tp_bspline_eval(int32_t N, const double* ctrl, double ts, int32_t deriv, int32_t nt, const double* t, double* out) {
+  if (N < 4 || !ctrl || !(ts > 0) || deriv < 0 || deriv > 2 || (nt > 0 && (!t || !out))) return TP_ERR_INVALID_ARG;
+  std::vector<double> cp(ctrl, ctrl + 3 * (size_t)N);
+  int n = N, degree = 3;
+  for (int k = 0; k < deriv; ++k) {  // bspline::getDerivative
+    std::vector<double> q((size_t)3 * (n - 1));
+    for (int i = 0; i < n - 1; ++i) {
+      const double den = (double)(i + degree + 1 - degree) * ts - (double)(i + 1 - degree) * ts;
+      for (int a = 0; a < 3; ++a) q[3 * i + a] = ((double)degree * (cp[3 * (i + 1) + a] - cp[3 * i + a])) / den;
+    }
+    cp.swap(q);
+    --n;
+    --degree;
+  }
+  for (int i = 0; i < nt; ++i) bspline_at(cp, n, degree, ts, t[i], out + 3 * i);
+  return TP_OK;
+}
+
+int64_t tp_vigo_frontend_batch(const tp_map_t* m, const tp_vigo_params* p, int32_t B, const double* starts,
+                               const double* goals, int32_t* offsets_out, double* ctrl_out, int64_t ctrl_cap,
+                               uint8_t* valid) {
+  if (!m || !p || B < 0 || !starts || !goals || !offsets_out || !ctrl_out) return TP_ERR_INVALID_ARG;
+  int64_t total = 0;
+  offsets_out[0] = 0;
+  const double zeros[12] = {0};
+  for (int b = 0; b < B; ++b) {
+    const P3 s = {starts[3 * b], starts[3 * b + 1], starts[3 * b + 2]};
+    const P3 g = {goals[3 * b], goals[3 * b + 1], goals[3 * b + 2]};
+    bool ok = true;
+    std::vector<double> ctrl;
+    double coef[3][8], T = 0;
+    if (!(norm(sub(g, s)) > 0) || !seed_minsnap(s, g, p->max_vel, coef, T)) ok = false;
+    std::vector<P3> adjusted, best;
+    if (ok) {
+      double dt = p->ctrl_pt_dist / p->max_vel;  // bsplineTraj::getInitTs
+      bool have = false;
+      for (int it = 0; it < 60; ++it) {
+        std::vector<P3> traj;
+        for (double t = 0; t <= T; t += dt) traj.push_back(poly_pos(coef, t));
+        std::vector<P3> adj;
+        const bool sat = input_path_check(m, traj, p->ctrl_pt_dist, p->max_path_length, adj);
+        if (sat) {
+          best = adj;
+          have = true;
+          break;
+        }
+        dt *= 0.8;
+      }
+      if (!have || best.empty()) ok = false;
+    }
+    if (ok) {
+      const P3 goal = best.back();
+      if (m->is_inflated_occupied(goal.x, goal.y, goal.z)) ok = false;  // updatePath :291-295
+    }
+    if (ok) {
+      std::vector<P3> inp;
+      adjust_path_length_direct(m, best, p->max_path_length, inp);
+      if (inp.size() < 4) ok = fill_path(best, inp);
+      if (ok) fit_bspline(p->ctrl_pt_ts, inp, zeros, ctrl);
+    }
+    const int64_t n = ok ? (int64_t)ctrl.size() / 3 : 0;
+    if (total + n > ctrl_cap) {
+      tp_set_error("tp_vigo_frontend_batch: ctrl_cap too small");
+      return TP_ERR_CAPACITY;
+    }
+    if (n) std::memcpy(ctrl_out + 3 * total, ctrl.data(), sizeof(double) * 3 * n);
+    total += n;
+    offsets_out[b + 1] = (int32_t)total;
+    if (valid) valid[b] = ok ? 1 : 0;
+  }
+  return total;
+}
+
+}  // extern "C"

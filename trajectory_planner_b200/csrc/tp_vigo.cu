@@ -1,0 +1,1235 @@
+// ViGO batch engine: kernels, per-GPU engine state and the C ABI entry points of include/tp_b200.h.
+// sm_100a only; compiled with --fmad=false (see tp_device.cuh).  No CPU fallback: every compute
+// entry point needs a CUDA device.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "tp_lbfgs.cuh"
+#include "tp_map.h"
+#include "tp_outer.cuh"
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t _e = (call);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      tp_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e));     \
+      return TP_ERR_CUDA;                                                                     \
+    }                                                                                         \
+  } while (0)
+
+// =========================================================================== kernels
+// ---- map queries (occMap::isInflatedOccupied / isUnknown / isInflatedOccupiedLine)
+// One thread per query; xyz is read as three coalesced FP64 streams per warp (24 B/query) and the
+// map word through the read-only path (one 32 B sector per random gather).
+__global__ void k_query_points(DevMap map, long n, const double* __restrict__ xyz, uint8_t* __restrict__ out, int unknown) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const D3 p = d3(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    out[i] = unknown ? (dm_unknown(map, p) ? 1 : 0) : (dm_inflated(map, p) ? 1 : 0);
+  }
+}
+__global__ void k_query_lines(DevMap map, long n, const double* __restrict__ a, const double* __restrict__ b,
+                              uint8_t* __restrict__ out) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    out[i] = dm_line(map, d3(a[3 * i], a[3 * i + 1], a[3 * i + 2]), d3(b[3 * i], b[3 * i + 1], b[3 * i + 2])) ? 1 : 0;
+}
+
+// ---- batch state set-up
+__global__ void k_init_states(BatchView bv, VigoConst C) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= bv.B) return;
+  TrajState& st = bv.st[b];
+  st.N = bv.off[b + 1] - bv.off[b];
+  st.off = bv.off[b];
+  st.status = TS_ACTIVE;
+  st.has_col = 0;
+  st.fail_count = 0;
+  st.round = 0;
+  st.nseg = 0;
+  st.n_pairs = 0;
+  st.err = 0;
+  st.lbfgs_runs = st.lbfgs_iters = st.lbfgs_evals = st.last_ret = 0;
+  st.astar_searches = st.astar_expansions = 0;
+  st.w_dist = C.p.w_distance;
+  st.w_dyn = C.p.w_dyn;
+  st.final_cost = 0;
+  st.linear_factor = 1.0;
+}
+__global__ void k_fill_int(int* p, long n, int v) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void k_iota(int* p, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
+}
+
+// ---- costFunction (test/parity entry): one block per trajectory
+template <bool STRICT>
+__global__ void __launch_bounds__(TP_LB_THREADS) k_cost(BatchView bv, VigoConst C, double* f_out, double* grad_out) {
+  extern __shared__ double sm[];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const TrajState& st = bv.st[b];
+  const int N = st.N, n = 3 * (N - 2 * TP_DEGREE);
+  if (n <= 0) {
+    if (tid == 0) f_out[b] = 0.0;
+    return;
+  }
+  double* cp = sm;
+  double* g = cp + 3 * N;
+  Red R;
+  R.buf = g + n;
+  R.flip = 0;
+  for (int e = tid; e < 3 * N; e += TP_LB_THREADS) cp[e] = bv.ctrl[3 * (size_t)st.off + e];
+  EvalCtx E;
+  E.N = N; E.n = n; E.cp = cp;
+  E.pairs = bv.pairs + (size_t)b * C.gcap;
+  E.head = bv.cp_head + st.off;
+  E.w_dist = st.w_dist; E.w_dyn = st.w_dyn;
+  E.n_dyn = bv.n_dyn; E.dyn_pos = bv.dyn_pos; E.dyn_vel = bv.dyn_vel; E.dyn_size = bv.dyn_size;
+  __syncthreads();
+  double f, dg;
+  eval_cost<STRICT>(C, E, R, g, nullptr, f, dg, tid);
+  if (tid == 0) f_out[b] = f;
+  double* go = grad_out + 3 * ((size_t)st.off - (size_t)2 * TP_DEGREE * b);
+  for (int e = tid; e < n; e += TP_LB_THREADS) go[e] = g[e];
+}
+
+// ---- optimize(): fused cost + L-BFGS, one block per ACTIVE trajectory
+template <bool STRICT>
+__global__ void __launch_bounds__(TP_LB_THREADS) k_lbfgs(BatchView bv, VigoConst C, const int* __restrict__ active,
+                                                         const int* __restrict__ n_active, tp_lbfgs_result* res_out,
+                                                         double* xfinal_out) {
+  extern __shared__ double sm[];
+  if ((int)blockIdx.x >= *n_active) return;
+  const int b = active[blockIdx.x], tid = threadIdx.x;
+  TrajState& st = bv.st[b];
+  const int N = st.N, n = 3 * (N - 2 * TP_DEGREE);
+  tp_lbfgs_result r;
+  if (n <= 0) {
+    r.ret = LB_INVALID_N; r.iters = 0; r.evals = 0; r.reserved = 0; r.fx = 0;
+  } else {
+    double* cp = sm;
+    double* gctrl = bv.ctrl + 3 * (size_t)st.off;
+    for (int e = tid; e < 3 * N; e += TP_LB_THREADS) cp[e] = gctrl[e];
+    EvalCtx E;
+    E.N = N; E.n = n; E.cp = cp;
+    E.pairs = bv.pairs + (size_t)b * C.gcap;
+    E.head = bv.cp_head + st.off;
+    E.w_dist = st.w_dist; E.w_dyn = st.w_dyn;
+    E.n_dyn = bv.n_dyn; E.dyn_pos = bv.dyn_pos; E.dyn_vel = bv.dyn_vel; E.dyn_size = bv.dyn_size;
+    double* xf = xfinal_out ? xfinal_out + 3 * ((size_t)st.off - (size_t)2 * TP_DEGREE * b) : nullptr;
+    lbfgs_run<STRICT>(C, E, cp + 3 * N, r, xf, tid);
+    // the control points keep the last evaluated point (bsplineTraj.cpp:803)
+    for (int e = tid; e < n; e += TP_LB_THREADS) gctrl[3 * TP_DEGREE + e] = cp[3 * TP_DEGREE + e];
+  }
+  if (tid == 0) {
+    st.lbfgs_runs += 1;
+    st.lbfgs_iters += r.iters;
+    st.lbfgs_evals += r.evals;
+    st.last_ret = r.ret;
+    st.final_cost = r.fx;
+    if (res_out) res_out[b] = r;
+  }
+}
+
+// ---- hasCollisionTrajectory (+ hasDynamicCollisionTrajectory), one block per active trajectory
+struct SmemCP {
+  const double* p;
+  __device__ __forceinline__ D3 operator()(int i) const { return d3(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }
+};
+__global__ void __launch_bounds__(TP_LB_THREADS) k_has_collision(BatchView bv, VigoConst C, DevMap map,
+                                                                 const int* __restrict__ active,
+                                                                 const int* __restrict__ n_active, uint8_t* hit_out) {
+  extern __shared__ double sm[];
+  if ((int)blockIdx.x >= *n_active) return;
+  const int b = active[blockIdx.x], tid = threadIdx.x;
+  TrajState& st = bv.st[b];
+  const int N = st.N;
+  if (N < 4) {
+    if (tid == 0) { st.has_col = 1; if (hit_out) hit_out[b] = 1; }
+    return;
+  }
+  for (int e = tid; e < 3 * N; e += TP_LB_THREADS) sm[e] = bv.ctrl[3 * (size_t)st.off + e];
+  __syncthreads();
+  SmemCP cp{sm};
+  const double cts = C.p.ctrl_pt_ts;
+  const double duration = (double)(N - TP_DEGREE) * cts;          // knots_(N), bspline.cpp:27
+  const double limit = (1.0 - C.p.not_check_ratio) * duration;    // bsplineTraj.h:313
+  int hit = 0, dyn = 0;
+  for (int s = tid; s < C.n_t_check; s += TP_LB_THREADS) {
+    const double t = bv.t_check[s];
+    if (!(t <= duration)) break;  // the table is increasing
+    const D3 p = bspline_at(cp, N, TP_DEGREE, cts, t);
+    if (t <= limit && dm_inflated(map, p)) hit = 1;
+    for (int j = 0; j < bv.n_dyn; ++j) {  // bsplineTraj.h:344-368 (samples of evalTraj(): t <= duration)
+      const double size = fmin(bv.dyn_size[3 * j] / 2, bv.dyn_size[3 * j + 1] / 2);
+      const double dx = p.x - bv.dyn_pos[3 * j], dy = p.y - bv.dyn_pos[3 * j + 1];
+      const double dist = sqrt((dx * dx + dy * dy) + 0.0 * 0.0) - size;
+      if (dist < 0) dyn = 1;
+    }
+  }
+  const int any = __syncthreads_or(hit | (dyn << 1));
+  if (tid == 0) {
+    st.has_col = any;
+    if (hit_out) hit_out[b] = (uint8_t)(any & 1);
+  }
+}
+
+// ---- linearFeasibilityReparam (bsplineTraj.cpp:1116-1137), one block per trajectory
+__global__ void __launch_bounds__(TP_LB_THREADS) k_reparam(BatchView bv, VigoConst C) {
+  extern __shared__ double sm[];
+  __shared__ double redv[TP_LB_WARPS], reda[TP_LB_WARPS];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  TrajState& st = bv.st[b];
+  if (st.status != TP_STATUS_SUCCESS) return;
+  const int N = st.N;
+  double* cp = sm;
+  double* q = cp + 3 * N;        // velocity spline control points (N-1), bspline.cpp:64-72
+  double* r = q + 3 * (N - 1);   // acceleration spline control points (N-2)
+  const double ts = C.p.ctrl_pt_ts;
+  for (int e = tid; e < 3 * N; e += TP_LB_THREADS) cp[e] = bv.ctrl[3 * (size_t)st.off + e];
+  __syncthreads();
+  for (int e = tid; e < 3 * (N - 1); e += TP_LB_THREADS) {
+    const int i = e / 3;
+    const double den = (double)(i + 3 + 1 - 3) * ts - (double)(i + 1 - 3) * ts;  // knots_(i+p+1) - knots_(i+1), p = 3
+    q[e] = (3.0 * (cp[e + 3] - cp[e])) / den;
+  }
+  __syncthreads();
+  for (int e = tid; e < 3 * (N - 2); e += TP_LB_THREADS) {
+    const int i = e / 3;
+    const double den = (double)(i + 2 + 1 - 2) * ts - (double)(i + 1 - 2) * ts;  // derivative spline: p = 2
+    r[e] = (2.0 * (q[e + 3] - q[e])) / den;
+  }
+  __syncthreads();
+  SmemCP vq{q}, ar{r};
+  const double duration = (double)(N - TP_DEGREE) * ts;
+  double mv = 0.0, ma = 0.0;
+  for (int s = tid; s < C.n_t_reparam; s += TP_LB_THREADS) {
+    const double t = bv.t_reparam[s];
+    if (!(t < duration)) break;
+    const double v = norm3(bspline_at(vq, N - 1, 2, ts, t));
+    const double a = norm3(bspline_at(ar, N - 2, 1, ts, t));
+    mv = fmax(mv, v);
+    ma = fmax(ma, a);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mv = fmax(mv, __shfl_xor_sync(0xffffffffu, mv, o));
+    ma = fmax(ma, __shfl_xor_sync(0xffffffffu, ma, o));
+  }
+  if ((tid & 31) == 0) { redv[tid >> 5] = mv; reda[tid >> 5] = ma; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < TP_LB_WARPS; ++w) { mv = fmax(mv, redv[w]); ma = fmax(ma, reda[w]); }
+    const double fv = C.p.max_vel / mv;
+    const double fa = sqrt(C.p.max_acc / ma);
+    st.linear_factor = fmin(fv, fa);
+  }
+}
+
+// ---- outer loop: one warp (= one block) per worker, trajectories pulled from a queue
+struct PlanSmem {
+  uint8_t hit[TP_MAX_CTRL];
+  uint8_t line[TP_MAX_CTRL];
+  int segA[TP_MAX_SEG_HARD][2];
+  int segB[TP_MAX_SEG_HARD][2];
+};
+__device__ __forceinline__ Worker make_worker(const VigoConst& C, const AStarPools& P, int w, int lane) {
+  Worker W;
+  W.nodes = P.nodes + (size_t)w * (P.pool_nodes + 1);
+  W.heap = P.heaps + (size_t)w * C.heap_cap;
+  W.path = P.paths + (size_t)w * C.path_cap * 3;
+  W.sc = P.sc + (size_t)w * C.max_seg * TP_SC_CAP * 3;
+  W.sc_len = P.sc_len + (size_t)w * C.max_seg;
+  W.round_ptr = P.rounds + w;
+  W.lane = lane;
+  return W;
+}
+
+// makePlan steps 1-3 (bsplineTraj.cpp:341-352)
+__global__ void __launch_bounds__(32) k_plan_init(BatchView bv, VigoConst C, DevMap map, AStarPools P, int* queue,
+                                                  int* active_out, int* n_active_out) {
+  __shared__ PlanSmem S;
+  const int lane = threadIdx.x;
+  Worker W = make_worker(C, P, blockIdx.x, lane);
+  for (;;) {
+    int b = 0;
+    if (lane == 0) b = atomicAdd(queue, 1);
+    b = __shfl_sync(0xffffffffu, b, 0);
+    if (b >= bv.B) break;
+    TrajState& st = bv.st[b];
+    int err = 0;
+    if (st.N < 2 * TP_DEGREE + 1 || st.N > TP_MAX_CTRL) {
+      if (lane == 0) st.status = TP_STATUS_INVALID;
+      continue;
+    }
+    int nseg = find_collision_seg(map, C, bv, st, S.hit, S.line, S.segA, lane, err);
+    const int npaths = path_search(map, C, bv, st, W, S.segA, nseg, err);
+    if (lane == 0) {
+      st.nseg = nseg;
+      for (int i = 0; i < nseg; ++i) { st.seg[i][0] = S.segA[i][0]; st.seg[i][1] = S.segA[i][1]; }
+      if (npaths < 0) {
+        st.status = TP_STATUS_FAIL_ASTAR;
+      } else {
+        assign_guides(map, C, bv, b, st, W, S.segA, nseg, npaths);
+        active_out[atomicAdd(n_active_out, 1)] = b;
+      }
+      st.err |= err;
+    }
+    __syncwarp();
+  }
+}
+
+// body of optimizeTrajectory's loop after the collision check (bsplineTraj.cpp:628-679)
+__global__ void __launch_bounds__(32) k_plan_step(BatchView bv, VigoConst C, DevMap map, AStarPools P, int* queue,
+                                                  const int* __restrict__ active_in, const int* __restrict__ n_active_in,
+                                                  int* active_out, int* n_active_out) {
+  __shared__ PlanSmem S;
+  __shared__ int prevSeg[TP_MAX_SEG_HARD][2];
+  const int lane = threadIdx.x;
+  Worker W = make_worker(C, P, blockIdx.x, lane);
+  const int n_in = *n_active_in;
+  for (;;) {
+    int q = 0;
+    if (lane == 0) q = atomicAdd(queue, 1);
+    q = __shfl_sync(0xffffffffu, q, 0);
+    if (q >= n_in) break;
+    const int b = active_in[q];
+    TrajState& st = bv.st[b];
+    int err = 0;
+    const int hasCol = st.has_col & 1, hasDyn = (st.has_col >> 1) & 1;
+    if (!hasCol && !hasDyn) {  // :628-630 -> :682-684
+      if (lane == 0) {
+        st.w_dist = C.p.w_distance;
+        st.w_dyn = C.p.w_dyn;
+        st.status = TP_STATUS_SUCCESS;
+      }
+      continue;
+    }
+    if (st.round >= C.p.max_outer_rounds) {  // replaces the 0.03 s wall clock (:633)
+      if (lane == 0) {
+        st.w_dist = C.p.w_distance;
+        st.w_dyn = C.p.w_dyn;
+        st.status = TP_STATUS_FAIL_OPTIMIZE;
+      }
+      continue;
+    }
+    const int fail_in = st.fail_count;
+    if (fail_in >= 4) {  // :640-648
+      int nseg = find_collision_seg(map, C, bv, st, S.hit, S.line, S.segA, lane, err);
+      const int np = path_search(map, C, bv, st, W, S.segA, nseg, err);
+      if (np >= 0 && lane == 0) assign_guides(map, C, bv, b, st, W, S.segA, nseg, np);
+      __syncwarp();
+    }
+    if (fail_in >= 8) {  // :650-654
+      if (lane == 0) {
+        st.round += 1;
+        st.w_dist = C.p.w_distance;
+        st.w_dyn = C.p.w_dyn;
+        st.status = TP_STATUS_FAIL_OPTIMIZE;
+        st.err |= err;
+      }
+      continue;
+    }
+    int add_fail = 0;
+    if (hasCol) {
+      // ---- isReguideRequired (:573-608)
+      const int nprev = st.nseg;
+      for (int i = lane; i < nprev; i += 32) { prevSeg[i][0] = st.seg[i][0]; prevSeg[i][1] = st.seg[i][1]; }
+      __syncwarp();
+      const int nnew = find_collision_seg(map, C, bv, st, S.hit, S.line, S.segA, lane, err);
+      int nre = 0;
+      if (lane == 0) {
+        st.nseg = nnew;
+        for (int i = 0; i < nnew; ++i) { st.seg[i][0] = S.segA[i][0]; st.seg[i][1] = S.segA[i][1]; }
+        // compareCollisionSeg (bsplineTraj.h:379-403) + set<int> of segment indices
+        unsigned long long need = 0ull;  // bit i: segment i needs a re-guide (max_seg <= 64)
+        for (int sidx = 0; sidx < nnew; ++sidx) {
+          const int s0 = S.segA[sidx][0], s1 = S.segA[sidx][1];
+          auto visit = [&](int i) {
+            const bool overl = index_in_seg(prevSeg, nprev, i);
+            if (!overl || cp_requires_new_guide(C, bv, b, st, i)) {
+              const int k = find_seg_index(S.segA, nnew, i);
+              if (k >= 0) need |= (1ull << k);
+            }
+          };
+          for (int i = s0 + 1; i <= s1 - 1; ++i) visit(i);
+          if (s1 - s0 - 1 == 0)
+            for (int i = s0; i <= s1; ++i) visit(i);
+        }
+        for (int k = 0; k < nnew; ++k)
+          if ((need >> k) & 1ull) {
+            S.segB[nre][0] = S.segA[k][0];
+            S.segB[nre][1] = S.segA[k][1];
+            ++nre;
+          }
+      }
+      nre = __shfl_sync(0xffffffffu, nre, 0);
+      __syncwarp();
+      if (nre > 0) {
+        int nre2 = nre;
+        const int np = path_search(map, C, bv, st, W, S.segB, nre2, err);
+        if (np >= 0) {
+          if (lane == 0) assign_guides(map, C, bv, b, st, W, S.segB, nre2, np);
+        } else
+          add_fail = 1;
+      } else
+        add_fail = 1;
+    }
+    if (lane == 0) {
+      st.round += 1;
+      if (add_fail) {
+        st.w_dist *= 2.0;
+        st.fail_count += 1;
+      }
+      if (hasDyn) st.w_dyn *= 2.0;
+      st.err |= err;
+      active_out[atomicAdd(n_active_out, 1)] = b;
+    }
+    __syncwarp();
+  }
+}
+
+// standalone A* (parity entry): one warp per (start, end) pair
+__global__ void __launch_bounds__(32) k_astar(VigoConst C, DevMap map, AStarPools P, int* queue, int S_,
+                                              const double* __restrict__ starts, const double* __restrict__ ends,
+                                              int* path_len, double* paths, int* expansions) {
+  const int lane = threadIdx.x;
+  Worker W = make_worker(C, P, blockIdx.x, lane);
+  for (;;) {
+    int s = 0;
+    if (lane == 0) s = atomicAdd(queue, 1);
+    s = __shfl_sync(0xffffffffu, s, 0);
+    if (s >= S_) break;
+    int ex = 0, err = 0;
+    const int len = astar_search(map, C, W, d3(starts[3 * s], starts[3 * s + 1], starts[3 * s + 2]),
+                                 d3(ends[3 * s], ends[3 * s + 1], ends[3 * s + 2]), ex, err);
+    if (lane == 0) {
+      path_len[s] = len;
+      expansions[s] = ex;
+    }
+    if (len > 0)
+      for (int e = lane; e < 3 * len; e += 32) paths[(size_t)s * C.path_cap * 3 + e] = W.path[e];
+    __syncwarp();
+  }
+}
+
+// standalone findCollisionSeg (parity entry)
+__global__ void __launch_bounds__(32) k_find_seg(BatchView bv, VigoConst C, DevMap map, int* nseg_out, int* segs_out) {
+  __shared__ PlanSmem S;
+  const int b = blockIdx.x, lane = threadIdx.x;
+  const TrajState& st = bv.st[b];
+  int err = 0;
+  int n = 0;
+  if (st.N >= 2 * TP_DEGREE + 1 && st.N <= TP_MAX_CTRL) n = find_collision_seg(map, C, bv, st, S.hit, S.line, S.segA, lane, err);
+  if (lane == 0) {
+    nseg_out[b] = n;
+    for (int i = 0; i < n; ++i) {
+      segs_out[((size_t)b * C.max_seg + i) * 2] = S.segA[i][0];
+      segs_out[((size_t)b * C.max_seg + i) * 2 + 1] = S.segA[i][1];
+    }
+  }
+}
+
+__global__ void k_collect_results(BatchView bv, tp_vigo_result* out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= bv.B) return;
+  const TrajState& st = bv.st[b];
+  tp_vigo_result r;
+  r.status = st.status == TS_ACTIVE ? TP_STATUS_FAIL_OPTIMIZE : st.status;
+  if (st.err != 0 && r.status != TP_STATUS_SUCCESS) r.status = TP_STATUS_FAIL_CAPACITY;
+  r.outer_rounds = st.round;
+  r.fail_count = st.fail_count;
+  r.lbfgs_runs = st.lbfgs_runs;
+  r.lbfgs_iters = st.lbfgs_iters;
+  r.lbfgs_evals = st.lbfgs_evals;
+  r.astar_searches = st.astar_searches;
+  r.astar_expansions = st.astar_expansions;
+  r.n_guide_pairs = st.n_pairs;
+  r.last_lbfgs_ret = st.last_ret;
+  r.final_cost = st.final_cost;
+  r.linear_factor = st.linear_factor;
+  out[b] = r;
+}
+
+// =========================================================================== engine
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return TP_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      tp_set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+      return TP_ERR_CUDA;
+    }
+    cap = want;
+    return TP_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() { return (T*)p; }
+};
+
+struct tp_engine {
+  int device = 0;
+  tp_engine_cfg cfg;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  int64_t launches = 0;
+  // map replica
+  bool has_map = false;
+  DevMap dmap;
+  DevBuf map_infl, map_known;
+  double map_res = 0;
+  // tables (depend on params + map res)
+  DevBuf t_check, t_reparam, a_line;
+  int n_t_check = 0, n_t_reparam = 0, n_a_line = 0;
+  double tab_check_ts = -1, tab_ts = -1, tab_res = -1;
+  // A* pools
+  AStarPools pools;
+  DevBuf pool_nodes, pool_heaps, pool_paths, pool_sc, pool_sclen, pool_rounds;
+  int pools_key[8] = {0};
+  // batch buffers
+  DevBuf off, ctrl, st, pairs, cp_head, cp_tail, active[2], counters, results, dyn, scratch_a, scratch_b, scratch_c;
+  int* h_counters = nullptr;  // pinned
+  // pinned staging for host-memory calls
+  void* h_stage = nullptr;
+  size_t h_stage_cap = 0;
+  bool lbfgs_attr_set = false;
+  int max_smem_optin = 0;
+};
+
+static int ensure_stage(tp_engine* e, size_t bytes) {
+  if (bytes <= e->h_stage_cap) return TP_OK;
+  if (e->h_stage) cudaFreeHost(e->h_stage);
+  e->h_stage = nullptr;
+  e->h_stage_cap = 0;
+  size_t want = bytes + bytes / 4 + 4096;
+  cudaError_t er = cudaMallocHost(&e->h_stage, want);
+  if (er != cudaSuccess) {
+    tp_set_error("cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(er));
+    return TP_ERR_CUDA;
+  }
+  e->h_stage_cap = want;
+  return TP_OK;
+}
+
+static void make_const(const tp_engine* e, const tp_vigo_params* p, VigoConst& C) {
+  memset(&C, 0, sizeof(C));
+  C.p = *p;
+  const double dth = p->dthresh;
+  C.dist_a = 3.0 * dth;                       // bsplineTraj.cpp:835
+  C.dist_b = -3.0 * (dth * dth);
+  C.dist_c = std::pow(dth, 3);
+  const double hth = 0.2;                     // :836-837
+  C.h_a = 3.0 * hth;
+  C.h_b = -3 * (hth * hth);
+  C.h_c = std::pow(hth, 3);
+  const double dd = p->dthresh_dyn;           // :1009
+  C.dyn_a = 3.0 * dd;
+  C.dyn_b = -3 * (dd * dd);
+  C.dyn_c = std::pow(dd, 3);
+  C.ts_inv_sqr = 1 / (p->ctrl_pt_ts * p->ctrl_pt_ts);  // :959
+  C.check_ts = e->map_res / p->max_vel / 2.0;           // bsplineTraj.h:312
+  C.pred_num = (int)(p->pred_horizon / p->ts);          // bsplineTraj.cpp:1007
+  for (int a = 0; a < 3; ++a) C.pool[a] = 2 * (int)(p->max_obstacle_size[a] / e->map_res);  // :191-193
+  int kl = (int)((p->max_height - p->min_height) / e->map_res) + 3;
+  if (kl > C.pool[2]) kl = C.pool[2];
+  if (kl < 1) kl = 1;
+  C.pool_kl = kl;
+  C.max_seg = e->cfg.max_segments;
+  C.gcap = e->cfg.max_guide_pairs;
+  C.path_cap = e->cfg.max_path_cells;
+  size_t pool_nodes = (size_t)C.pool[0] * C.pool[1] * C.pool_kl;
+  size_t hc = e->cfg.astar_heap_cap > 0 ? (size_t)e->cfg.astar_heap_cap : std::min(pool_nodes + 1, (size_t)1 << 20);
+  C.heap_cap = (int)hc;
+}
+
+// sample-time tables: the reference accumulates t += dt in FP64; reproduce the same sums once
+static int ensure_tables(tp_engine* e, VigoConst& C) {
+  const int max_n = TP_MAX_CTRL;
+  const double max_dur = (double)(max_n - TP_DEGREE) * C.p.ctrl_pt_ts;
+  if (e->tab_check_ts != C.check_ts) {
+    std::vector<double> t;
+    for (double x = 0; x <= max_dur; x += C.check_ts) {
+      t.push_back(x);
+      if (t.size() > (size_t)4000000) break;
+    }
+    if (e->t_check.ensure(t.size() * 8) != TP_OK) return TP_ERR_CUDA;
+    CK(cudaMemcpyAsync(e->t_check.p, t.data(), t.size() * 8, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->n_t_check = (int)t.size();
+    e->tab_check_ts = C.check_ts;
+  }
+  if (e->tab_ts != C.p.ts) {
+    std::vector<double> t;
+    for (double x = 0.0; x < max_dur; x += C.p.ts) {
+      t.push_back(x);
+      if (t.size() > (size_t)4000000) break;
+    }
+    if (e->t_reparam.ensure(t.size() * 8) != TP_OK) return TP_ERR_CUDA;
+    CK(cudaMemcpyAsync(e->t_reparam.p, t.data(), t.size() * 8, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->n_t_reparam = (int)t.size();
+    e->tab_ts = C.p.ts;
+  }
+  if (e->tab_res != e->map_res) {
+    std::vector<double> t;
+    for (double a = 0.0; a <= 1.0; a += e->map_res) {  // bsplineTraj.h:197
+      t.push_back(a);
+      if (t.size() > (size_t)100000) break;
+    }
+    if (e->a_line.ensure(t.size() * 8) != TP_OK) return TP_ERR_CUDA;
+    CK(cudaMemcpyAsync(e->a_line.p, t.data(), t.size() * 8, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->n_a_line = (int)t.size();
+    e->tab_res = e->map_res;
+  }
+  C.n_t_check = e->n_t_check;
+  C.n_t_reparam = e->n_t_reparam;
+  C.n_a_line = e->n_a_line;
+  return TP_OK;
+}
+
+static int ensure_pools(tp_engine* e, const VigoConst& C) {
+  const int key[8] = {C.pool[0], C.pool[1], C.pool_kl, C.heap_cap, C.path_cap, C.max_seg, 0, 0};
+  if (memcmp(key, e->pools_key, sizeof(key)) == 0 && e->pools.workers > 0) return TP_OK;
+  const size_t pool_nodes = (size_t)C.pool[0] * C.pool[1] * C.pool_kl;
+  const size_t per_worker = (pool_nodes + 1) * sizeof(ANode) + (size_t)C.heap_cap * 4 + (size_t)C.path_cap * 24 +
+                            (size_t)C.max_seg * TP_SC_CAP * 24 + (size_t)C.max_seg * 4 + 4;
+  int workers = e->cfg.astar_workers;
+  if (workers <= 0) {
+    const double budget = e->cfg.astar_mem_gb * 1e9;
+    size_t freeb = 0, totalb = 0;
+    cudaMemGetInfo(&freeb, &totalb);
+    double use = std::min(budget, 0.5 * (double)freeb);
+    workers = (int)std::min<double>(use / (double)per_worker, (double)e->sm_count * 32);
+    workers = (workers / e->sm_count) * e->sm_count;
+    if (workers < e->sm_count) workers = std::max(1, (int)(use / (double)per_worker));
+  }
+  if (workers < 1) workers = 1;
+  if (e->pool_nodes.ensure((size_t)workers * (pool_nodes + 1) * sizeof(ANode)) != TP_OK) return TP_ERR_CUDA;
+  if (e->pool_heaps.ensure((size_t)workers * C.heap_cap * 4) != TP_OK) return TP_ERR_CUDA;
+  if (e->pool_paths.ensure((size_t)workers * C.path_cap * 24) != TP_OK) return TP_ERR_CUDA;
+  if (e->pool_sc.ensure((size_t)workers * C.max_seg * TP_SC_CAP * 24) != TP_OK) return TP_ERR_CUDA;
+  if (e->pool_sclen.ensure((size_t)workers * C.max_seg * 4) != TP_OK) return TP_ERR_CUDA;
+  if (e->pool_rounds.ensure((size_t)workers * 4) != TP_OK) return TP_ERR_CUDA;
+  CK(cudaMemsetAsync(e->pool_nodes.p, 0, (size_t)workers * (pool_nodes + 1) * sizeof(ANode), e->stream));
+  CK(cudaMemsetAsync(e->pool_rounds.p, 0, (size_t)workers * 4, e->stream));
+  e->pools.nodes = e->pool_nodes.as<ANode>();
+  e->pools.heaps = e->pool_heaps.as<uint32_t>();
+  e->pools.paths = e->pool_paths.as<double>();
+  e->pools.sc = e->pool_sc.as<double>();
+  e->pools.sc_len = e->pool_sclen.as<int>();
+  e->pools.rounds = e->pool_rounds.as<uint32_t>();
+  e->pools.pool_nodes = pool_nodes;
+  e->pools.workers = workers;
+  memcpy(e->pools_key, key, sizeof(key));
+  return TP_OK;
+}
+
+static int check_params(const tp_engine* e, const tp_vigo_params* p) {
+  if (!e || !p) { tp_set_error("null engine/params"); return TP_ERR_INVALID_ARG; }
+  if (!e->has_map) { tp_set_error("engine has no map: call tp_engine_set_map first"); return TP_ERR_NO_MAP; }
+  if (p->lbfgs_m < 1 || p->lbfgs_m > 64 || !(p->ctrl_pt_ts > 0) || !(p->max_vel > 0) || !(p->ts > 0) ||
+      p->lbfgs_max_linesearch < 1) {
+    tp_set_error("invalid ViGO parameters");
+    return TP_ERR_INVALID_ARG;
+  }
+  return TP_OK;
+}
+
+// Batch set-up shared by all ViGO entry points: offsets/ctrl on the device, states initialised.
+struct BatchSetup {
+  BatchView bv;
+  VigoConst C;
+  int max_n = 0;
+  long total = 0;
+  std::vector<int> h_off;
+};
+
+static int setup_batch(tp_engine* e, const tp_vigo_params* p, int B, const int32_t* offsets, const double* ctrl, int mem,
+                       cudaStream_t s, BatchSetup& bs, bool need_guides) {
+  int rc = check_params(e, p);
+  if (rc != TP_OK) return rc;
+  if (B <= 0 || !offsets || !ctrl) { tp_set_error("empty batch or null pointers"); return TP_ERR_INVALID_ARG; }
+  make_const(e, p, bs.C);
+  rc = ensure_tables(e, bs.C);
+  if (rc != TP_OK) return rc;
+  bs.h_off.resize(B + 1);
+  if (mem == TP_MEM_DEVICE) {
+    CK(cudaMemcpyAsync(bs.h_off.data(), offsets, (size_t)(B + 1) * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  } else
+    memcpy(bs.h_off.data(), offsets, (size_t)(B + 1) * 4);
+  bs.max_n = 0;
+  for (int b = 0; b < B; ++b) {
+    const int n = bs.h_off[b + 1] - bs.h_off[b];
+    if (n < 0) { tp_set_error("offsets must be non-decreasing"); return TP_ERR_INVALID_ARG; }
+    if (n > TP_MAX_CTRL) { tp_set_error("trajectory %d has %d control points (max %d)", b, n, TP_MAX_CTRL); return TP_ERR_CAPACITY; }
+    bs.max_n = std::max(bs.max_n, n);
+  }
+  bs.total = bs.h_off[B];
+  const size_t tot = (size_t)std::max<long>(bs.total, 1);
+  if (e->off.ensure((size_t)(B + 1) * 4) != TP_OK || e->st.ensure((size_t)B * sizeof(TrajState)) != TP_OK ||
+      e->cp_head.ensure(tot * 4) != TP_OK || e->cp_tail.ensure(tot * 4) != TP_OK ||
+      e->pairs.ensure((size_t)B * bs.C.gcap * sizeof(GuidePair)) != TP_OK || e->counters.ensure(64 * 4) != TP_OK ||
+      e->active[0].ensure((size_t)B * 4) != TP_OK || e->active[1].ensure((size_t)B * 4) != TP_OK)
+    return TP_ERR_CUDA;
+  BatchView& bv = bs.bv;
+  memset(&bv, 0, sizeof(bv));
+  bv.B = B;
+  bv.total_pts = (int)bs.total;
+  if (mem == TP_MEM_DEVICE) {
+    bv.off = offsets;
+    bv.ctrl = const_cast<double*>(ctrl);
+  } else {
+    if (e->ctrl.ensure(tot * 24) != TP_OK) return TP_ERR_CUDA;
+    CK(cudaMemcpyAsync(e->off.p, offsets, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(e->ctrl.p, ctrl, (size_t)bs.total * 24, cudaMemcpyHostToDevice, s));
+    bv.off = e->off.as<int>();
+    bv.ctrl = e->ctrl.as<double>();
+  }
+  bv.st = e->st.as<TrajState>();
+  bv.pairs = e->pairs.as<GuidePair>();
+  bv.cp_head = e->cp_head.as<int>();
+  bv.cp_tail = e->cp_tail.as<int>();
+  bv.t_check = e->t_check.as<double>();
+  bv.t_reparam = e->t_reparam.as<double>();
+  bv.a_line = e->a_line.as<double>();
+  k_init_states<<<(B + 127) / 128, 128, 0, s>>>(bv, bs.C);
+  k_fill_int<<<std::min<long>((long)(tot + 255) / 256, 1184), 256, 0, s>>>(bv.cp_head, (long)tot, -1);
+  k_fill_int<<<std::min<long>((long)(tot + 255) / 256, 1184), 256, 0, s>>>(bv.cp_tail, (long)tot, -1);
+  e->launches += 3;
+  (void)need_guides;
+  return TP_OK;
+}
+
+// flat guide list (host memory) -> device linked lists; optional per-trajectory weights
+static int upload_guides(tp_engine* e, BatchSetup& bs, const int32_t* g_offsets, const int32_t* g_cp, const double* g_p,
+                         const double* g_v, const double* w_override, cudaStream_t s) {
+  const int B = bs.bv.B;
+  const int gcap = bs.C.gcap;
+  std::vector<TrajState> hst((size_t)B);
+  CK(cudaMemcpyAsync(hst.data(), bs.bv.st, (size_t)B * sizeof(TrajState), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  std::vector<int> head((size_t)std::max<long>(bs.total, 1), -1), tail(head.size(), -1);
+  std::vector<GuidePair> pairs((size_t)B * gcap);
+  memset(pairs.data(), 0, pairs.size() * sizeof(GuidePair));
+  const tp_map* hm = nullptr;
+  (void)hm;
+  for (int b = 0; b < B; ++b) {
+    if (w_override) {
+      hst[b].w_dist = w_override[2 * b];
+      hst[b].w_dyn = w_override[2 * b + 1];
+    }
+    if (!g_offsets) continue;
+    const int g0 = g_offsets[b], g1 = g_offsets[b + 1];
+    if (g1 - g0 > gcap) { tp_set_error("trajectory %d has %d guide pairs (engine max_guide_pairs %d)", b, g1 - g0, gcap); return TP_ERR_CAPACITY; }
+    for (int g = g0; g < g1; ++g) {
+      const int gi = g - g0;
+      GuidePair& pr = pairs[(size_t)b * gcap + gi];
+      for (int a = 0; a < 3; ++a) { pr.p[a] = g_p[3 * g + a]; pr.v[a] = g_v[3 * g + a]; }
+      pr.next = -1;
+      pr.unknown = -1;  // resolved on the device below
+      const int c = g_cp[g];
+      if (c < 0 || c >= hst[b].N) { tp_set_error("guide pair %d: control point %d out of range", g, c); return TP_ERR_INVALID_ARG; }
+      const int ci = hst[b].off + c;
+      if (tail[ci] < 0) head[ci] = gi; else pairs[(size_t)b * gcap + tail[ci]].next = gi;
+      tail[ci] = gi;
+    }
+    hst[b].n_pairs = g1 - g0;
+  }
+  CK(cudaMemcpyAsync(bs.bv.st, hst.data(), (size_t)B * sizeof(TrajState), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(bs.bv.cp_head, head.data(), head.size() * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(bs.bv.cp_tail, tail.data(), tail.size() * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(bs.bv.pairs, pairs.data(), pairs.size() * sizeof(GuidePair), cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(s));
+  return TP_OK;
+}
+
+__global__ void k_resolve_unknown(BatchView bv, VigoConst C, DevMap map) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= (long)bv.B * C.gcap) return;
+  const int b = (int)(i / C.gcap), gi = (int)(i % C.gcap);
+  if (gi >= bv.st[b].n_pairs) return;
+  GuidePair& pr = bv.pairs[i];
+  pr.unknown = dm_unknown(map, d3(pr.p[0], pr.p[1], pr.p[2])) ? 1 : 0;
+}
+
+static int set_lbfgs_smem(tp_engine* e, size_t bytes) {
+  if ((int)bytes > e->max_smem_optin) {
+    tp_set_error("L-BFGS state needs %zu B of shared memory (> %d B per block)", bytes, e->max_smem_optin);
+    return TP_ERR_CAPACITY;
+  }
+  if (!e->lbfgs_attr_set) {
+    CK(cudaFuncSetAttribute(k_lbfgs<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
+    CK(cudaFuncSetAttribute(k_lbfgs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
+    CK(cudaFuncSetAttribute(k_cost<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
+    CK(cudaFuncSetAttribute(k_cost<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
+    e->lbfgs_attr_set = true;
+  }
+  return TP_OK;
+}
+
+// =========================================================================== C ABI
+extern "C" {
+
+int tp_version(void) { return 100; }
+int tp_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+void tp_engine_default_cfg(tp_engine_cfg* c) {
+  memset(c, 0, sizeof(*c));
+  c->astar_workers = 0;
+  c->max_segments = 32;
+  c->max_guide_pairs = 256;
+  c->astar_heap_cap = 0;
+  c->max_path_cells = 4096;
+  c->lbfgs_threads = TP_LB_THREADS;
+  c->astar_mem_gb = 48.0;
+}
+void tp_vigo_default_params(tp_vigo_params* p) {
+  // cfg/bspline_interactive/bspline_planner_param.yaml + desired_velocity/acceleration
+  // (src/bspline_node.cpp:210-211,230-231)
+  memset(p, 0, sizeof(*p));
+  p->ts = 0.1; p->dthresh = 0.5; p->max_vel = 2.0; p->max_acc = 3.0;
+  p->w_distance = 1.0; p->w_smooth = 1.0; p->w_feas = 1.0; p->w_dyn = 1.0;
+  p->min_height = 0.7; p->max_height = 1.3; p->uncertain_factor = 1.0;
+  p->pred_horizon = 2.0; p->dthresh_dyn = 0.5; p->max_path_length = 20.0;
+  p->max_obstacle_size[0] = 5; p->max_obstacle_size[1] = 5; p->max_obstacle_size[2] = 3;
+  p->ctrl_pt_dist = 0.25; p->ctrl_pt_ts = 0.2; p->not_check_ratio = 0.0;
+  p->lbfgs_g_eps = 0.01; p->plan_in_z = 0; p->lbfgs_m = 16; p->lbfgs_max_iter = 200;
+  p->lbfgs_max_linesearch = 40; p->max_outer_rounds = 24; p->astar_max_expansions = 200000;
+  p->strict_order = 0;
+}
+
+tp_engine_t* tp_engine_create(int device, const tp_engine_cfg* cfg) {
+  int n = 0;
+  cudaError_t er = cudaGetDeviceCount(&n);
+  if (er != cudaSuccess || n <= 0) {
+    tp_set_error("no CUDA device available (%s); this engine has no CPU fallback",
+                 er != cudaSuccess ? cudaGetErrorString(er) : "device count 0");
+    return nullptr;
+  }
+  if (device < 0 || device >= n) {
+    tp_set_error("device %d out of range (count %d)", device, n);
+    return nullptr;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) {
+    tp_set_error("cudaSetDevice(%d) failed", device);
+    return nullptr;
+  }
+  tp_engine* e = new tp_engine();
+  e->device = device;
+  if (cfg) e->cfg = *cfg; else tp_engine_default_cfg(&e->cfg);
+  if (e->cfg.max_segments <= 0) e->cfg.max_segments = 32;
+  if (e->cfg.max_segments > TP_MAX_SEG_HARD) e->cfg.max_segments = TP_MAX_SEG_HARD;
+  if (e->cfg.max_guide_pairs <= 0) e->cfg.max_guide_pairs = 256;
+  if (e->cfg.max_path_cells <= 0) e->cfg.max_path_cells = 4096;
+  if (!(e->cfg.astar_mem_gb > 0)) e->cfg.astar_mem_gb = 48.0;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMallocHost((void**)&e->h_counters, 64 * sizeof(int)) != cudaSuccess) {
+    tp_set_error("engine initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    delete e;
+    return nullptr;
+  }
+  e->sm_count = prop.multiProcessorCount;
+  e->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  memset(&e->pools, 0, sizeof(e->pools));
+  return e;
+}
+void tp_engine_destroy(tp_engine_t* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  DevBuf* bufs[] = {&e->map_infl, &e->map_known, &e->t_check, &e->t_reparam, &e->a_line, &e->pool_nodes, &e->pool_heaps,
+                    &e->pool_paths, &e->pool_sc, &e->pool_sclen, &e->pool_rounds, &e->off, &e->ctrl, &e->st, &e->pairs,
+                    &e->cp_head, &e->cp_tail, &e->active[0], &e->active[1], &e->counters, &e->results, &e->dyn,
+                    &e->scratch_a, &e->scratch_b, &e->scratch_c};
+  for (DevBuf* b : bufs) b->release();
+  if (e->h_counters) cudaFreeHost(e->h_counters);
+  if (e->h_stage) cudaFreeHost(e->h_stage);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+int tp_engine_set_map(tp_engine_t* e, const tp_map_t* m) {
+  if (!e || !m) return TP_ERR_INVALID_ARG;
+  CK(cudaSetDevice(e->device));
+  std::vector<uint32_t> wi, wk;
+  m->pack(2, wi);
+  m->pack(1, wk);
+  if (e->map_infl.ensure(wi.size() * 4) != TP_OK || e->map_known.ensure(wk.size() * 4) != TP_OK) return TP_ERR_CUDA;
+  CK(cudaMemcpy(e->map_infl.p, wi.data(), wi.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e->map_known.p, wk.data(), wk.size() * 4, cudaMemcpyHostToDevice));
+  e->dmap.inflated = e->map_infl.as<uint32_t>();
+  e->dmap.known = e->map_known.as<uint32_t>();
+  e->dmap.res = m->res;
+  for (int a = 0; a < 3; ++a) { e->dmap.mn[a] = m->origin[a]; e->dmap.dim[a] = m->dims[a]; }
+  e->dmap.wz = m->wz();
+  e->map_res = m->res;
+  e->has_map = true;
+  return TP_OK;
+}
+int tp_engine_synchronize(tp_engine_t* e) {
+  if (!e) return TP_ERR_INVALID_ARG;
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  return TP_OK;
+}
+int64_t tp_engine_launch_count(const tp_engine_t* e) { return e ? e->launches : 0; }
+void* tp_engine_stream(tp_engine_t* e) { return e ? (void*)e->stream : nullptr; }
+
+static cudaStream_t pick_stream(tp_engine* e, void* s) { return s ? (cudaStream_t)s : e->stream; }
+
+static int query_common(tp_engine_t* e, int64_t n, const double* a, const double* b, uint8_t* out, int mem, void* stream,
+                        int kind) {
+  if (!e) return TP_ERR_INVALID_ARG;
+  if (!e->has_map) { tp_set_error("engine has no map"); return TP_ERR_NO_MAP; }
+  if (n < 0 || (n > 0 && (!a || !out))) return TP_ERR_INVALID_ARG;
+  if (n == 0) return TP_OK;
+  CK(cudaSetDevice(e->device));
+  cudaStream_t s = pick_stream(e, stream);
+  const double* da = a;
+  const double* db = b;
+  uint8_t* dout = out;
+  if (mem == TP_MEM_HOST) {
+    if (e->scratch_a.ensure((size_t)n * 24) != TP_OK || e->scratch_c.ensure((size_t)n) != TP_OK) return TP_ERR_CUDA;
+    CK(cudaMemcpyAsync(e->scratch_a.p, a, (size_t)n * 24, cudaMemcpyHostToDevice, s));
+    da = e->scratch_a.as<double>();
+    if (kind == 2) {
+      if (e->scratch_b.ensure((size_t)n * 24) != TP_OK) return TP_ERR_CUDA;
+      CK(cudaMemcpyAsync(e->scratch_b.p, b, (size_t)n * 24, cudaMemcpyHostToDevice, s));
+      db = e->scratch_b.as<double>();
+    }
+    dout = e->scratch_c.as<uint8_t>();
+  }
+  const int threads = 256;
+  const long blocks = std::min<long>((n + threads - 1) / threads, (long)e->sm_count * 8);
+  if (kind == 2) k_query_lines<<<(int)blocks, threads, 0, s>>>(e->dmap, (long)n, da, db, dout);
+  else k_query_points<<<(int)blocks, threads, 0, s>>>(e->dmap, (long)n, da, dout, kind);
+  e->launches += 1;
+  CK(cudaGetLastError());
+  if (mem == TP_MEM_HOST) {
+    CK(cudaMemcpyAsync(out, dout, (size_t)n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  return TP_OK;
+}
+int tp_query_points(tp_engine_t* e, int64_t n, const double* xyz, uint8_t* hit, int mem, void* stream) {
+  return query_common(e, n, xyz, nullptr, hit, mem, stream, 0);
+}
+int tp_query_unknown(tp_engine_t* e, int64_t n, const double* xyz, uint8_t* unknown, int mem, void* stream) {
+  return query_common(e, n, xyz, nullptr, unknown, mem, stream, 1);
+}
+int tp_query_lines(tp_engine_t* e, int64_t n, const double* a, const double* b, uint8_t* hit, int mem, void* stream) {
+  if (n > 0 && !b) return TP_ERR_INVALID_ARG;
+  return query_common(e, n, a, b, hit, mem, stream, 2);
+}
+
+// identity active list + its count in counters[0]
+static int make_identity_active(tp_engine* e, int B, cudaStream_t s) {
+  k_iota<<<(B + 255) / 256, 256, 0, s>>>(e->active[0].as<int>(), B);
+  e->launches += 1;
+  e->h_counters[0] = B;
+  CK(cudaMemcpyAsync(e->counters.p, e->h_counters, 4, cudaMemcpyHostToDevice, s));
+  return TP_OK;
+}
+
+int tp_vigo_cost_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, const int32_t* offsets, const double* ctrl,
+                       const int32_t* g_offsets, const int32_t* g_cp, const double* g_p, const double* g_v,
+                       const double* w_override, double* f, double* grad, int mem, void* stream) {
+  if (mem != TP_MEM_HOST) { tp_set_error("tp_vigo_cost_batch: host memory only"); return TP_ERR_INVALID_ARG; }
+  if (!e || !f || !grad) return TP_ERR_INVALID_ARG;
+  CK(cudaSetDevice(e->device));
+  cudaStream_t s = pick_stream(e, stream);
+  BatchSetup bs;
+  int rc = setup_batch(e, p, B, offsets, ctrl, mem, s, bs, true);
+  if (rc != TP_OK) return rc;
+  rc = upload_guides(e, bs, g_offsets, g_cp, g_p, g_v, w_override, s);
+  if (rc != TP_OK) return rc;
+  k_resolve_unknown<<<(int)(((long)B * bs.C.gcap + 255) / 256), 256, 0, s>>>(bs.bv, bs.C, e->dmap);
+  const size_t nvar = (size_t)std::max<long>(3 * (bs.total - 6L * B), 1);
+  if (e->scratch_a.ensure((size_t)B * 8) != TP_OK || e->scratch_b.ensure(nvar * 8) != TP_OK) return TP_ERR_CUDA;
+  const size_t smem = ((size_t)3 * bs.max_n + 3 * (size_t)bs.max_n + 40) * 8;
+  rc = set_lbfgs_smem(e, smem);
+  if (rc != TP_OK) return rc;
+  if (p->strict_order) k_cost<true><<<B, TP_LB_THREADS, smem, s>>>(bs.bv, bs.C, e->scratch_a.as<double>(), e->scratch_b.as<double>());
+  else k_cost<false><<<B, TP_LB_THREADS, smem, s>>>(bs.bv, bs.C, e->scratch_a.as<double>(), e->scratch_b.as<double>());
+  e->launches += 2;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(f, e->scratch_a.p, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
+  // ragged gradient: trajectory b's slice starts at 3*(off[b] - 6b); trajectories with N < 7 own nothing
+  CK(cudaMemcpyAsync(grad, e->scratch_b.p, nvar * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return TP_OK;
+}
+
+int tp_vigo_optimize_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, const int32_t* offsets, double* ctrl,
+                           const int32_t* g_offsets, const int32_t* g_cp, const double* g_p, const double* g_v,
+                           const double* w_override, tp_lbfgs_result* res, double* x_final, int mem, void* stream) {
+  if (mem != TP_MEM_HOST) { tp_set_error("tp_vigo_optimize_batch: host memory only"); return TP_ERR_INVALID_ARG; }
+  if (!e) return TP_ERR_INVALID_ARG;
+  CK(cudaSetDevice(e->device));
+  cudaStream_t s = pick_stream(e, stream);
+  BatchSetup bs;
+  int rc = setup_batch(e, p, B, offsets, ctrl, mem, s, bs, true);
+  if (rc != TP_OK) return rc;
+  rc = upload_guides(e, bs, g_offsets, g_cp, g_p, g_v, w_override, s);
+  if (rc != TP_OK) return rc;
+  k_resolve_unknown<<<(int)(((long)B * bs.C.gcap + 255) / 256), 256, 0, s>>>(bs.bv, bs.C, e->dmap);
+  const size_t nvar = (size_t)std::max<long>(3 * (bs.total - 6L * B), 1);
+  if (e->results.ensure((size_t)B * sizeof(tp_lbfgs_result)) != TP_OK || e->scratch_b.ensure(nvar * 8) != TP_OK) return TP_ERR_CUDA;
+  CK(cudaMemsetAsync(e->results.p, 0, (size_t)B * sizeof(tp_lbfgs_result), s));
+  const size_t smem = lbfgs_smem_doubles(bs.max_n, p->lbfgs_m) * 8;
+  rc = set_lbfgs_smem(e, smem);
+  if (rc != TP_OK) return rc;
+  rc = make_identity_active(e, B, s);
+  if (rc != TP_OK) return rc;
+  if (p->strict_order)
+    k_lbfgs<true><<<B, TP_LB_THREADS, smem, s>>>(bs.bv, bs.C, e->active[0].as<int>(), e->counters.as<int>(),
+                                                  e->results.as<tp_lbfgs_result>(), x_final ? e->scratch_b.as<double>() : nullptr);
+  else
+    k_lbfgs<false><<<B, TP_LB_THREADS, smem, s>>>(bs.bv, bs.C, e->active[0].as<int>(), e->counters.as<int>(),
+                                                   e->results.as<tp_lbfgs_result>(), x_final ? e->scratch_b.as<double>() : nullptr);
+  e->launches += 2;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(ctrl, bs.bv.ctrl, (size_t)bs.total * 24, cudaMemcpyDeviceToHost, s));
+  if (res) CK(cudaMemcpyAsync(res, e->results.p, (size_t)B * sizeof(tp_lbfgs_result), cudaMemcpyDeviceToHost, s));
+  if (x_final) CK(cudaMemcpyAsync(x_final, e->scratch_b.p, nvar * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return TP_OK;
+}
+
+int tp_vigo_has_collision_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, const int32_t* offsets,
+                                const double* ctrl, uint8_t* hit, int mem, void* stream) {
+  if (mem != TP_MEM_HOST) { tp_set_error("tp_vigo_has_collision_batch: host memory only"); return TP_ERR_INVALID_ARG; }
+  if (!e || !hit) return TP_ERR_INVALID_ARG;
+  CK(cudaSetDevice(e->device));
+  cudaStream_t s = pick_stream(e, stream);
+  BatchSetup bs;
+  int rc = setup_batch(e, p, B, offsets, ctrl, mem, s, bs, false);
+  if (rc != TP_OK) return rc;
+  if (e->scratch_c.ensure((size_t)B) != TP_OK) return TP_ERR_CUDA;
+  CK(cudaMemsetAsync(e->scratch_c.p, 0, (size_t)B, s));
+  rc = make_identity_active(e, B, s);
+  if (rc != TP_OK) return rc;
+  k_has_collision<<<B, TP_LB_THREADS, (size_t)3 * bs.max_n * 8, s>>>(bs.bv, bs.C, e->dmap, e->active[0].as<int>(),
+                                                                      e->counters.as<int>(), e->scratch_c.as<uint8_t>());
+  e->launches += 1;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(hit, e->scratch_c.p, (size_t)B, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return TP_OK;
+}
+
+int tp_vigo_find_collision_seg_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, const int32_t* offsets,
+                                     const double* ctrl, int32_t* nseg, int32_t* segs, int mem, void* stream) {
+  if (mem != TP_MEM_HOST) { tp_set_error("tp_vigo_find_collision_seg_batch: host memory only"); return TP_ERR_INVALID_ARG; }
+  if (!e || !nseg || !segs) return TP_ERR_INVALID_ARG;
+  CK(cudaSetDevice(e->device));
+  cudaStream_t s = pick_stream(e, stream);
+  BatchSetup bs;
+  int rc = setup_batch(e, p, B, offsets, ctrl, mem, s, bs, false);
+  if (rc != TP_OK) return rc;
+  const size_t nsegs = (size_t)B * bs.C.max_seg * 2;
+  if (e->scratch_a.ensure((size_t)B * 4) != TP_OK || e->scratch_b.ensure(nsegs * 4) != TP_OK) return TP_ERR_CUDA;
+  CK(cudaMemsetAsync(e->scratch_b.p, 0, nsegs * 4, s));
+  k_find_seg<<<B, 32, 0, s>>>(bs.bv, bs.C, e->dmap, e->scratch_a.as<int>(), e->scratch_b.as<int>());
+  e->launches += 1;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(nseg, e->scratch_a.p, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(segs, e->scratch_b.p, nsegs * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return TP_OK;
+}
+
+int tp_astar_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t S, const double* starts, const double* ends,
+                   int32_t* path_len, double* paths, int32_t* expansions, int mem, void* stream) {
+  if (mem != TP_MEM_HOST) { tp_set_error("tp_astar_batch: host memory only"); return TP_ERR_INVALID_ARG; }
+  int rc = check_params(e, p);
+  if (rc != TP_OK) return rc;
+  if (S <= 0 || !starts || !ends || !path_len || !paths || !expansions) return TP_ERR_INVALID_ARG;
+  CK(cudaSetDevice(e->device));
+  cudaStream_t s = pick_stream(e, stream);
+  VigoConst C;
+  make_const(e, p, C);
+  rc = ensure_tables(e, C);
+  if (rc != TP_OK) return rc;
+  rc = ensure_pools(e, C);
+  if (rc != TP_OK) return rc;
+  const size_t pbytes = (size_t)S * C.path_cap * 24;
+  if (e->scratch_a.ensure((size_t)S * 48) != TP_OK || e->scratch_b.ensure(pbytes) != TP_OK ||
+      e->scratch_c.ensure((size_t)S * 8) != TP_OK || e->counters.ensure(64 * 4) != TP_OK)
+    return TP_ERR_CUDA;
+  double* dS = e->scratch_a.as<double>();
+  double* dE = dS + 3 * (size_t)S;
+  CK(cudaMemcpyAsync(dS, starts, (size_t)S * 24, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(dE, ends, (size_t)S * 24, cudaMemcpyHostToDevice, s));
+  CK(cudaMemsetAsync(e->counters.p, 0, 64 * 4, s));
+  int* dlen = e->scratch_c.as<int>();
+  int* dexp = dlen + S;
+  const int grid = std::min(e->pools.workers, S);
+  k_astar<<<grid, 32, 0, s>>>(C, e->dmap, e->pools, e->counters.as<int>(), S, dS, dE, dlen, e->scratch_b.as<double>(), dexp);
+  e->launches += 1;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(path_len, dlen, (size_t)S * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(expansions, dexp, (size_t)S * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(paths, e->scratch_b.p, pbytes, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return TP_OK;
+}
+
+// shared by init_guides and make_plan: makePlan steps 1-3 on the whole batch
+static int run_plan_init(tp_engine* e, BatchSetup& bs, cudaStream_t s) {
+  int rc = ensure_pools(e, bs.C);
+  if (rc != TP_OK) return rc;
+  CK(cudaMemsetAsync(e->counters.p, 0, 64 * 4, s));
+  int* cnt = e->counters.as<int>();
+  const int grid = std::min(e->pools.workers, bs.bv.B);
+  k_plan_init<<<grid, 32, 0, s>>>(bs.bv, bs.C, e->dmap, e->pools, cnt + 1, e->active[0].as<int>(), cnt + 0);
+  e->launches += 1;
+  CK(cudaGetLastError());
+  return TP_OK;
+}
+
+int tp_vigo_init_guides_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, const int32_t* offsets,
+                              const double* ctrl, uint8_t* ok, int32_t* nseg, int32_t* segs, int32_t* g_count,
+                              int32_t* g_cp, double* g_p, double* g_v) {
+  if (!e || !ok || !nseg || !segs || !g_count || !g_cp || !g_p || !g_v) return TP_ERR_INVALID_ARG;
+  CK(cudaSetDevice(e->device));
+  cudaStream_t s = e->stream;
+  BatchSetup bs;
+  int rc = setup_batch(e, p, B, offsets, ctrl, TP_MEM_HOST, s, bs, true);
+  if (rc != TP_OK) return rc;
+  rc = run_plan_init(e, bs, s);
+  if (rc != TP_OK) return rc;
+  const int gcap = bs.C.gcap;
+  std::vector<TrajState> hst((size_t)B);
+  std::vector<GuidePair> pairs((size_t)B * gcap);
+  std::vector<int> head((size_t)std::max<long>(bs.total, 1));
+  CK(cudaMemcpyAsync(hst.data(), bs.bv.st, (size_t)B * sizeof(TrajState), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(pairs.data(), bs.bv.pairs, pairs.size() * sizeof(GuidePair), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(head.data(), bs.bv.cp_head, head.size() * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  for (int b = 0; b < B; ++b) {
+    const TrajState& st = hst[b];
+    ok[b] = st.status == TS_ACTIVE ? 1 : 0;
+    nseg[b] = st.nseg;
+    for (int i = 0; i < bs.C.max_seg; ++i) {
+      segs[((size_t)b * bs.C.max_seg + i) * 2] = i < st.nseg ? st.seg[i][0] : 0;
+      segs[((size_t)b * bs.C.max_seg + i) * 2 + 1] = i < st.nseg ? st.seg[i][1] : 0;
+    }
+    // flat list ordered by control point, append order within a control point
+    int w = 0;
+    for (int c = 0; c < st.N; ++c)
+      for (int gi = head[st.off + c]; gi >= 0; gi = pairs[(size_t)b * gcap + gi].next) {
+        const GuidePair& pr = pairs[(size_t)b * gcap + gi];
+        g_cp[(size_t)b * gcap + w] = c;
+        for (int a = 0; a < 3; ++a) {
+          g_p[((size_t)b * gcap + w) * 3 + a] = pr.p[a];
+          g_v[((size_t)b * gcap + w) * 3 + a] = pr.v[a];
+        }
+        ++w;
+      }
+    g_count[b] = w;
+  }
+  return TP_OK;
+}
+
+int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, const int32_t* offsets,
+                            const double* ctrl_in, double* ctrl_out, tp_vigo_result* results, int32_t n_dyn,
+                            const double* dyn_pos, const double* dyn_vel, const double* dyn_size, int mem, void* stream) {
+  if (!e || !ctrl_out || !results) return TP_ERR_INVALID_ARG;
+  if (n_dyn < 0 || (n_dyn > 0 && (!dyn_pos || !dyn_vel || !dyn_size))) return TP_ERR_INVALID_ARG;
+  CK(cudaSetDevice(e->device));
+  cudaStream_t s = pick_stream(e, stream);
+  BatchSetup bs;
+  // device mode works in place on ctrl_out
+  if (mem == TP_MEM_DEVICE && ctrl_in != ctrl_out) {
+    std::vector<int> ho(B + 1);
+    CK(cudaMemcpyAsync(ho.data(), offsets, (size_t)(B + 1) * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaMemcpyAsync(ctrl_out, ctrl_in, (size_t)ho[B] * 24, cudaMemcpyDeviceToDevice, s));
+  }
+  int rc = setup_batch(e, p, B, offsets, mem == TP_MEM_DEVICE ? ctrl_out : ctrl_in, mem, s, bs, true);
+  if (rc != TP_OK) return rc;
+  // dynamic obstacles (always host pointers: a handful of values)
+  if (n_dyn > 0) {
+    if (e->dyn.ensure((size_t)n_dyn * 72) != TP_OK) return TP_ERR_CUDA;
+    double* d = e->dyn.as<double>();
+    CK(cudaMemcpyAsync(d, dyn_pos, (size_t)n_dyn * 24, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d + 3 * (size_t)n_dyn, dyn_vel, (size_t)n_dyn * 24, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d + 6 * (size_t)n_dyn, dyn_size, (size_t)n_dyn * 24, cudaMemcpyHostToDevice, s));
+    bs.bv.n_dyn = n_dyn;
+    bs.bv.dyn_pos = d;
+    bs.bv.dyn_vel = d + 3 * (size_t)n_dyn;
+    bs.bv.dyn_size = d + 6 * (size_t)n_dyn;
+  }
+  const size_t smem_lb = lbfgs_smem_doubles(bs.max_n, p->lbfgs_m) * 8;
+  rc = set_lbfgs_smem(e, smem_lb);
+  if (rc != TP_OK) return rc;
+  const size_t smem_cp = (size_t)3 * bs.max_n * 8;
+  const size_t smem_rp = (size_t)9 * bs.max_n * 8;
+  // ---- steps 1-3: collision segments, A*, guide points  -> active list 0, count in counters[0]
+  rc = run_plan_init(e, bs, s);
+  if (rc != TP_OK) return rc;
+  int* cnt = e->counters.as<int>();
+  // counters layout: [0] n_active(list0) [1] init queue; per round r: [2+4r..] = n_active_next, queue
+  int cur = 0;
+  int* n_cur = cnt + 0;
+  const int max_rounds = p->max_outer_rounds + 2;
+  CK(cudaMemcpyAsync(e->h_counters, n_cur, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  int n_active = e->h_counters[0];
+  for (int r = 0; r < max_rounds && n_active > 0; ++r) {
+    // optimize()
+    if (p->strict_order)
+      k_lbfgs<true><<<n_active, TP_LB_THREADS, smem_lb, s>>>(bs.bv, bs.C, e->active[cur].as<int>(), n_cur, nullptr, nullptr);
+    else
+      k_lbfgs<false><<<n_active, TP_LB_THREADS, smem_lb, s>>>(bs.bv, bs.C, e->active[cur].as<int>(), n_cur, nullptr, nullptr);
+    // hasCollisionTrajectory
+    k_has_collision<<<n_active, TP_LB_THREADS, smem_cp, s>>>(bs.bv, bs.C, e->dmap, e->active[cur].as<int>(), n_cur, nullptr);
+    // loop body: success / failure / re-guide / weight doubling
+    int* slot = cnt + 2 + 2 * (r % 24);
+    CK(cudaMemsetAsync(slot, 0, 8, s));
+    k_plan_step<<<std::min(e->pools.workers, n_active), 32, 0, s>>>(bs.bv, bs.C, e->dmap, e->pools, slot + 1,
+                                                                    e->active[cur].as<int>(), n_cur,
+                                                                    e->active[cur ^ 1].as<int>(), slot);
+    e->launches += 3;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(e->h_counters, slot, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    n_active = e->h_counters[0];
+    n_cur = slot;
+    cur ^= 1;
+  }
+  // ---- steps 5-6: time re-parameterisation of the successful trajectories
+  k_reparam<<<B, TP_LB_THREADS, smem_rp, s>>>(bs.bv, bs.C);
+  if (e->results.ensure((size_t)B * sizeof(tp_vigo_result)) != TP_OK) return TP_ERR_CUDA;
+  tp_vigo_result* dres = mem == TP_MEM_DEVICE ? results : e->results.as<tp_vigo_result>();
+  k_collect_results<<<(B + 127) / 128, 128, 0, s>>>(bs.bv, dres);
+  e->launches += 2;
+  CK(cudaGetLastError());
+  if (mem == TP_MEM_HOST) {
+    CK(cudaMemcpyAsync(ctrl_out, bs.bv.ctrl, (size_t)bs.total * 24, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(results, dres, (size_t)B * sizeof(tp_vigo_result), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  return TP_OK;
+}
+
+}  // extern "C"
