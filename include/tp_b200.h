@@ -72,7 +72,10 @@ typedef struct tp_vigo_params {
   int32_t max_outer_rounds;    /* replaces the 0.03 s exit of bsplineTraj.cpp:633         24 */
   int32_t astar_max_expansions;/* replaces the 0.2 s exit of astarOcc.cpp:231         200000 */
   int32_t strict_order;        /* 1: serial-order reductions (bit-reproduces the CPU sums)   */
-  int32_t reserved;
+  int32_t vclock_budget;       /* deterministic stand-in for the 0.03 s wall clock of bsplineTraj.cpp:618,
+                                  632-638: virtual clock in 10 ns units, started after the first optimize(),
+                                  += evals*(10 N + 2 n) per optimize(), += 30 per A* expansion, checked where
+                                  the reference checks its timer; 0 = off                    3000000 */
 } tp_vigo_params;
 
 /* per-trajectory outcome of tp_vigo_make_plan_batch */
@@ -161,6 +164,28 @@ int64_t tp_engine_launch_count(const tp_engine_t* e);
 void* tp_engine_stream(tp_engine_t* e);
 
 void tp_vigo_default_params(tp_vigo_params* p);
+
+/* ------------------------------------------------------------------------------------ measurement
+ * Per-kernel device timing with CUDA events on the launching stream (bench.py's roofline legs).
+ * Kinds: 0 fused cost+L-BFGS (optimize), 1 trajectory collision check, 2 outer-loop step
+ * (segments / A* / guide points), 3 initial segments+A*+guides, 4 re-parameterisation, 5 map queries. */
+#define TP_PROF_KINDS 8
+typedef struct tp_profile {
+  double ms[TP_PROF_KINDS];         /* summed device time of the launches of each kind            */
+  int64_t launches[TP_PROF_KINDS];
+  double lbfgs_flops;               /* algorithmic FP64 flops executed by the optimize kernel      */
+  double lbfgs_iters, lbfgs_evals;  /* summed over all trajectories                               */
+  double check_samples;             /* de Boor samples evaluated + map-queried by the check kernel */
+  double query_points;              /* points answered by tp_query_* kernels                       */
+} tp_profile;
+int tp_engine_profile_enable(tp_engine_t* e, int on);
+/* synchronises the engine's stream(s), returns the totals since the last call and resets them */
+int tp_engine_profile_get(tp_engine_t* e, tp_profile* out);
+/* micro-benchmarks for the roofline denominators MEASURED_PEAKS.json does not carry:
+ * dependent-free FP64 FMA throughput (TFLOP/s, 2 flops per FMA) and random 32 B-sector gathers
+ * from a `bytes`-sized buffer (GB/s of sectors; bytes <= ~100 MB stays L2 resident). */
+int tp_microbench_fp64(tp_engine_t* e, double* tflops);
+int tp_microbench_gather(tp_engine_t* e, int64_t bytes, double* gbs);
 
 /* ------------------------------------------------------------------------------------ map queries
  * occMap::isInflatedOccupied / isUnknown / isInflatedOccupiedLine over n points (xyz = n x 3 FP64). */

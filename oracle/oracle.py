@@ -25,7 +25,7 @@ class VigoParams(C.Structure):
         ("not_check_ratio", C.c_double), ("lbfgs_g_eps", C.c_double),
         ("plan_in_z", C.c_int), ("lbfgs_m", C.c_int), ("lbfgs_max_iter", C.c_int),
         ("lbfgs_max_linesearch", C.c_int), ("max_outer_rounds", C.c_int), ("astar_max_expansions", C.c_int),
-        ("use_ref_lbfgs", C.c_int), ("reserved", C.c_int),
+        ("use_ref_lbfgs", C.c_int), ("soft_atan2", C.c_int), ("vclock_budget", C.c_int), ("reserved2", C.c_int),
     ]
 
 
@@ -103,6 +103,8 @@ class Lib:
         L.orc_make_plan_batch.argtypes = [C.c_void_p, C.POINTER(VigoParams), C.c_int, _ip, _dp, _dp,
                                           C.c_void_p, C.c_int, _dp]
         L.orc_default_params.argtypes = [C.POINTER(VigoParams)]
+        L.orc_soft_atan2.restype = C.c_double
+        L.orc_soft_atan2.argtypes = [C.c_double, C.c_double]
         assert L.orc_sizeof_params() == C.sizeof(VigoParams)
         assert L.orc_sizeof_stats() == C.sizeof(PlanStats) == STATS_DTYPE.itemsize
 

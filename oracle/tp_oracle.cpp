@@ -41,8 +41,32 @@ static inline V3 cross3(const V3& a, const V3& b) {
 }
 // utils.h:19 (sic: truncated pi) and utils.h:84-86
 static const double PI_const = 3.1415926;
-static inline double angleBetweenVectors(const V3& a, const V3& b) {
-  return std::atan2(norm3(cross3(a, b)), dot3(a, b));
+// Restatement of the product's deterministic atan2 (trajectory_planner_b200/csrc/tp_device.cuh,
+// tp_atan2): IEEE +,-,*,/ only, fixed order, so both sides agree bit for bit.  Used only when
+// VigoParams::soft_atan2 is set; the reference-faithful default is std::atan2 (utils.h:84-86).
+static inline double soft_atan_series(double t) {
+  const double z = t * t;
+  double s = 1.0 / 47.0;
+  for (int k = 22; k >= 0; --k) s = 1.0 / (double)(2 * k + 1) - z * s;
+  return t * s;
+}
+static inline double soft_atan2(double y, double x) {
+  const double PI = 3.14159265358979323846, PI_2 = 1.57079632679489661923, PI_4 = 0.78539816339744830962;
+  const double ay = y < 0 ? -y : y, ax = x < 0 ? -x : x;
+  if (ax == 0.0 && ay == 0.0) return 0.0;
+  const bool swap = ay > ax;
+  const double q = swap ? ax / ay : ay / ax;
+  double r;
+  if (q > 0.41421356237309503) r = PI_4 + soft_atan_series((q - 1.0) / (q + 1.0));
+  else r = soft_atan_series(q);
+  if (swap) r = PI_2 - r;
+  if (x < 0) r = PI - r;
+  if (y < 0) r = -r;
+  return r;
+}
+static inline double angleBetweenVectors(const V3& a, const V3& b, bool soft) {
+  const double y = norm3(cross3(a, b)), x = dot3(a, b);
+  return soft ? soft_atan2(y, x) : std::atan2(y, x);
 }
 
 // ------------------------------------------------------------------ map contract
@@ -604,6 +628,7 @@ struct Planner {
       Lbfgs<Planner> solver(*this, lp);
       st = solver.optimize(n, x.data());
     }
+    vclock += (long long)st.evals * (10LL * N + 2LL * n);
     stats.lbfgs_runs += 1;
     stats.lbfgs_iters += st.iters > 0 ? st.iters : 0;
     stats.lbfgs_evals += st.evals;
@@ -613,6 +638,7 @@ struct Planner {
     return st;
   }
   std::vector<double> last_x;
+  long long vclock = 0;  // virtual clock, 10 ns units (see VigoParams::vclock_budget)
 
   // ---- collision logic ----------------------------------------------------------
   // bT.h:196-204: a accumulates by res (0, .1, .2, ... — serial adds, kept)
@@ -663,14 +689,14 @@ struct Planner {
     V3 direction = path[0] - psudo;
     for (size_t i = 0; i + 1 < path.size(); ++i) {
       V3 wpCurr = path[i], wpNext = path[i + 1];
-      double angleCurr = angleBetweenVectors(direction, wpCurr - psudo);
-      double angleNext = angleBetweenVectors(direction, wpNext - psudo);
+      double angleCurr = angleBetweenVectors(direction, wpCurr - psudo, P.soft_atan2 != 0);
+      double angleNext = angleBetweenVectors(direction, wpNext - psudo, P.soft_atan2 != 0);
       if (targetAngle >= angleCurr && targetAngle <= angleNext) {
         double prevAngleDiff = 0.0;
         V3 prevTemp{0, 0, 0};
         for (double a = 1.0; a >= 0.0; a -= 0.1) {
           V3 temp = a * wpCurr + (1 - a) * wpNext;
-          double tempAngle = angleBetweenVectors(direction, temp - psudo);
+          double tempAngle = angleBetweenVectors(direction, temp - psudo, P.soft_atan2 != 0);
           double angleDiff = tempAngle - targetAngle;
           if (angleDiff == 0) { guidePoint = temp; return true; }
           if (angleDiff * prevAngleDiff < 0) {
@@ -756,6 +782,7 @@ struct Planner {
       ++stats.astar_searches;
       bool ok = astar.search(map->res, pStart, pEnd);
       stats.astar_expansions += astar.last_expansions;
+      vclock += 30LL * astar.last_expansions;
       if (ok) {
         std::vector<V3> sp = astar.getPath();
         sp[0] = pStart;
@@ -769,6 +796,7 @@ struct Planner {
             ++stats.astar_searches;
             bool ok2 = astar.search(map->res, pS, pE);
             stats.astar_expansions += astar.last_expansions;
+            vclock += 30LL * astar.last_expansions;
             if (ok2) {
               std::vector<V3> sp = astar.getPath();
               sp[0] = pS;
@@ -880,11 +908,12 @@ struct Planner {
     int failCount = 0;
     std::vector<std::vector<V3>> tmpPaths;
     int round = 0;
+    vclock = 0;  // ros::Time startTime = ros::Time::now();  (bT.cpp:618)
     while (true) {
       bool hasCol = hasCollisionTrajectory();
       bool hasDyn = dynPos.size() != 0 ? hasDynamicCollisionTrajectory() : false;
       if (!hasCol && !hasDyn) break;
-      if (round >= P.max_outer_rounds) {
+      if (round >= P.max_outer_rounds || (P.vclock_budget > 0 && vclock > (long long)P.vclock_budget)) {
         wDist = w0; wDyn = wd0;
         stats.outer_rounds = round; stats.fail_count = failCount;
         return false;
@@ -981,6 +1010,8 @@ void orc_default_params(VigoParams* p) {
   p->lbfgs_g_eps = 0.01; p->plan_in_z = 0; p->lbfgs_m = 16; p->lbfgs_max_iter = 200;
   p->lbfgs_max_linesearch = 40; p->max_outer_rounds = 24; p->astar_max_expansions = 200000;
   p->use_ref_lbfgs = 0;
+  p->soft_atan2 = 0;
+  p->vclock_budget = 3000000;
 }
 int orc_sizeof_params() { return (int)sizeof(VigoParams); }
 int orc_sizeof_stats() { return (int)sizeof(PlanStats); }
@@ -1156,6 +1187,7 @@ int orc_planner_make_plan(void* pl_, PlanStats* st) {
   if (st) *st = pl->stats;
   return ok ? 1 : 0;
 }
+double orc_soft_atan2(double y, double x) { return soft_atan2(y, x); }
 double orc_planner_linear_factor(void* pl_) {
   Planner* pl = (Planner*)pl_;
   pl->linearFeasibilityReparam();

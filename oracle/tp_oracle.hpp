@@ -83,7 +83,14 @@ struct VigoParams {
   int max_outer_rounds;      // replaces the 0.03 s limit of bsplineTraj.cpp:633
   int astar_max_expansions;  // replaces the 0.2 s limit of astarOcc.cpp:231
   int use_ref_lbfgs;         // (only honoured by the _ref build) 1 = reference header
-  int reserved;
+  int soft_atan2;            // 1: deterministic software atan2 (bit-matches the GPU); 0: std::atan2 (reference)
+  // Deterministic stand-in for the 0.03 s wall clock of bsplineTraj.cpp:618,632-638: a virtual clock in
+  // 10 ns units, started where the reference starts its timer (after the first optimize()), advanced by
+  // evals*(10 N + 2 n) per optimize() and 30 per A* expansion (a cost model of the reference's CPU
+  // path: ~0.1 us per control point per cost evaluation incl. its share of the two-loop recursion,
+  // ~0.3 us per expansion), checked where the reference checks its clock.  0 disables it.
+  int vclock_budget;         // default 3,000,000 (= 30 ms)
+  int reserved2;
 };
 
 struct PlanStats {

@@ -58,8 +58,11 @@ def test_cost_and_gradient_parity(tp, engine, orc, sq_omap, problems, strict):
     worst_f, worst_g = 0.0, 0.0
     for b in range(B):
         c = ctrl[off[b]:off[b + 1]]
-        planners[b].set_weights(weights[b, 0], weights[b, 1])
-        fo, go, _ = planners[b].cost(c[3:-3].ravel())
+        pl = orc.Planner(sq_omap)
+        pl.set_ctrl(c)          # perturbed end points too
+        pl.add_guides(*per[b])
+        pl.set_weights(weights[b, 0], weights[b, 1])
+        fo, go, _ = pl.cost(c[3:-3].ravel())
         gs = g[3 * (off[b] - 6 * b): 3 * (off[b + 1] - 6 * (b + 1))]
         worst_f = max(worst_f, abs(f[b] - fo) / max(abs(fo), 1e-300))
         worst_g = max(worst_g, np.max(np.abs(gs - go)) / max(np.max(np.abs(go)), 1e-300))
@@ -83,16 +86,19 @@ def test_cost_plan_in_z_and_dynamic_obstacles(tp, engine, orc, sq_omap, problems
     ctrl = problems["ctrl"][:off[B]].copy()
     ctrl += rng.normal(0, 0.2, ctrl.shape)
     per = []
-    pls = []
     for b in range(B):
         pl = orc.Planner(sq_omap, po)
         pl.set_ctrl(traj(problems, b))
         pl.init_guides()
         per.append(pl.get_guides())
-        pls.append(pl)
+    dyn = (np.array([[0.0, 0.0, 1.0], [3.0, -2.0, 1.0]]), np.array([[0.5, 0.2, 0.0], [-0.3, 0.4, 0.0]]),
+           np.array([[0.6, 0.8, 1.7], [0.5, 0.5, 1.7]]))
     f, g = engine.cost_batch(p, off, ctrl, flat_guides(per))
     for b in range(B):
-        fo, go, _ = pls[b].cost(ctrl[off[b]:off[b + 1]][3:-3].ravel())
+        pl = orc.Planner(sq_omap, po)
+        pl.set_ctrl(ctrl[off[b]:off[b + 1]])
+        pl.add_guides(*per[b])
+        fo, go, _ = pl.cost(ctrl[off[b]:off[b + 1]][3:-3].ravel())
         gs = g[3 * (off[b] - 6 * b): 3 * (off[b + 1] - 6 * (b + 1))]
         assert abs(f[b] - fo) <= 1e-10 * abs(fo)
         assert np.max(np.abs(gs - go)) <= 1e-10 * np.max(np.abs(go))
@@ -100,30 +106,42 @@ def test_cost_plan_in_z_and_dynamic_obstacles(tp, engine, orc, sq_omap, problems
 
 @pytest.mark.parametrize("strict", [0, 1])
 def test_optimize_parity(tp, engine, orc, sq_omap, problems, strict):
-    """One optimize() (fused cost + L-BFGS kernel) vs lbfgs_optimize on the CPU."""
-    B = 48
-    off = problems["offsets"][:B + 1]
+    """One optimize() (fused cost + L-BFGS kernel) vs lbfgs_optimize on the CPU, identical inputs.
+
+    strict_order=1 must reproduce the CPU iterate BIT FOR BIT (same ret / iterations / evaluations /
+    control points).  The default fixed-tree reductions differ from the CPU's serial sums in the last
+    bits of every dot product; the solve amplifies that (jerk Hessian condition number ~1e9, loose
+    g_epsilon), so there the comparison is per-evaluation (test_cost_and_gradient_parity) plus the
+    statistics asserted below."""
+    B = len(problems["offsets"]) - 1
+    off = problems["offsets"]
     per, planners, _ = _oracle_guides(orc, sq_omap, problems, B)
     p = tp.default_params()
     p.strict_order = strict
-    ctrl_out, res, xf = engine.optimize_batch(p, off, problems["ctrl"][:off[B]], flat_guides(per))
-    same_iters, within, worst_same, exact = 0, 0, 0.0, 0
+    ctrl_out, res, xf = engine.optimize_batch(p, off, problems["ctrl"], flat_guides(per))
+    same, within, exact, worst_same = 0, 0, 0, 0.0
+    fx_rel = []
     for b in range(B):
         o = planners[b].optimize()
         co = planners[b].get_ctrl()
         cg = ctrl_out[off[b]:off[b + 1]]
         d = float(np.max(np.abs(cg - co)))
+        fx_rel.append(abs(res["fx"][b] - o["fx"]) / abs(o["fx"]))
         if res["iters"][b] == o["iters"] and res["evals"][b] == o["evals"] and res["ret"][b] == o["ret"]:
-            same_iters += 1
+            same += 1
             worst_same = max(worst_same, d)
             within += d <= 1e-6
             exact += d == 0.0
-    print(f"strict={strict}: equal (ret,iters,evals) {same_iters}/{B}, of those within 1e-6 m: {within}, "
-          f"bit-identical: {exact}, worst {worst_same:.3e}")
-    assert same_iters >= int(0.75 * B)
-    assert within == same_iters
+        # solver's own x equals the control points unless the line search failed
+        if res["ret"][b] >= 0 or res["ret"][b] == -1004:
+            assert np.array_equal(xf[3 * (off[b] - 6 * b): 3 * (off[b + 1] - 6 * (b + 1))].reshape(-1, 3), cg[3:-3])
+    print(f"strict={strict}: equal (ret,iters,evals) {same}/{B}; of those within 1e-6 m {within}, bit-identical "
+          f"{exact}, worst {worst_same:.3e}; final-cost rel diff median {np.median(fx_rel):.2e} max {np.max(fx_rel):.2e}")
     if strict:
-        assert same_iters == B and worst_same <= 1e-9
+        assert same == B and exact == B
+    else:
+        assert same >= int(0.2 * B)
+        assert np.median(fx_rel) <= 1e-3 and np.max(fx_rel) <= 0.25
 
 
 def test_has_collision_and_segments_bit_exact(tp, engine, orc, sq_omap, problems):
@@ -140,6 +158,14 @@ def test_has_collision_and_segments_bit_exact(tp, engine, orc, sq_omap, problems
         assert np.array_equal(segs[b], pl.find_collision_seg()), b
         nhit += int(hit[b])
     assert 0 < nhit  # the workload does cross obstacles
+    # after one optimize() most trajectories are collision free: the decision must still agree
+    per, planners, _ = _oracle_guides(orc, sq_omap, problems, B)
+    moved = np.concatenate([(planners[b].optimize(), planners[b].get_ctrl())[1] for b in range(B)], 0)
+    hit2 = engine.has_collision_batch(p, off, moved)
+    segs2 = engine.find_collision_seg_batch(p, off, moved)
+    for b in range(B):
+        assert bool(hit2[b]) == planners[b].has_collision(), b
+        assert np.array_equal(segs2[b], planners[b].find_collision_seg()), b
 
 
 def test_astar_paths_bit_exact(tp, engine, orc, sq_omap, problems):
@@ -153,9 +179,11 @@ def test_astar_paths_bit_exact(tp, engine, orc, sq_omap, problems):
         for s0, s1 in pl.find_collision_seg():
             starts.append(c[s0])
             ends.append(c[s1])
-    # plus pairs that fail (goal buried in an obstacle / out of the pool)
+    # plus pairs that fail (goal buried in an obstacle / out of the pool) and a trivial one
     starts.append([0.0, 0.0, 1.0]); ends.append([30.0, 0.0, 1.0])
     starts.append([-8.0, -8.0, 1.0]); ends.append([-7.0, -7.6, 1.0])
+    starts.append([0.0, 0.0, 1.0]); ends.append([0.02, 0.01, 1.0])
+    starts.append([0.0, 0.0, 2.5]); ends.append([1.0, 0.5, 1.0])   # start above the height band
     paths, ex = engine.astar_batch(p, starts, ends)
     pl = orc.Planner(sq_omap)
     nfound = 0
@@ -169,79 +197,144 @@ def test_astar_paths_bit_exact(tp, engine, orc, sq_omap, problems):
     assert nfound > 10
 
 
-def test_init_guides_parity(tp, engine, orc, sq_omap, problems):
-    """findCollisionSeg + pathSearch + assignGuidePointsSemiCircle (makePlan steps 1-3)."""
+@pytest.mark.parametrize("soft", [0, 1])
+def test_init_guides_parity(tp, engine, orc, sq_omap, problems, soft):
+    """findCollisionSeg + pathSearch + shortcut + assignGuidePointsSemiCircle (makePlan steps 1-3).
+    soft=0: oracle with std::atan2 (reference-faithful) -> guide points agree to 1e-9;
+    soft=1: oracle with the same deterministic atan2 the device uses -> bit-identical."""
     B = len(problems["offsets"]) - 1
     p = tp.default_params()
     out = engine.init_guides_batch(p, problems["offsets"], problems["ctrl"])
-    per, planners, oks = _oracle_guides(orc, sq_omap, problems, B)
+    po = sq_omap.lib.default_params()
+    po.soft_atan2 = soft
     npairs = 0
     for b in range(B):
-        assert out[b]["ok"] == oks[b], b
-        if not oks[b]:
+        pl = orc.Planner(sq_omap, po)
+        pl.set_ctrl(traj(problems, b))
+        ok = pl.init_guides()
+        assert out[b]["ok"] == ok, b
+        if not ok:
             continue
-        assert np.array_equal(out[b]["segs"], planners[b].get_segs()), b
-        cp, gp, gv = per[b]
+        assert np.array_equal(out[b]["segs"], pl.get_segs()), b
+        cp, gp, gv = pl.get_guides()
         assert np.array_equal(out[b]["cp"], cp), b
         npairs += len(cp)
         if len(cp):
-            assert np.max(np.abs(out[b]["p"] - gp)) <= 1e-9, b   # atan2 is not glibc's
-            assert np.max(np.abs(out[b]["v"] - gv)) <= 1e-9, b
+            if soft:
+                assert np.array_equal(out[b]["p"], gp) and np.array_equal(out[b]["v"], gv), b
+            else:
+                assert np.max(np.abs(out[b]["p"] - gp)) <= 1e-9, b
+                assert np.max(np.abs(out[b]["v"] - gv)) <= 1e-9, b
     assert npairs > 50
 
 
+def _plan_compare(off, out, res, out_o, st_o):
+    B = len(off) - 1
+    keys = ["outer_rounds", "fail_count", "lbfgs_runs", "lbfgs_iters", "lbfgs_evals", "astar_searches",
+            "astar_expansions", "n_guide_pairs", "last_lbfgs_ret"]
+    status_o = np.where(st_o["success"] == 1, 1, 0)
+    status_g = np.where(res["status"] == 1, 1, 0)
+    r = dict(agree=int(np.sum(status_o == status_g)), same_flow=0, within=0, exact=0, worst=0.0, lf_worst=0.0,
+             succ_g=float(status_g.mean()), succ_o=float(status_o.mean()))
+    for b in range(B):
+        if status_o[b] == status_g[b] and all(res[k][b] == st_o[k][b] for k in keys):
+            r["same_flow"] += 1
+            d = float(np.max(np.abs(out[off[b]:off[b + 1]] - out_o[off[b]:off[b + 1]])))
+            r["worst"] = max(r["worst"], d)
+            r["within"] += d <= 1e-6
+            r["exact"] += d == 0.0
+            if status_g[b] == 1:
+                r["lf_worst"] = max(r["lf_worst"], abs(res["linear_factor"][b] - st_o["linear_factor"][b]))
+    return r
+
+
+def test_make_plan_batch_strict_is_bit_faithful(tp, engine, orc, sq_omap, problems):
+    """The batched entry point in strict order vs the oracle's makePlan with the shared deterministic
+    atan2: whole-solve control flow (rounds, fail counts, A* expansions, L-BFGS iterations) and final
+    control points must be identical."""
+    off = problems["offsets"]
+    B = len(off) - 1
+    p = tp.default_params()
+    p.strict_order = 1
+    out, res = engine.make_plan_batch(p, off, problems["ctrl"])
+    po = sq_omap.lib.default_params()
+    po.soft_atan2 = 1
+    _, out_o, st_o = orc.make_plan_batch(sq_omap, po, off, problems["ctrl"], nthreads=4)
+    r = _plan_compare(off, out, res, out_o, st_o)
+    print("strict vs oracle(soft atan2):", r)
+    assert r["agree"] == B and r["same_flow"] == B
+    assert r["within"] == B and r["worst"] <= 1e-9 and r["lf_worst"] <= 1e-9
+    assert (res["status"] == 1).sum() > 0.8 * B
+
+
 @pytest.mark.parametrize("strict", [0, 1])
-def test_make_plan_batch_parity(tp, engine, orc, sq_omap, problems, strict):
-    """The batched entry point vs the oracle's makePlan on the same control points."""
+def test_make_plan_batch_vs_reference_faithful_oracle(tp, engine, orc, sq_omap, problems, strict):
+    """Same, against the oracle with std::atan2 (the reference's libm).  ULP-level differences in guide
+    points (and, for strict=0, in reduction order) are amplified by the solve, so identical control flow
+    holds only for a fraction; the solve QUALITY must be statistically the same."""
     off = problems["offsets"]
     B = len(off) - 1
     p = tp.default_params()
     p.strict_order = strict
     out, res = engine.make_plan_batch(p, off, problems["ctrl"])
     po = sq_omap.lib.default_params()
-    ok_o, out_o, st_o = orc.make_plan_batch(sq_omap, po, off, problems["ctrl"], nthreads=4)
-    status_o = np.where(st_o["success"] == 1, 1, 0)
-    status_g = np.where(res["status"] == 1, 1, 0)
-    same_flow = 0
-    within = 0
-    worst = 0.0
-    lf_worst = 0.0
+    _, out_o, st_o = orc.make_plan_batch(sq_omap, po, off, problems["ctrl"], nthreads=4)
+    r = _plan_compare(off, out, res, out_o, st_o)
+    print(f"strict={strict} vs oracle(std::atan2):", r)
+    assert r["agree"] >= int(0.9 * B)
+    assert abs(r["succ_g"] - r["succ_o"]) <= 0.06
+    assert r["same_flow"] >= int((0.5 if strict else 0.15) * B)
+    # every successful GPU trajectory is collision free under the oracle's own check
     for b in range(B):
-        keys = ["outer_rounds", "fail_count", "lbfgs_runs", "lbfgs_iters", "lbfgs_evals", "astar_searches",
-                "astar_expansions", "n_guide_pairs"]
-        if status_o[b] == status_g[b] and all(res[k][b] == st_o[k][b] for k in keys):
-            same_flow += 1
-            d = float(np.max(np.abs(out[off[b]:off[b + 1]] - out_o[off[b]:off[b + 1]])))
-            worst = max(worst, d)
-            within += d <= 1e-6
-            if status_g[b] == 1:
-                lf_worst = max(lf_worst, abs(res["linear_factor"][b] - st_o["linear_factor"][b]))
-    agree = int(np.sum(status_o == status_g))
-    print(f"strict={strict}: status agree {agree}/{B}; identical control flow {same_flow}/{B}; of those within "
-          f"1e-6 m: {within} (worst {worst:.3e}); linear factor worst {lf_worst:.3e}; "
-          f"success rate gpu {status_g.mean():.3f} oracle {status_o.mean():.3f}")
-    assert agree >= int(0.9 * B)
-    assert same_flow >= int(0.6 * B)
-    assert within == same_flow
-    assert lf_worst <= 1e-6
-    if strict:
-        assert same_flow >= int(0.95 * B)
+        if res["status"][b] == 1:
+            pl = orc.Planner(sq_omap)
+            pl.set_ctrl(out[off[b]:off[b + 1]])
+            assert not pl.has_collision(), b
+
+
+def test_make_plan_with_dynamic_obstacles(tp, engine, orc, sq_omap, problems):
+    off = problems["offsets"][:17]
+    B = 16
+    ctrl = problems["ctrl"][:off[B]]
+    mid = np.array([traj(problems, b)[len(traj(problems, b)) // 2] for b in range(2)])
+    dyn = (mid + [0.3, 0.3, 0.0], np.array([[0.2, 0.1, 0.0], [-0.1, 0.2, 0.0]]), np.array([[0.5, 0.5, 1.7], [0.4, 0.6, 1.7]]))
+    p = tp.default_params()
+    p.strict_order = 1
+    out, res = engine.make_plan_batch(p, off, ctrl, dyn)
+    po = sq_omap.lib.default_params()
+    po.soft_atan2 = 1
+    same = 0
+    for b in range(B):
+        pl = orc.Planner(sq_omap, po)
+        pl.set_ctrl(ctrl[off[b]:off[b + 1]])
+        pl.set_dyn(*dyn)
+        ok, st = pl.make_plan()
+        if ok == (res["status"][b] == 1) and st["lbfgs_iters"] == res["lbfgs_iters"][b]:
+            same += 1
+            assert np.max(np.abs(pl.get_ctrl() - out[off[b]:off[b + 1]])) <= 1e-9, b
+    print("dynamic obstacles: identical flow", same, "/", B)
+    assert same >= B - 2   # pow(x,0.5) vs sqrt and the obstacle-size sqrt are the only unshared ops
 
 
 def test_bspline_traj_class_drop_in(tp, engine, orc, sq_omap, problems):
     """The reference-shaped planner object: updatePath / makePlan / getPose / isCurrTrajValid."""
-    bt = tp.BsplineTraj(engine)
+    p = tp.default_params()
+    p.strict_order = 1
+    bt = tp.BsplineTraj(engine, p)
     ok = bt.updatePathFromStartGoal(problems["starts"][0], problems["goals"][0])
     assert ok
     c0 = bt.getControlPoints()
     assert c0.shape[0] == 3
-    pl = orc.Planner(sq_omap)
+    po = sq_omap.lib.default_params()
+    po.soft_atan2 = 1
+    pl = orc.Planner(sq_omap, po)
     pl.set_ctrl(c0.T)
     ok_o, st = pl.make_plan()
     assert bt.makePlan() == ok_o
+    assert np.array_equal(bt.getControlPoints().T, pl.get_ctrl())
     if ok_o:
         assert bt.isCurrTrajValid()
-        assert abs(bt.getLinearFactor() - st["linear_factor"]) < 1e-6
+        assert abs(bt.getLinearFactor() - st["linear_factor"]) < 1e-12
         x, y, z, yaw = bt.getPose(0.5 * bt.getDuration())
         ref = orc.bspline_at(bt.getControlPoints().T, [0.5 * bt.getDuration()])[0]
-        assert np.allclose([x, y, z], ref, atol=1e-12)
+        assert np.array_equal([x, y, z], ref)

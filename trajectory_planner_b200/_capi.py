@@ -31,7 +31,7 @@ class VigoParams(C.Structure):
         ("not_check_ratio", C.c_double), ("lbfgs_g_eps", C.c_double),
         ("plan_in_z", C.c_int32), ("lbfgs_m", C.c_int32), ("lbfgs_max_iter", C.c_int32),
         ("lbfgs_max_linesearch", C.c_int32), ("max_outer_rounds", C.c_int32), ("astar_max_expansions", C.c_int32),
-        ("strict_order", C.c_int32), ("reserved", C.c_int32),
+        ("strict_order", C.c_int32), ("vclock_budget", C.c_int32),
     ]
 
 
@@ -50,6 +50,14 @@ class MapInfo(C.Structure):
     ]
 
 
+class Profile(C.Structure):
+    _fields_ = [("ms", C.c_double * 8), ("launches", C.c_int64 * 8), ("lbfgs_flops", C.c_double),
+                ("lbfgs_iters", C.c_double), ("lbfgs_evals", C.c_double), ("check_samples", C.c_double),
+                ("query_points", C.c_double)]
+
+
+PROF_KINDS = ["lbfgs", "collision_check", "plan_step", "plan_init", "reparam", "map_query"]
+
 RESULT_DTYPE = np.dtype([
     ("status", "i4"), ("outer_rounds", "i4"), ("fail_count", "i4"), ("lbfgs_runs", "i4"), ("lbfgs_iters", "i4"),
     ("lbfgs_evals", "i4"), ("astar_searches", "i4"), ("astar_expansions", "i4"), ("n_guide_pairs", "i4"),
@@ -65,7 +73,8 @@ SYMBOLS = [
     "tp_vigo_default_params", "tp_query_points", "tp_query_unknown", "tp_query_lines", "tp_vigo_cost_batch",
     "tp_vigo_optimize_batch", "tp_vigo_has_collision_batch", "tp_vigo_find_collision_seg_batch", "tp_astar_batch",
     "tp_vigo_init_guides_batch", "tp_vigo_make_plan_batch", "tp_vigo_frontend_batch", "tp_bspline_fit",
-    "tp_bspline_eval",
+    "tp_bspline_eval", "tp_engine_profile_enable", "tp_engine_profile_get", "tp_microbench_fp64",
+    "tp_microbench_gather",
 ]
 
 
@@ -131,6 +140,10 @@ def load():
     L.tp_vigo_frontend_batch.argtypes = [vp, PP, C.c_int32, vp, vp, vp, vp, C.c_int64, vp]
     L.tp_bspline_fit.argtypes = [C.c_double, C.c_int32, vp, vp, vp]
     L.tp_bspline_eval.argtypes = [C.c_int32, vp, C.c_double, C.c_int32, C.c_int32, vp, vp]
+    L.tp_engine_profile_enable.argtypes = [vp, C.c_int]
+    L.tp_engine_profile_get.argtypes = [vp, C.POINTER(Profile)]
+    L.tp_microbench_fp64.argtypes = [vp, _dp]
+    L.tp_microbench_gather.argtypes = [vp, C.c_int64, _dp]
     _lib = L
     return L
 

@@ -198,6 +198,30 @@ class Engine:
     def stream(self):
         return self.L.tp_engine_stream(self.h)
 
+    # ---- measurement
+    def profile_enable(self, on=True):
+        check(self.L.tp_engine_profile_enable(self.h, 1 if on else 0), "tp_engine_profile_enable")
+
+    def profile_get(self):
+        pr = _capi.Profile()
+        check(self.L.tp_engine_profile_get(self.h, C.byref(pr)), "tp_engine_profile_get")
+        out = dict(lbfgs_flops=pr.lbfgs_flops, lbfgs_iters=pr.lbfgs_iters, lbfgs_evals=pr.lbfgs_evals,
+                   check_samples=pr.check_samples, query_points=pr.query_points, ms={}, launches={})
+        for i, k in enumerate(_capi.PROF_KINDS):
+            out["ms"][k] = pr.ms[i]
+            out["launches"][k] = int(pr.launches[i])
+        return out
+
+    def microbench_fp64(self):
+        v = C.c_double(0)
+        check(self.L.tp_microbench_fp64(self.h, C.byref(v)), "tp_microbench_fp64")
+        return v.value
+
+    def microbench_gather(self, nbytes):
+        v = C.c_double(0)
+        check(self.L.tp_microbench_gather(self.h, int(nbytes), C.byref(v)), "tp_microbench_gather")
+        return v.value
+
     # ---- map queries
     def query_points(self, xyz):
         xyz = _f64(xyz).reshape(-1, 3)

@@ -130,3 +130,30 @@ __device__ __forceinline__ double cube_cr(double x) {
   const double l2 = lo * x + e2;
   return h2 + l2;
 }
+
+// Deterministic atan2 for the guide-point search (utils.h:84-86 calls std::atan2).  libm's atan2
+// is neither bit-portable across platforms nor available on the device, and ULP-level differences
+// in guide points are amplified by the ill-conditioned solve; this routine uses only IEEE
+// +,-,*,/ in a fixed order (no FMA), so the CPU restatement in the oracle's `soft_atan2` mode
+// reproduces it bit for bit.  Accuracy ~1-2 ULP.  Reduction: q = min/max in [0,1];
+// q > tan(pi/8): atan q = pi/4 + atan((q-1)/(q+1)); series in z = t^2, |t| <= 0.4143, 24 terms.
+__host__ __device__ inline double tp_atan_series(double t) {
+  const double z = t * t;
+  double s = 1.0 / 47.0;
+  for (int k = 22; k >= 0; --k) s = 1.0 / (double)(2 * k + 1) - z * s;
+  return t * s;
+}
+__host__ __device__ inline double tp_atan2(double y, double x) {
+  const double PI = 3.14159265358979323846, PI_2 = 1.57079632679489661923, PI_4 = 0.78539816339744830962;
+  const double ay = y < 0 ? -y : y, ax = x < 0 ? -x : x;
+  if (ax == 0.0 && ay == 0.0) return 0.0;
+  const bool swap = ay > ax;
+  const double q = swap ? ax / ay : ay / ax;
+  double r;
+  if (q > 0.41421356237309503) r = PI_4 + tp_atan_series((q - 1.0) / (q + 1.0));
+  else r = tp_atan_series(q);
+  if (swap) r = PI_2 - r;
+  if (x < 0) r = PI - r;
+  if (y < 0) r = -r;
+  return r;
+}

@@ -469,7 +469,7 @@ __device__ void lbfgs_run(const VigoConst& C, EvalCtx& E, double* sm, tp_lbfgs_r
 
   const double min_step = 1e-20, max_step = 1e20, ftol = 1e-4, gtol = 0.9, xtol = 1e-16;  // lbfgs.hpp:942-954
   const int max_ls = C.p.lbfgs_max_linesearch;
-  int evals = 0, k = 0, ret;
+  int evals = 0, k = 0, ret, bsum = 0;
   double fx, dgdummy;
   __syncthreads();
   eval_cost<STRICT>(C, E, R, g, nullptr, fx, dgdummy, tid);
@@ -609,6 +609,7 @@ __device__ void lbfgs_run(const VigoConst& C, EvalCtx& E, double* sm, tp_lbfgs_r
       const double ys = yv[0], yy = yv[1];
       if (tid == 0) YS[end] = ys;  // read back only by this thread's registers below (broadcast via ysj)
       const int bound = (m <= k) ? m : k;
+      bsum += bound;
       ++k;
       end = (end + 1) % m;
       for (int e = tid; e < n; e += TP_LB_THREADS) d[e] = -g[e];
@@ -655,7 +656,7 @@ __device__ void lbfgs_run(const VigoConst& C, EvalCtx& E, double* sm, tp_lbfgs_r
   out.ret = ret;
   out.iters = k;
   out.evals = evals;
-  out.reserved = 0;
+  out.reserved = bsum;  // sum of two-loop depths (flop accounting)
   out.fx = fx;
   __syncthreads();
 }

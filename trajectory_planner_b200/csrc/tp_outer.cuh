@@ -27,10 +27,11 @@
 // per-warp working set
 struct Worker {
   ANode* nodes;
-  uint32_t* heap;
-  double* path;   // xyz, path_cap points
-  double* sc;     // max_seg x TP_SC_CAP x 3
-  int* sc_len;    // max_seg
+  HeapEnt* heap_sm;  // shared, TP_HEAP_SMEM entries
+  HeapEnt* heap_gl;  // HBM spill for entries >= TP_HEAP_SMEM
+  double* path;      // xyz, path_cap points
+  double* sc;        // max_seg x TP_SC_CAP x 3
+  int* sc_len;       // max_seg
   uint32_t* round_ptr;
   int lane;
 };
@@ -69,55 +70,75 @@ __device__ __forceinline__ double as_heu(int i, int j, int k, int ei, int ej, in
   const double tie = 1.0 + 1.0 / 10000;
   return tie * h;
 }
-// Only the z layers whose cell centre can lie inside [min_height, max_height] are stored
-// (pool_kl of them, starting at k_lo): cells outside the band are rejected before any node state
-// is consulted (astarOcc.cpp:202), so they never need storage.
-__device__ __forceinline__ size_t as_lin(const VigoConst& C, const AStarFrame& F, int i, int j, int k) {
-  return ((size_t)i * C.pool[1] + j) * C.pool_kl + (k - F.k_lo);
-}
 
-// ---- libstdc++ heap mechanics (std::priority_queue without decrease-key, astarOcc.cpp:150-228)
-// comp(a,b) = a->fScore > b->fScore; keys are read at comparison time because the reference
-// mutates fScore in place.
-__device__ __forceinline__ void heap_sift_up(const ANode* nodes, uint32_t* heap, int hole, int top, uint32_t value) {
-  const double fv = nodes[value].f;
-  int parent = (hole - 1) / 2;
-  while (hole > top && nodes[heap[parent]].f > fv) {
-    heap[hole] = heap[parent];
-    hole = parent;
-    parent = (hole - 1) / 2;
+// ---- libstdc++ heap mechanics (std::priority_queue without decrease-key, astarOcc.cpp:150-228).
+// comp(a,b) = a->fScore > b->fScore with keys read at comparison time; here the key lives in the
+// heap entry and is patched whenever the reference mutates fScore in place, so every comparison
+// sees exactly the value the reference would read through the node pointer.
+struct Heap {
+  HeapEnt* sm;
+  HeapEnt* gl;
+  ANode* nodes;
+  int size;
+  __device__ __forceinline__ HeapEnt get(int i) const { return i < TP_HEAP_SMEM ? sm[i] : gl[i - TP_HEAP_SMEM]; }
+  __device__ __forceinline__ double key(int i) const { return i < TP_HEAP_SMEM ? sm[i].f : gl[i - TP_HEAP_SMEM].f; }
+  __device__ __forceinline__ void put(int i, const HeapEnt& e) {
+    if (i < TP_HEAP_SMEM) sm[i] = e; else gl[i - TP_HEAP_SMEM] = e;
+    nodes[e.node].heap_pos = (uint32_t)i;
   }
-  heap[hole] = value;
-}
-__device__ __forceinline__ void heap_push(const ANode* nodes, uint32_t* heap, int& size, uint32_t value) {
-  heap_sift_up(nodes, heap, size, 0, value);
-  ++size;
-}
-__device__ __forceinline__ uint32_t heap_pop(const ANode* nodes, uint32_t* heap, int& size) {
-  const uint32_t top = heap[0];
-  if (size > 1) {
-    const uint32_t value = heap[size - 1];
-    const int len = size - 1;
-    int hole = 0, second = 0;
-    while (second < (len - 1) / 2) {
-      second = 2 * (second + 1);
-      if (nodes[heap[second]].f > nodes[heap[second - 1]].f) second--;
-      heap[hole] = heap[second];
-      hole = second;
-    }
-    if ((len & 1) == 0 && second == (len - 2) / 2) {
-      second = 2 * (second + 1);
-      heap[hole] = heap[second - 1];
-      hole = second - 1;
-    }
-    heap_sift_up(nodes, heap, hole, 0, value);
+  __device__ __forceinline__ void set_key(int i, double f) {
+    if (i < TP_HEAP_SMEM) sm[i].f = f; else gl[i - TP_HEAP_SMEM].f = f;
   }
-  --size;
-  return top;
-}
+  // std::__push_heap
+  __device__ __forceinline__ void sift_up(int hole, int top, const HeapEnt& value) {
+    int parent = (hole - 1) / 2;
+    while (hole > top && key(parent) > value.f) {
+      put(hole, get(parent));
+      hole = parent;
+      parent = (hole - 1) / 2;
+    }
+    put(hole, value);
+  }
+  __device__ __forceinline__ void push(uint32_t node, double f) {
+    HeapEnt e;
+    e.f = f; e.node = node; e.pad = 0;
+    sift_up(size, 0, e);
+    ++size;
+  }
+  // top() + std::pop_heap (= __adjust_heap on the hole at the root, then __push_heap) + pop_back
+  __device__ __forceinline__ uint32_t pop() {
+    const uint32_t top = get(0).node;
+    if (size > 1) {
+      const HeapEnt value = get(size - 1);
+      const int len = size - 1;
+      int hole = 0, second = 0;
+      while (second < (len - 1) / 2) {
+        second = 2 * (second + 1);
+        if (key(second) > key(second - 1)) second--;
+        put(hole, get(second));
+        hole = second;
+      }
+      if ((len & 1) == 0 && second == (len - 2) / 2) {
+        second = 2 * (second + 1);
+        put(hole, get(second - 1));
+        hole = second - 1;
+      }
+      sift_up(hole, 0, value);
+    }
+    --size;
+    return top;
+  }
+};
 
 // AStar::AstarSearch + getPath.  Returns the number of path points written to W.path (cell centres
 // start -> goal) or -1.  All 32 lanes call it with identical arguments.
+//
+// Node storage: only the z layers whose cell centre can lie inside [min_height, max_height] are
+// stored (pool_kl of them, starting at k_lo) — cells outside the band are rejected before any node
+// state is consulted (astarOcc.cpp:202) — plus one spare slot for the start cell, which the
+// reference expands from even when it lies outside the band.  Per expansion the warp makes ONE
+// round of global loads (current node, <= 26 neighbour nodes as LDG.128, <= 26 map words, all in
+// flight together); the open-set heap lives in shared memory.
 __device__ int astar_search(const DevMap& map, const VigoConst& C, Worker& W, const D3& start_in, const D3& end_in,
                             int& expansions, int& err) {
   const int lane = W.lane;
@@ -133,9 +154,8 @@ __device__ int astar_search(const DevMap& map, const VigoConst& C, Worker& W, co
   round = __shfl_sync(0xffffffffu, round, 0);
   F.round = round;
   expansions = 0;
-  // height band -> stored layers: smallest k with (k - CZ)*step + center.z >= min_height, found
-  // with the reference's own expression so the decision per cell is identical
   {
+    // smallest k with (k - CZ)*step + center.z >= min_height, found with the reference's expression
     int k = (int)floor((C.p.min_height - F.center.z) * F.inv_step) + C.pool[2] / 2 - 1;
     if (k < 0) k = 0;
     while (k < C.pool[2] && (double)(k - C.pool[2] / 2) * F.step + F.center.z < C.p.min_height) ++k;
@@ -165,54 +185,55 @@ __device__ int astar_search(const DevMap& map, const VigoConst& C, Worker& W, co
   if (!ok) return -1;
   si = __shfl_sync(0xffffffffu, si, 0); sj = __shfl_sync(0xffffffffu, sj, 0); sk = __shfl_sync(0xffffffffu, sk, 0);
   ei = __shfl_sync(0xffffffffu, ei, 0); ej = __shfl_sync(0xffffffffu, ej, 0); ek = __shfl_sync(0xffffffffu, ek, 0);
-  // The start cell may sit outside the height band (the reference still expands from it); it is the
-  // only such cell that needs node storage, so it gets the spare slot after the pool.
-  const size_t spare = (size_t)C.pool[0] * C.pool[1] * C.pool_kl;
+  const int PY = C.pool[1], KL = C.pool_kl;
+  const uint32_t spare = (uint32_t)((size_t)C.pool[0] * PY * KL);
+  const int k_lo = F.k_lo;
   auto lin_of = [&](int i, int j, int k) -> uint32_t {
-    if (i == si && j == sj && k == sk) return (uint32_t)spare;
-    return (uint32_t)as_lin(C, F, i, j, k);
+    if (i == si && j == sj && k == sk) return spare;
+    return (uint32_t)(((size_t)i * PY + j) * KL + (k - k_lo));
   };
-  auto in_band_layers = [&](int k) -> bool { return k >= F.k_lo && k < F.k_lo + C.pool_kl; };
+  auto ijk_of = [&](uint32_t lin, int& i, int& j, int& k) {
+    if (lin == spare) { i = si; j = sj; k = sk; return; }
+    k = (int)(lin % (uint32_t)KL) + k_lo;
+    const uint32_t r = lin / (uint32_t)KL;
+    j = (int)(r % (uint32_t)PY);
+    i = (int)(r / (uint32_t)PY);
+  };
   ANode* nodes = W.nodes;
-  uint32_t* heap = W.heap;
-  int hsize = 0;
-  const uint32_t start_lin = (uint32_t)spare;
-  // a goal outside the height band can never be reached (astarOcc.cpp:202 rejects it as a
-  // neighbour) unless it is the start cell itself
-  const bool goal_is_start = (si == ei && sj == ej && sk == ek);
+  Heap H;
+  H.sm = W.heap_sm;
+  H.gl = W.heap_gl;
+  H.nodes = nodes;
+  H.size = 0;
   if (lane == 0) {
     ANode nd;
     nd.stamp_state = (round << 2) | ST_OPEN;
     nd.parent = NODE_NONE;
     nd.g = 0;
-    nd.f = as_heu(si, sj, sk, ei, ej, ek);
-    nd.pad = ((uint64_t)(uint32_t)si) | ((uint64_t)(uint32_t)sj << 20) | ((uint64_t)(uint32_t)sk << 40);
-    nodes[start_lin] = nd;
-    heap[0] = start_lin;
-    hsize = 1;
+    nd.heap_pos = 0; nd.pad0 = 0; nd.pad1 = 0;
+    nodes[spare] = nd;
+    H.push(spare, as_heu(si, sj, sk, ei, ej, ek));
   }
   __syncwarp();
   int result = -1;
   int num_iter = 0;
   uint32_t goal_lin = NODE_NONE;
   for (;;) {
-    // ---- pop (lane 0)
+    // ---- pop (lane 0, shared memory)
     uint32_t cur = NODE_NONE;
-    if (lane == 0 && hsize > 0) cur = heap_pop(nodes, heap, hsize);
+    if (lane == 0 && H.size > 0) cur = H.pop();
     cur = __shfl_sync(0xffffffffu, cur, 0);
     if (cur == NODE_NONE) break;  // open set empty
     ++num_iter;
-    // node -> (i,j,k): kept in the node's pad word
-    const uint64_t packed = nodes[cur].pad;
-    const int ci = (int)(packed & 0xFFFFF), cj = (int)((packed >> 20) & 0xFFFFF), ck = (int)((packed >> 40) & 0xFFFFF);
+    int ci, cj, ck;
+    ijk_of(cur, ci, cj, ck);
     if (ci == ei && cj == ej && ck == ek) {
       goal_lin = cur;
       result = 0;
       break;
     }
-    const double gcur = nodes[cur].g;
+    const double gcur = nodes[cur].g;  // uniform address: one broadcast load, overlaps the loads below
     if (lane == 0) nodes[cur].stamp_state = (round << 2) | ST_CLOSED;
-    __syncwarp();
     // ---- lane-parallel neighbour evaluation (astarOcc.cpp:173-229); lane L <-> (dx,dy,dz) in the
     // reference's loop order
     int kind = 0;  // 0 skip, 1 push (new node), 2 in-place update
@@ -221,36 +242,39 @@ __device__ int astar_search(const DevMap& map, const VigoConst& C, Worker& W, co
     if (lane < 27 && lane != 13) {
       const int dx = lane / 9 - 1, dy = (lane / 3) % 3 - 1, dz = lane % 3 - 1;
       const int ni = ci + dx, nj = cj + dy, nk = ck + dz;
-      const bool inb = !(ni < 1 || ni >= C.pool[0] - 1 || nj < 1 || nj >= C.pool[1] - 1 || nk < 1 || nk >= C.pool[2] - 1);
+      const bool inb = !(ni < 1 || ni >= C.pool[0] - 1 || nj < 1 || nj >= PY - 1 || nk < 1 || nk >= C.pool[2] - 1);
       if (inb) {
         const D3 pc = as_index2coord(C, F, ni, nj, nk);
         const bool is_start = (ni == si && nj == sj && nk == sk);
         const bool band = !(pc.z > C.p.max_height || pc.z < C.p.min_height);
+        const bool layer_ok = nk >= k_lo && nk < k_lo + KL;
+        if (band && !layer_ok && !is_start) err |= ERR_BAND;  // cannot happen (pool_kl has slack)
         // cells outside the band are rejected by :202 whatever their node state says, except that a
         // CLOSED start node is skipped one line earlier — same outcome (skip) either way.
-        if (band && !in_band_layers(nk) && !is_start) err |= ERR_BAND;  // cannot happen (pool_kl has slack)
-        if ((band && in_band_layers(nk)) || is_start) {
+        if ((band && layer_ok) || is_start) {
           nl = lin_of(ni, nj, nk);
-          const uint32_t meta = nodes[nl].stamp_state;
-          const bool explored = (meta >> 2) == round;
-          const uint32_t state = meta & 3u;
+          const uint4 raw = *reinterpret_cast<const uint4*>(&nodes[nl]);  // stamp_state, parent, g
+          const bool blocked_map = band ? dm_inflated(map, pc) : true;   // issued before `raw` is consumed
+          const bool explored = (raw.x >> 2) == round;
+          const uint32_t state = raw.x & 3u;
           if (!(explored && state == ST_CLOSED)) {
-            if (!band || dm_inflated(map, pc)) {
+            if (blocked_map) {
               // blocked this round: remember it so the map is not queried again (observably the same
               // as the reference's stale-state handling: the cell is skipped on every visit)
               nodes[nl].stamp_state = (round << 2) | ST_CLOSED;
             } else {
               tentative = gcur + sqrt((double)(dx * dx + dy * dy + dz * dz));
+              const double gold = __hiloint2double((int)raw.w, (int)raw.z);
               if (!explored) {
                 kind = 1;
-                ANode nd;
-                nd.stamp_state = (round << 2) | ST_OPEN;
-                nd.parent = cur;
-                nd.g = tentative;
-                nd.f = tentative + as_heu(ni, nj, nk, ei, ej, ek);
-                nd.pad = ((uint64_t)(uint32_t)ni) | ((uint64_t)(uint32_t)nj << 20) | ((uint64_t)(uint32_t)nk << 40);
-                nodes[nl] = nd;
-              } else if (tentative < nodes[nl].g) {
+                fnew = tentative + as_heu(ni, nj, nk, ei, ej, ek);
+                uint4 w;
+                w.x = (round << 2) | ST_OPEN;
+                w.y = cur;
+                w.z = (uint32_t)__double2loint(tentative);
+                w.w = (uint32_t)__double2hiint(tentative);
+                *reinterpret_cast<uint4*>(&nodes[nl]) = w;
+              } else if (tentative < gold) {
                 kind = 2;
                 fnew = tentative + as_heu(ni, nj, nk, ei, ej, ek);
               }
@@ -262,32 +286,33 @@ __device__ int astar_search(const DevMap& map, const VigoConst& C, Worker& W, co
     __syncwarp();
     // ---- serial pass in the reference's neighbour order: in-place key updates and pushes
     unsigned mask = __ballot_sync(0xffffffffu, kind != 0);
+    int overflow = 0;
     while (mask) {
       const int L = __ffs(mask) - 1;
       mask &= mask - 1;
       const int kL = __shfl_sync(0xffffffffu, kind, L);
       const uint32_t nL = __shfl_sync(0xffffffffu, nl, L);
+      const double fL = __shfl_sync(0xffffffffu, fnew, L);
       if (kL == 2) {
-        if (lane == L) {
-          nodes[nl].parent = cur;
-          nodes[nl].g = tentative;
-          nodes[nl].f = fnew;
+        const double tL = __shfl_sync(0xffffffffu, tentative, L);
+        if (lane == 0) {
+          nodes[nL].parent = cur;
+          nodes[nL].g = tL;
+          H.set_key((int)nodes[nL].heap_pos, fL);
         }
       } else if (lane == 0) {
-        if (hsize >= C.heap_cap) err |= ERR_HEAP_OVERFLOW;
-        else heap_push(nodes, heap, hsize, nL);
+        if (H.size >= C.heap_cap) overflow = 1;
+        else H.push(nL, fL);
       }
       __syncwarp();
     }
-    const int overflow = __any_sync(0xffffffffu, (err & (ERR_HEAP_OVERFLOW | ERR_BAND)) != 0);
-    if (overflow) {
+    if (__any_sync(0xffffffffu, overflow != 0 || (err & ERR_BAND) != 0)) {
       err |= ERR_HEAP_OVERFLOW;
       break;
     }
     if (C.p.astar_max_expansions > 0 && num_iter >= C.p.astar_max_expansions) break;
   }
   expansions = num_iter;
-  (void)goal_is_start;
   if (result < 0) return -1;
   // ---- retrievePath + getPath (astarOcc.cpp:77-88, 246-254), lane 0
   int len = 0;
@@ -304,8 +329,9 @@ __device__ int astar_search(const DevMap& map, const VigoConst& C, Worker& W, co
       p = goal_lin;
       int w = len - 1;
       while (p != NODE_NONE) {
-        const uint64_t pk = nodes[p].pad;
-        const D3 c = as_index2coord(C, F, (int)(pk & 0xFFFFF), (int)((pk >> 20) & 0xFFFFF), (int)((pk >> 40) & 0xFFFFF));
+        int i, j, k;
+        ijk_of(p, i, j, k);
+        const D3 c = as_index2coord(C, F, i, j, k);
         W.path[3 * w] = c.x;
         W.path[3 * w + 1] = c.y;
         W.path[3 * w + 2] = c.z;
@@ -385,7 +411,7 @@ __device__ int shortcut_path(const DevMap& map, const VigoConst& C, const BatchV
 }
 
 // utils.h:84-86
-__device__ __forceinline__ double angle_between(const D3& a, const D3& b) { return atan2(norm3(cross3(a, b)), dot3(a, b)); }
+__device__ __forceinline__ double angle_between(const D3& a, const D3& b) { return tp_atan2(norm3(cross3(a, b)), dot3(a, b)); }
 
 // bsplineTraj::findGuidePointSemiCircle (bsplineTraj.h:251-304), serial (lane 0)
 __device__ bool find_guide_point(int cpIdx, int segFirst, int segSecond, const double* path, int plen, D3& guide) {
@@ -547,6 +573,7 @@ __device__ int path_search(const DevMap& map, const VigoConst& C, const BatchVie
     if (lane == 0) {
       st.astar_searches += 1;
       st.astar_expansions += ex;
+      st.vclock += 30LL * ex;
     }
     if (len < 0) return false;
     // searchedPath[0] = pStart; push_back(pEnd)  (:457-458)

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -52,6 +53,7 @@ __global__ void k_init_states(BatchView bv, VigoConst C) {
   st.err = 0;
   st.lbfgs_runs = st.lbfgs_iters = st.lbfgs_evals = st.last_ret = 0;
   st.astar_searches = st.astar_expansions = 0;
+  st.vclock = 0;
   st.w_dist = C.p.w_distance;
   st.w_dyn = C.p.w_dyn;
   st.final_cost = 0;
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(TP_LB_THREADS) k_cost(BatchView bv, VigoConst 
 template <bool STRICT>
 __global__ void __launch_bounds__(TP_LB_THREADS) k_lbfgs(BatchView bv, VigoConst C, const int* __restrict__ active,
                                                          const int* __restrict__ n_active, tp_lbfgs_result* res_out,
-                                                         double* xfinal_out) {
+                                                         double* xfinal_out, double* counters) {
   extern __shared__ double sm[];
   if ((int)blockIdx.x >= *n_active) return;
   const int b = active[blockIdx.x], tid = threadIdx.x;
@@ -130,7 +132,15 @@ __global__ void __launch_bounds__(TP_LB_THREADS) k_lbfgs(BatchView bv, VigoConst
     st.lbfgs_evals += r.evals;
     st.last_ret = r.ret;
     st.final_cost = r.fx;
+    if (n > 0) st.vclock += (long long)r.evals * (10LL * N + 2LL * n);
     if (res_out) res_out[b] = r;
+    if (counters && n > 0) {
+      // algorithmic FP64 flops: E(81N + 21G + 4n) + sum_k (8 b_k + 15) n
+      const double fl = (double)r.evals * (81.0 * N + 21.0 * st.n_pairs + 4.0 * n) + (8.0 * r.reserved + 15.0 * r.iters) * n;
+      atomicAdd(&counters[0], fl);
+      atomicAdd(&counters[1], (double)r.iters);
+      atomicAdd(&counters[2], (double)r.evals);
+    }
   }
 }
 
@@ -141,7 +151,8 @@ struct SmemCP {
 };
 __global__ void __launch_bounds__(TP_LB_THREADS) k_has_collision(BatchView bv, VigoConst C, DevMap map,
                                                                  const int* __restrict__ active,
-                                                                 const int* __restrict__ n_active, uint8_t* hit_out) {
+                                                                 const int* __restrict__ n_active, uint8_t* hit_out,
+                                                                 double* counters) {
   extern __shared__ double sm[];
   if ((int)blockIdx.x >= *n_active) return;
   const int b = active[blockIdx.x], tid = threadIdx.x;
@@ -174,6 +185,7 @@ __global__ void __launch_bounds__(TP_LB_THREADS) k_has_collision(BatchView bv, V
   if (tid == 0) {
     st.has_col = any;
     if (hit_out) hit_out[b] = (uint8_t)(any & 1);
+    if (counters) atomicAdd(&counters[3], floor(duration / C.check_ts) + 1.0);
   }
 }
 
@@ -230,15 +242,17 @@ __global__ void __launch_bounds__(TP_LB_THREADS) k_reparam(BatchView bv, VigoCon
 
 // ---- outer loop: one warp (= one block) per worker, trajectories pulled from a queue
 struct PlanSmem {
+  HeapEnt heap[TP_HEAP_SMEM];
   uint8_t hit[TP_MAX_CTRL];
   uint8_t line[TP_MAX_CTRL];
   int segA[TP_MAX_SEG_HARD][2];
   int segB[TP_MAX_SEG_HARD][2];
 };
-__device__ __forceinline__ Worker make_worker(const VigoConst& C, const AStarPools& P, int w, int lane) {
+__device__ __forceinline__ Worker make_worker(const VigoConst& C, const AStarPools& P, int w, int lane, HeapEnt* heap_sm) {
   Worker W;
   W.nodes = P.nodes + (size_t)w * (P.pool_nodes + 1);
-  W.heap = P.heaps + (size_t)w * C.heap_cap;
+  W.heap_sm = heap_sm;
+  W.heap_gl = P.heaps + (size_t)w * C.heap_cap;
   W.path = P.paths + (size_t)w * C.path_cap * 3;
   W.sc = P.sc + (size_t)w * C.max_seg * TP_SC_CAP * 3;
   W.sc_len = P.sc_len + (size_t)w * C.max_seg;
@@ -252,7 +266,7 @@ __global__ void __launch_bounds__(32) k_plan_init(BatchView bv, VigoConst C, Dev
                                                   int* active_out, int* n_active_out) {
   __shared__ PlanSmem S;
   const int lane = threadIdx.x;
-  Worker W = make_worker(C, P, blockIdx.x, lane);
+  Worker W = make_worker(C, P, blockIdx.x, lane, S.heap);
   for (;;) {
     int b = 0;
     if (lane == 0) b = atomicAdd(queue, 1);
@@ -288,7 +302,7 @@ __global__ void __launch_bounds__(32) k_plan_step(BatchView bv, VigoConst C, Dev
   __shared__ PlanSmem S;
   __shared__ int prevSeg[TP_MAX_SEG_HARD][2];
   const int lane = threadIdx.x;
-  Worker W = make_worker(C, P, blockIdx.x, lane);
+  Worker W = make_worker(C, P, blockIdx.x, lane, S.heap);
   const int n_in = *n_active_in;
   for (;;) {
     int q = 0;
@@ -307,7 +321,10 @@ __global__ void __launch_bounds__(32) k_plan_step(BatchView bv, VigoConst C, Dev
       }
       continue;
     }
-    if (st.round >= C.p.max_outer_rounds) {  // replaces the 0.03 s wall clock (:633)
+    if (st.round == 0 && lane == 0) st.vclock = 0;  // the reference starts its timer after the first optimize() (:618)
+    __syncwarp();
+    // deterministic replacements of the 0.03 s wall clock (:632-638): virtual clock + round cap
+    if (st.round >= C.p.max_outer_rounds || (C.p.vclock_budget > 0 && st.vclock > (long long)C.p.vclock_budget)) {
       if (lane == 0) {
         st.w_dist = C.p.w_distance;
         st.w_dyn = C.p.w_dyn;
@@ -395,8 +412,9 @@ __global__ void __launch_bounds__(32) k_plan_step(BatchView bv, VigoConst C, Dev
 __global__ void __launch_bounds__(32) k_astar(VigoConst C, DevMap map, AStarPools P, int* queue, int S_,
                                               const double* __restrict__ starts, const double* __restrict__ ends,
                                               int* path_len, double* paths, int* expansions) {
+  __shared__ HeapEnt heap_sm[TP_HEAP_SMEM];
   const int lane = threadIdx.x;
-  Worker W = make_worker(C, P, blockIdx.x, lane);
+  Worker W = make_worker(C, P, blockIdx.x, lane, heap_sm);
   for (;;) {
     int s = 0;
     if (lane == 0) s = atomicAdd(queue, 1);
@@ -507,6 +525,39 @@ struct tp_engine {
   size_t h_stage_cap = 0;
   bool lbfgs_attr_set = false;
   int max_smem_optin = 0;
+  // measurement
+  bool profile = false;
+  DevBuf dev_counters;  // 8 doubles
+  struct ProfEntry { int kind; int n; cudaEvent_t a, b; };
+  std::vector<ProfEntry> prof_entries;
+  std::vector<cudaEvent_t> ev_pool;
+  double query_points = 0;
+  double* counters_ptr() { return profile ? dev_counters.as<double>() : nullptr; }
+};
+
+// RAII per-launch timer: records two events around a launch when profiling is on
+struct ProfScope {
+  tp_engine* e;
+  cudaStream_t s;
+  cudaEvent_t b = nullptr;
+  int kind;
+  ProfScope(tp_engine* e_, int kind_, cudaStream_t s_, int n_ = 0) : e(e_), s(s_), kind(kind_) {
+    if (!e->profile) return;
+    cudaEvent_t a;
+    auto get = [&]() {
+      cudaEvent_t ev;
+      if (!e->ev_pool.empty()) { ev = e->ev_pool.back(); e->ev_pool.pop_back(); }
+      else cudaEventCreate(&ev);
+      return ev;
+    };
+    a = get();
+    b = get();
+    cudaEventRecord(a, s);
+    e->prof_entries.push_back({kind, n_, a, b});
+  }
+  ~ProfScope() {
+    if (b) cudaEventRecord(b, s);
+  }
 };
 
 static int ensure_stage(tp_engine* e, size_t bytes) {
@@ -605,7 +656,7 @@ static int ensure_pools(tp_engine* e, const VigoConst& C) {
   const int key[8] = {C.pool[0], C.pool[1], C.pool_kl, C.heap_cap, C.path_cap, C.max_seg, 0, 0};
   if (memcmp(key, e->pools_key, sizeof(key)) == 0 && e->pools.workers > 0) return TP_OK;
   const size_t pool_nodes = (size_t)C.pool[0] * C.pool[1] * C.pool_kl;
-  const size_t per_worker = (pool_nodes + 1) * sizeof(ANode) + (size_t)C.heap_cap * 4 + (size_t)C.path_cap * 24 +
+  const size_t per_worker = (pool_nodes + 1) * sizeof(ANode) + (size_t)C.heap_cap * sizeof(HeapEnt) + (size_t)C.path_cap * 24 +
                             (size_t)C.max_seg * TP_SC_CAP * 24 + (size_t)C.max_seg * 4 + 4;
   int workers = e->cfg.astar_workers;
   if (workers <= 0) {
@@ -613,21 +664,22 @@ static int ensure_pools(tp_engine* e, const VigoConst& C) {
     size_t freeb = 0, totalb = 0;
     cudaMemGetInfo(&freeb, &totalb);
     double use = std::min(budget, 0.5 * (double)freeb);
-    workers = (int)std::min<double>(use / (double)per_worker, (double)e->sm_count * 32);
+    workers = (int)std::min<double>(use / (double)per_worker, (double)e->sm_count * 11);
     workers = (workers / e->sm_count) * e->sm_count;
     if (workers < e->sm_count) workers = std::max(1, (int)(use / (double)per_worker));
   }
   if (workers < 1) workers = 1;
   if (e->pool_nodes.ensure((size_t)workers * (pool_nodes + 1) * sizeof(ANode)) != TP_OK) return TP_ERR_CUDA;
-  if (e->pool_heaps.ensure((size_t)workers * C.heap_cap * 4) != TP_OK) return TP_ERR_CUDA;
+  if (e->pool_heaps.ensure((size_t)workers * C.heap_cap * sizeof(HeapEnt)) != TP_OK) return TP_ERR_CUDA;
   if (e->pool_paths.ensure((size_t)workers * C.path_cap * 24) != TP_OK) return TP_ERR_CUDA;
   if (e->pool_sc.ensure((size_t)workers * C.max_seg * TP_SC_CAP * 24) != TP_OK) return TP_ERR_CUDA;
   if (e->pool_sclen.ensure((size_t)workers * C.max_seg * 4) != TP_OK) return TP_ERR_CUDA;
   if (e->pool_rounds.ensure((size_t)workers * 4) != TP_OK) return TP_ERR_CUDA;
   CK(cudaMemsetAsync(e->pool_nodes.p, 0, (size_t)workers * (pool_nodes + 1) * sizeof(ANode), e->stream));
   CK(cudaMemsetAsync(e->pool_rounds.p, 0, (size_t)workers * 4, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
   e->pools.nodes = e->pool_nodes.as<ANode>();
-  e->pools.heaps = e->pool_heaps.as<uint32_t>();
+  e->pools.heaps = e->pool_heaps.as<HeapEnt>();
   e->pools.paths = e->pool_paths.as<double>();
   e->pools.sc = e->pool_sc.as<double>();
   e->pools.sc_len = e->pool_sclen.as<int>();
@@ -814,6 +866,7 @@ void tp_vigo_default_params(tp_vigo_params* p) {
   p->lbfgs_g_eps = 0.01; p->plan_in_z = 0; p->lbfgs_m = 16; p->lbfgs_max_iter = 200;
   p->lbfgs_max_linesearch = 40; p->max_outer_rounds = 24; p->astar_max_expansions = 200000;
   p->strict_order = 0;
+  p->vclock_budget = 3000000;
 }
 
 tp_engine_t* tp_engine_create(int device, const tp_engine_cfg* cfg) {
@@ -919,8 +972,12 @@ static int query_common(tp_engine_t* e, int64_t n, const double* a, const double
   }
   const int threads = 256;
   const long blocks = std::min<long>((n + threads - 1) / threads, (long)e->sm_count * 8);
-  if (kind == 2) k_query_lines<<<(int)blocks, threads, 0, s>>>(e->dmap, (long)n, da, db, dout);
-  else k_query_points<<<(int)blocks, threads, 0, s>>>(e->dmap, (long)n, da, dout, kind);
+  {
+    ProfScope ps(e, 5, s);
+    if (kind == 2) k_query_lines<<<(int)blocks, threads, 0, s>>>(e->dmap, (long)n, da, db, dout);
+    else k_query_points<<<(int)blocks, threads, 0, s>>>(e->dmap, (long)n, da, dout, kind);
+  }
+  e->query_points += (double)n;
   e->launches += 1;
   CK(cudaGetLastError());
   if (mem == TP_MEM_HOST) {
@@ -1001,10 +1058,10 @@ int tp_vigo_optimize_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, c
   if (rc != TP_OK) return rc;
   if (p->strict_order)
     k_lbfgs<true><<<B, TP_LB_THREADS, smem, s>>>(bs.bv, bs.C, e->active[0].as<int>(), e->counters.as<int>(),
-                                                  e->results.as<tp_lbfgs_result>(), x_final ? e->scratch_b.as<double>() : nullptr);
+                                                  e->results.as<tp_lbfgs_result>(), x_final ? e->scratch_b.as<double>() : nullptr, nullptr);
   else
     k_lbfgs<false><<<B, TP_LB_THREADS, smem, s>>>(bs.bv, bs.C, e->active[0].as<int>(), e->counters.as<int>(),
-                                                   e->results.as<tp_lbfgs_result>(), x_final ? e->scratch_b.as<double>() : nullptr);
+                                                   e->results.as<tp_lbfgs_result>(), x_final ? e->scratch_b.as<double>() : nullptr, nullptr);
   e->launches += 2;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(ctrl, bs.bv.ctrl, (size_t)bs.total * 24, cudaMemcpyDeviceToHost, s));
@@ -1028,7 +1085,7 @@ int tp_vigo_has_collision_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t
   rc = make_identity_active(e, B, s);
   if (rc != TP_OK) return rc;
   k_has_collision<<<B, TP_LB_THREADS, (size_t)3 * bs.max_n * 8, s>>>(bs.bv, bs.C, e->dmap, e->active[0].as<int>(),
-                                                                      e->counters.as<int>(), e->scratch_c.as<uint8_t>());
+                                                                      e->counters.as<int>(), e->scratch_c.as<uint8_t>(), nullptr);
   e->launches += 1;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(hit, e->scratch_c.p, (size_t)B, cudaMemcpyDeviceToHost, s));
@@ -1100,7 +1157,10 @@ static int run_plan_init(tp_engine* e, BatchSetup& bs, cudaStream_t s) {
   CK(cudaMemsetAsync(e->counters.p, 0, 64 * 4, s));
   int* cnt = e->counters.as<int>();
   const int grid = std::min(e->pools.workers, bs.bv.B);
-  k_plan_init<<<grid, 32, 0, s>>>(bs.bv, bs.C, e->dmap, e->pools, cnt + 1, e->active[0].as<int>(), cnt + 0);
+  {
+    ProfScope ps(e, 3, s);
+    k_plan_init<<<grid, 32, 0, s>>>(bs.bv, bs.C, e->dmap, e->pools, cnt + 1, e->active[0].as<int>(), cnt + 0);
+  }
   e->launches += 1;
   CK(cudaGetLastError());
   return TP_OK;
@@ -1197,18 +1257,27 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
   int n_active = e->h_counters[0];
   for (int r = 0; r < max_rounds && n_active > 0; ++r) {
     // optimize()
-    if (p->strict_order)
-      k_lbfgs<true><<<n_active, TP_LB_THREADS, smem_lb, s>>>(bs.bv, bs.C, e->active[cur].as<int>(), n_cur, nullptr, nullptr);
-    else
-      k_lbfgs<false><<<n_active, TP_LB_THREADS, smem_lb, s>>>(bs.bv, bs.C, e->active[cur].as<int>(), n_cur, nullptr, nullptr);
+    {
+      ProfScope ps(e, 0, s, n_active);
+      if (p->strict_order)
+        k_lbfgs<true><<<n_active, TP_LB_THREADS, smem_lb, s>>>(bs.bv, bs.C, e->active[cur].as<int>(), n_cur, nullptr, nullptr, e->counters_ptr());
+      else
+        k_lbfgs<false><<<n_active, TP_LB_THREADS, smem_lb, s>>>(bs.bv, bs.C, e->active[cur].as<int>(), n_cur, nullptr, nullptr, e->counters_ptr());
+    }
     // hasCollisionTrajectory
-    k_has_collision<<<n_active, TP_LB_THREADS, smem_cp, s>>>(bs.bv, bs.C, e->dmap, e->active[cur].as<int>(), n_cur, nullptr);
+    {
+      ProfScope ps(e, 1, s, n_active);
+      k_has_collision<<<n_active, TP_LB_THREADS, smem_cp, s>>>(bs.bv, bs.C, e->dmap, e->active[cur].as<int>(), n_cur, nullptr, e->counters_ptr());
+    }
     // loop body: success / failure / re-guide / weight doubling
     int* slot = cnt + 2 + 2 * (r % 24);
     CK(cudaMemsetAsync(slot, 0, 8, s));
-    k_plan_step<<<std::min(e->pools.workers, n_active), 32, 0, s>>>(bs.bv, bs.C, e->dmap, e->pools, slot + 1,
-                                                                    e->active[cur].as<int>(), n_cur,
-                                                                    e->active[cur ^ 1].as<int>(), slot);
+    {
+      ProfScope ps(e, 2, s, n_active);
+      k_plan_step<<<std::min(e->pools.workers, n_active), 32, 0, s>>>(bs.bv, bs.C, e->dmap, e->pools, slot + 1,
+                                                                      e->active[cur].as<int>(), n_cur,
+                                                                      e->active[cur ^ 1].as<int>(), slot);
+    }
     e->launches += 3;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(e->h_counters, slot, 4, cudaMemcpyDeviceToHost, s));
@@ -1218,7 +1287,10 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
     cur ^= 1;
   }
   // ---- steps 5-6: time re-parameterisation of the successful trajectories
-  k_reparam<<<B, TP_LB_THREADS, smem_rp, s>>>(bs.bv, bs.C);
+  {
+    ProfScope ps(e, 4, s);
+    k_reparam<<<B, TP_LB_THREADS, smem_rp, s>>>(bs.bv, bs.C);
+  }
   if (e->results.ensure((size_t)B * sizeof(tp_vigo_result)) != TP_OK) return TP_ERR_CUDA;
   tp_vigo_result* dres = mem == TP_MEM_DEVICE ? results : e->results.as<tp_vigo_result>();
   k_collect_results<<<(B + 127) / 128, 128, 0, s>>>(bs.bv, dres);
@@ -1229,6 +1301,125 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
     CK(cudaMemcpyAsync(results, dres, (size_t)B * sizeof(tp_vigo_result), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
   }
+  return TP_OK;
+}
+
+// ---- measurement
+__global__ void k_fp64_fma(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9 + 1.0, a1 = a0 + 0.1, a2 = a0 + 0.2, a3 = a0 + 0.3, a4 = a0 + 0.4, a5 = a0 + 0.5,
+         a6 = a0 + 0.6, a7 = a0 + 0.7;
+  const double m = 0.9999999, c = 1e-7;
+  for (int i = 0; i < iters; ++i) {
+    a0 = __fma_rn(a0, m, c); a1 = __fma_rn(a1, m, c); a2 = __fma_rn(a2, m, c); a3 = __fma_rn(a3, m, c);
+    a4 = __fma_rn(a4, m, c); a5 = __fma_rn(a5, m, c); a6 = __fma_rn(a6, m, c); a7 = __fma_rn(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+__global__ void k_gather32(const uint4* __restrict__ buf, long n_sectors, long per_thread, unsigned long long* sink) {
+  // every thread reads `per_thread` pseudo-random 32 B sectors (two 16 B loads of one sector)
+  unsigned long long x = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull + 12345;
+  unsigned long long acc = 0;
+  for (long i = 0; i < per_thread; ++i) {
+    x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+    const long sidx = (long)(x % (unsigned long long)n_sectors);
+    const uint4 a = __ldg(&buf[2 * sidx]);
+    const uint4 b = __ldg(&buf[2 * sidx + 1]);
+    acc += a.x + b.w;
+  }
+  if (acc == 0xFFFFFFFFFFFFFFFFull) *sink = acc;
+}
+
+int tp_engine_profile_enable(tp_engine_t* e, int on) {
+  if (!e) return TP_ERR_INVALID_ARG;
+  CK(cudaSetDevice(e->device));
+  if (on) {
+    if (e->dev_counters.ensure(8 * 8) != TP_OK) return TP_ERR_CUDA;
+    CK(cudaMemset(e->dev_counters.p, 0, 64));
+  }
+  e->profile = on != 0;
+  return TP_OK;
+}
+int tp_engine_profile_get(tp_engine_t* e, tp_profile* out) {
+  if (!e || !out) return TP_ERR_INVALID_ARG;
+  CK(cudaSetDevice(e->device));
+  CK(cudaDeviceSynchronize());
+  memset(out, 0, sizeof(*out));
+  for (auto& pe : e->prof_entries) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, pe.a, pe.b) == cudaSuccess && pe.kind >= 0 && pe.kind < TP_PROF_KINDS) {
+      out->ms[pe.kind] += ms;
+      out->launches[pe.kind] += 1;
+      if (getenv("TP_PROF_DUMP")) fprintf(stderr, "[tp-prof] kind %d n %d ms %.4f\n", pe.kind, pe.n, ms);
+    }
+    e->ev_pool.push_back(pe.a);
+    e->ev_pool.push_back(pe.b);
+  }
+  e->prof_entries.clear();
+  if (e->dev_counters.p) {
+    double h[8];
+    CK(cudaMemcpy(h, e->dev_counters.p, 64, cudaMemcpyDeviceToHost));
+    out->lbfgs_flops = h[0];
+    out->lbfgs_iters = h[1];
+    out->lbfgs_evals = h[2];
+    out->check_samples = h[3];
+    CK(cudaMemset(e->dev_counters.p, 0, 64));
+  }
+  out->query_points = e->query_points;
+  e->query_points = 0;
+  return TP_OK;
+}
+int tp_microbench_fp64(tp_engine_t* e, double* tflops) {
+  if (!e || !tflops) return TP_ERR_INVALID_ARG;
+  CK(cudaSetDevice(e->device));
+  const int blocks = e->sm_count * 8, threads = 256, iters = 1 << 15;
+  if (e->scratch_a.ensure((size_t)blocks * threads * 8) != TP_OK) return TP_ERR_CUDA;
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  double best = 0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CK(cudaEventRecord(a, e->stream));
+    k_fp64_fma<<<blocks, threads, 0, e->stream>>>(e->scratch_a.as<double>(), iters);
+    CK(cudaEventRecord(b, e->stream));
+    CK(cudaEventSynchronize(b));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    const double fl = 2.0 * 8.0 * (double)iters * blocks * threads;
+    if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  e->launches += 5;
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  *tflops = best;
+  return TP_OK;
+}
+int tp_microbench_gather(tp_engine_t* e, int64_t bytes, double* gbs) {
+  if (!e || !gbs || bytes < 4096) return TP_ERR_INVALID_ARG;
+  CK(cudaSetDevice(e->device));
+  const long n_sectors = bytes / 32;
+  if (e->scratch_b.ensure((size_t)n_sectors * 32) != TP_OK || e->scratch_c.ensure(64) != TP_OK) return TP_ERR_CUDA;
+  CK(cudaMemsetAsync(e->scratch_b.p, 1, (size_t)n_sectors * 32, e->stream));
+  const int blocks = e->sm_count * 16, threads = 256;
+  const long per_thread = 256;
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  double best = 0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CK(cudaEventRecord(a, e->stream));
+    k_gather32<<<blocks, threads, 0, e->stream>>>(e->scratch_b.as<uint4>(), n_sectors, per_thread,
+                                                   e->scratch_c.as<unsigned long long>());
+    CK(cudaEventRecord(b, e->stream));
+    CK(cudaEventSynchronize(b));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    const double by = 32.0 * (double)per_thread * blocks * threads;
+    if (rep > 0) best = std::max(best, by / (ms * 1e-3) / 1e9);
+  }
+  e->launches += 5;
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  *gbs = best;
   return TP_OK;
 }
 

@@ -35,6 +35,7 @@ struct TrajState {
   int lbfgs_runs, lbfgs_iters, lbfgs_evals, last_ret;
   int astar_searches, astar_expansions;
   int pad;
+  long long vclock;         // virtual clock (tp_vigo_params::vclock_budget)
   double w_dist, w_dyn;     // weightDistance_, weightDynamicObstacle_ (mutated by the outer loop)
   double final_cost, linear_factor;
   int seg[TP_MAX_SEG_HARD][2];
@@ -55,12 +56,22 @@ struct VigoConst {
   int n_t_check, n_t_reparam, n_a_line;
 };
 
-struct ANode {  // one A* grid node (astarOcc.h:16-31), 32 B = one sector
+struct ANode {  // one A* grid node (astarOcc.h:16-31), 32 B = one sector; first 16 B = one LDG.128
   uint32_t stamp_state;  // (round << 2) | state
   uint32_t parent;
-  double g, f;
-  uint64_t pad;
+  double g;
+  uint32_t heap_pos;     // position of this node's entry in the open-set heap (valid while OPEN)
+  uint32_t pad0;
+  uint64_t pad1;
 };
+// open-set heap entry: the key is cached beside the node id so that the sift loops never leave
+// shared memory; in-place key updates (astarOcc.cpp:223-228) patch the cached copy via heap_pos.
+struct HeapEnt {
+  double f;
+  uint32_t node;
+  uint32_t pad;
+};
+#define TP_HEAP_SMEM 1024  // heap entries kept in shared memory per search; the rest spills to HBM
 
 struct BatchView {
   int B;
@@ -82,7 +93,7 @@ struct BatchView {
 
 struct AStarPools {
   ANode* nodes;        // [workers * pool_nodes]
-  uint32_t* heaps;     // [workers * heap_cap]
+  HeapEnt* heaps;      // [workers * heap_cap]   spill area for heap entries >= TP_HEAP_SMEM
   double* paths;       // [workers * path_cap * 3]
   double* sc;          // [workers * max_seg * TP_SC_CAP * 3]   shortcut paths
   int* sc_len;         // [workers * max_seg]
