@@ -1,0 +1,228 @@
+"""CPU tests of the ORACLE (test infrastructure): pinned to the reference's own solver/lbfgs.hpp, to the
+committed golden vectors, and to analytic known answers.  The reference holds no golden vectors for this
+path, so the pins are: (1) oracle/_ref = the restatement linked against the reference's
+lbfgs.hpp, (2) tests/golden/vigo_golden.npz generated from (1) by tools/make_golden.py, (3) KATs."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import make_problems, oracle_map_from, traj
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden", "vigo_golden.npz")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "liborc_ref.so")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+def test_oracle_reproduces_golden_vectors(orc, sq_omap, gold):
+    """The oracle with ITS OWN L-BFGS port reproduces, bit for bit, vectors generated through the
+    reference's lbfgs.hpp: cost/gradient, one optimize(), collision decisions, the whole makePlan."""
+    off, ctrl, pert = gold["offsets"], gold["ctrl"], gold["ctrl_perturbed"]
+    B = len(off) - 1
+    for soft in (0, 1):
+        tag = f"soft{soft}"
+        po = sq_omap.lib.default_params()
+        po.soft_atan2 = soft
+        g_off = gold[f"{tag}_g_off"]
+        gpos = 0
+        for b in range(B):
+            c = ctrl[off[b]:off[b + 1]]
+            pl = orc.Planner(sq_omap, po)
+            pl.set_ctrl(c)
+            assert int(pl.has_collision()) == gold["has_collision"][b]
+            pl.init_guides()
+            cp, gp, gv = pl.get_guides()
+            sl = slice(g_off[b], g_off[b + 1])
+            assert np.array_equal(cp, gold[f"{tag}_g_cp"][sl])
+            assert np.array_equal(gp, gold[f"{tag}_g_p"][sl]) and np.array_equal(gv, gold[f"{tag}_g_v"][sl])
+            pc = pert[off[b]:off[b + 1]]
+            pl2 = orc.Planner(sq_omap, po)
+            pl2.set_ctrl(pc)
+            pl2.add_guides(cp, gp, gv)
+            f, g, _ = pl2.cost(pc[3:-3].ravel())
+            assert f == gold[f"{tag}_cost"][b]
+            assert np.array_equal(g, gold[f"{tag}_grad"][gpos:gpos + len(g)])
+            gpos += len(g)
+            o = pl.optimize()
+            # (the reference's lbfgs_optimize does not report its iteration count: golden iters = -1)
+            assert [o["ret"], o["evals"]] == list(gold[f"{tag}_opt_stats"][b, [0, 2]].astype(int))
+            assert o["fx"] == gold[f"{tag}_opt_stats"][b, 3]
+            assert np.array_equal(pl.get_ctrl(), gold[f"{tag}_opt_ctrl"][off[b]:off[b + 1]])
+        _, out, st = orc.make_plan_batch(sq_omap, po, off, ctrl, nthreads=4)
+        assert np.array_equal(out, gold[f"{tag}_plan_ctrl"])
+        gs = gold[f"{tag}_plan_stats"]
+        okm = gs["success"] == 1
+        for k in st.dtype.names:
+            if k != "lbfgs_iters":
+                sel = okm if k == "linear_factor" else slice(None)
+                assert np.array_equal(st[k][sel], gs[k][sel]), k
+
+
+def test_oracle_map_queries_and_astar_golden(orc, sq_omap, gold):
+    assert np.array_equal(sq_omap.query(gold["q_xyz"]), gold["q_hit"])
+    assert np.array_equal(sq_omap.query_unknown(gold["q_xyz"]), gold["q_unknown"])
+    assert np.array_equal(sq_omap.query_lines(gold["q_xyz"], gold["q_b"]), gold["q_line"])
+    pl = orc.Planner(sq_omap)
+    pos = 0
+    for s, e, n, ex in zip(gold["astar_starts"], gold["astar_ends"], gold["astar_len"], gold["astar_exp"]):
+        p, x = pl.astar(s, e)
+        assert x == ex
+        assert (p is None) == (n < 0)
+        if p is not None:
+            assert np.array_equal(p, gold["astar_paths"][pos:pos + n])
+            pos += n
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref not built (needs /root/reference)")
+def test_lbfgs_port_is_pinned_to_reference_header(orc, sq_map):
+    """lbfgs_port.hpp vs the reference's solver/lbfgs.hpp (oracle/_ref, use_ref_lbfgs=1) on the ViGO cost
+    function: same return code, iteration / evaluation counts and bit-identical iterates, over 96 seeded
+    problems and over whole makePlan runs (which chain ~5 optimize() calls with escalating weights)."""
+    import trajectory_planner_b200 as tp
+    omr = oracle_map_from(orc, sq_map, ref=True)
+    omp = oracle_map_from(orc, sq_map, ref=False)
+    assert omr.lib.L.orc_is_ref_build() == 1 and omp.lib.L.orc_is_ref_build() == 0
+    pr = make_problems(tp, sq_map, omp, 96, seed=4242)
+    off = pr["offsets"]
+    pr_ = omr.lib.default_params()
+    pr_.use_ref_lbfgs = 1
+    pp = omp.lib.default_params()
+    rets = set()
+    for b in range(len(off) - 1):
+        a = orc.Planner(omr, pr_)
+        c = orc.Planner(omp, pp)
+        for pl in (a, c):
+            pl.set_ctrl(traj(pr, b))
+            pl.init_guides()
+        oa, oc = a.optimize(), c.optimize()
+        # (iteration count is not reported by the reference's lbfgs_optimize)
+        assert (oa["ret"], oa["evals"], oa["fx"]) == (oc["ret"], oc["evals"], oc["fx"]), (b, oa, oc)
+        assert np.array_equal(oa["x"], oc["x"])
+        assert np.array_equal(a.get_ctrl(), c.get_ctrl())
+        rets.add(oa["ret"])
+    assert len(rets) >= 2  # convergence and at least one other exit are exercised
+    _, out_r, st_r = orc.make_plan_batch(omr, pr_, off, pr["ctrl"], nthreads=4)
+    _, out_p, st_p = orc.make_plan_batch(omp, pp, off, pr["ctrl"], nthreads=4)
+    assert np.array_equal(out_r, out_p)
+    ok = st_r["success"] == 1
+    for k in st_r.dtype.names:
+        if k == "lbfgs_iters":
+            continue   # not reported by the reference's lbfgs_optimize
+        sel = ok if k == "linear_factor" else slice(None)   # only defined when makePlan succeeded
+        assert np.array_equal(st_r[k][sel], st_p[k][sel]), k
+
+
+# ------------------------------------------------------------------------------------ known answers
+def _planner(orc, omap, ctrl, **kw):
+    po = omap.lib.default_params()
+    for k, v in kw.items():
+        setattr(po, k, v)
+    pl = orc.Planner(omap, po)
+    pl.set_ctrl(np.asarray(ctrl, float))
+    return pl
+
+
+def test_kat_collinear_control_points_have_zero_cost(orc, sq_omap):
+    """Equally spaced collinear control points at 0.1 m spacing: jerk = 0, |v| = 0.5 <= 1, a = 0 ->
+    every term is exactly 0 and so is the gradient (bsplineTraj.cpp:934-999)."""
+    c = np.array([[0.125 * i, 0.0625 * i, 1.0] for i in range(20)])   # dyadic spacing: exact arithmetic
+    pl = _planner(orc, sq_omap, c)
+    f, g, terms = pl.cost(c[3:-3].ravel())
+    assert f == 0.0 and np.all(g == 0.0) and np.all(np.asarray(terms) == 0.0)
+    c = np.array([[0.1 * i, 0.05 * i, 1.0] for i in range(20)])        # inexact spacing: rounding only
+    f, g, _ = _planner(orc, sq_omap, c).cost(c[3:-3].ravel())
+    assert 0.0 <= f <= 1e-28 and np.max(np.abs(g)) <= 1e-13
+
+
+def test_kat_feasibility_and_smoothness_hand_computed(orc, sq_omap):
+    """One displaced control point, hand-evaluated with the reference's formulas:
+    smoothness S = sum |c[i+3]-3c[i+2]+3c[i+1]-c[i]|^2; feasibility with maxVel=maxAcc=1 HARD-CODED
+    (bsplineTraj.cpp:955-956), k = 1/0.2^2 = 25."""
+    N = 12
+    c = np.array([[0.1 * i, 0.0, 1.0] for i in range(N)])
+    c[6, 1] = 0.3
+    pl = _planner(orc, sq_omap, c)
+    f, g, terms = pl.cost(c[3:-3].ravel())
+    S = sum(np.sum((c[i + 3] - 3 * c[i + 2] + 3 * c[i + 1] - c[i]) ** 2) for i in range(N - 3))
+    k = 25.0
+    F = 0.0
+    for i in range(N - 1):
+        v = (c[i + 1] - c[i]) / 0.2
+        F += np.sum(np.where(v > 1, (v - 1) ** 2 * k, 0) + np.where(v < -1, (v + 1) ** 2 * k, 0))
+    for i in range(N - 2):
+        a = (c[i + 2] - 2 * c[i + 1] + c[i]) * k
+        F += np.sum(np.where(a > 1, (a - 1) ** 2, 0) + np.where(a < -1, (a + 1) ** 2, 0))
+    assert F > 0 and S > 0
+    assert abs(terms[1] - S) <= 1e-12 * S and abs(terms[2] - F) <= 1e-12 * F
+    assert terms[0] == 0.0 and abs(f - (S + F)) <= 1e-12 * f
+
+
+def test_kat_distance_cost_pieces(orc, sq_omap):
+    """The three pieces of the distance barrier (bsplineTraj.cpp:852-894) for one guide pair, d_thr=0.5."""
+    N = 10
+    base = np.array([[0.1 * i, 0.0, 1.0] for i in range(N)])
+    for dist, expect in [(1.2, (1.2 - 0.5 - 0.0) ** 3 if False else None), (0.3, 0.2 ** 3), (-0.2, None)]:
+        c = base.copy()
+        pl = _planner(orc, sq_omap, c)
+        gp = c[4] - np.array([0.0, dist, 0.0])     # (c - p) . v = dist with v = +y
+        pl.add_guides(np.array([4], np.int32), gp[None], np.array([[0.0, 1.0, 0.0]]))
+        f, g, terms = pl.cost(c[3:-3].ravel())
+        e = 0.5 - dist
+        if e <= -0.5:
+            want = (-e) ** 3
+        elif 0 < e <= 0.5:
+            want = e ** 3
+        elif e >= 0.5:
+            want = 3 * 0.5 * e * e - 3 * 0.25 * e + 0.125
+        else:
+            want = 0.0
+        assert abs(terms[0] - want) <= 1e-15 + 1e-13 * abs(want), (dist, terms[0], want)
+
+
+@pytest.mark.parametrize("plan_in_z", [0, 1])
+def test_gradient_matches_finite_differences(orc, sq_omap, problems, plan_in_z):
+    """Central differences of the oracle cost vs its analytic gradient.  With plan_in_z=1 the reference
+    writes the height-barrier gradient into the X row (bsplineTraj.cpp:904-925): that term is therefore
+    NOT a true gradient and is excluded by comparing only where the barrier is inactive (z = 1.0 sits
+    inside [0.7+0.2, 1.3-0.2] -> active cubic piece; so we just check plan_in_z=0 strictly and the
+    y/z rows for plan_in_z=1)."""
+    rng = np.random.default_rng(1)
+    for b in range(4):
+        c = traj(problems, b) + rng.normal(0, 0.1, traj(problems, b).shape)
+        pl0 = _planner(orc, sq_omap, traj(problems, b), plan_in_z=plan_in_z)
+        pl0.init_guides()
+        cp, gp, gv = pl0.get_guides()
+        pl = _planner(orc, sq_omap, c, plan_in_z=plan_in_z)
+        pl.add_guides(cp, gp, gv)
+        x = c[3:-3].ravel().copy()
+        f, g, _ = pl.cost(x)
+        h = 1e-6
+        idx = rng.choice(len(x), size=min(24, len(x)), replace=False)
+        for i in idx:
+            if plan_in_z and i % 3 != 1:
+                continue
+            xp, xm = x.copy(), x.copy()
+            xp[i] += h
+            xm[i] -= h
+            fd = (pl.cost(xp)[0] - pl.cost(xm)[0]) / (2 * h)
+            assert abs(fd - g[i]) <= 1e-4 * max(1.0, abs(g[i])), (b, i, fd, g[i])
+
+
+def test_de_boor_matches_scipy_bspline(orc):
+    from scipy.interpolate import BSpline
+    rng = np.random.default_rng(2)
+    N, ts = 23, 0.2
+    c = rng.normal(0, 1, (N, 3))
+    knots = (np.arange(N + 4) - 3) * ts                # bspline.cpp:19-28
+    t = np.linspace(0, (N - 3) * ts, 301)
+    want = BSpline(knots, c, 3)(t)
+    got = orc.bspline_at(c, t)
+    assert np.max(np.abs(got - want)) <= 1e-12
+    wantd = BSpline(knots, c, 3).derivative(1)(t[:-1])
+    gotd = orc.bspline_deriv_at(c, t[:-1], 1)
+    assert np.max(np.abs(gotd - wantd)) <= 1e-10
