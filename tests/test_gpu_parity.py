@@ -415,3 +415,46 @@ def test_golden_fast_mode_per_evaluation_and_quality(tp, engine):
     assert np.mean((r["status"] == 1).astype(int) == gs["success"]) >= 0.9
     hit = engine.has_collision_batch(p, off, out)
     assert not np.any(hit[r["status"] == 1])
+
+
+def test_astar_exhaustive_failure_and_long_detour(tp, orc):
+    """A* on a synthetic map: (1) goal inside a sealed box -> the reference pops the start's whole connected
+    component and fails; the CUDA path detects unreachability with a flood fill and must report the SAME
+    failure and the SAME expansion count; (2) a long detour (> the flood-fill trigger) that IS reachable:
+    the parked heap is restored and the path stays bit-identical."""
+    res, origin, dims, inf = 0.1, (-8.0, -8.0, -0.1), (160, 160, 30), (4, 4, 2)
+    m = tp.OccMap(res, origin, dims, inf)
+    om = orc.Map(res, origin, dims, inf)
+    pts = []
+    zs = np.arange(0.05, 2.9, 0.1)
+    def wall(x0, y0, x1, y1):
+        n = int(max(abs(x1 - x0), abs(y1 - y0)) / 0.05) + 1
+        for t in np.linspace(0, 1, n):
+            for z in zs:
+                pts.append([x0 + t * (x1 - x0), y0 + t * (y1 - y0), z])
+    # sealed box around (2.5, 0): interior 3 m wide
+    wall(1.0, -1.5, 4.0, -1.5); wall(4.0, -1.5, 4.0, 1.5); wall(4.0, 1.5, 1.0, 1.5); wall(1.0, 1.5, 1.0, -1.5)
+    # a long wall with a gap far away -> long detour
+    wall(-3.0, -4.5, -3.0, 3.0)
+    pts = np.array(pts)
+    m.add_points(pts)
+    om.add_points(pts)
+    e = tp.Engine(0)
+    e.set_map(m)
+    p = tp.default_params()
+    starts = np.array([[-1.0, 0.0, 1.0], [-1.5, -1.0, 1.0], [0.0, 0.3, 1.0], [2.5, 0.2, 1.0]])
+    ends = np.array([[2.5, 0.0, 1.0], [-4.5, -1.0, 1.0], [2.6, -0.4, 1.0], [2.2, -0.6, 1.0]])
+    paths, ex = e.astar_batch(p, starts, ends)
+    pl = orc.Planner(om)
+    big = 0
+    for s in range(len(starts)):
+        po, eo = pl.astar(starts[s], ends[s])
+        assert ex[s] == eo, (s, ex[s], eo)
+        assert (po is None) == (paths[s] is None), s
+        if po is not None:
+            assert np.array_equal(po, paths[s]), s
+        big += eo > 1536
+    assert paths[0] is None and ex[0] > 5000      # exhaustive failure, count from the flood fill
+    assert paths[1] is not None and ex[1] > 1536  # reachable long detour across the trigger
+    assert big >= 3 and paths[2] is None and paths[3] is not None
+    e.close()

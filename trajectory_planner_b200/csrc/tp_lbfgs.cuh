@@ -204,7 +204,11 @@ __device__ __forceinline__ void dynamic_terms(const VigoConst& C, const EvalCtx&
 
 // Gradient of the optimised elements owned by this thread (gather form) + this thread's share
 // of the weighted cost.  g (shared, n) receives costFunction's gradient (bsplineTraj.cpp:817-819).
-__device__ __forceinline__ double eval_partial(const VigoConst& C, const EvalCtx& E, double* g, int tid) {
+// `d` (may be null): search direction; `dg_part` accumulates this thread's share of g.d over the
+// elements it has just WRITTEN (g[i] is produced by thread (i+9) mod THREADS here, not by the thread
+// that owns index i elsewhere, so the dot must not re-read g before the next barrier).
+__device__ __forceinline__ double eval_partial(const VigoConst& C, const EvalCtx& E, double* g, const double* d,
+                                               double& dg_part, int tid) {
   const int N = E.N;
   const double* cp = E.cp;
   const double cts = C.p.ctrl_pt_ts;
@@ -267,7 +271,9 @@ __device__ __forceinline__ double eval_partial(const VigoConst& C, const EvalCtx
       dynamic_terms(C, E, c, a, go, cO);
       if (a == 0) sO += cO;
     }
-    g[e - 3 * TP_DEGREE] = E.w_dist * gd + C.p.w_smooth * gs + C.p.w_feas * gf + E.w_dyn * go;
+    const double gv = E.w_dist * gd + C.p.w_smooth * gs + C.p.w_feas * gf + E.w_dyn * go;
+    g[e - 3 * TP_DEGREE] = gv;
+    if (d) dg_part += gv * d[e - 3 * TP_DEGREE];
   }
   return E.w_dist * sD + C.p.w_smooth * sS + C.p.w_feas * sF + E.w_dyn * sO;
 }
@@ -314,7 +320,8 @@ __device__ double serial_cost(const VigoConst& C, const EvalCtx& E) {
 template <bool STRICT>
 __device__ __forceinline__ void eval_cost(const VigoConst& C, const EvalCtx& E, Red& R, double* g, const double* d,
                                           double& f, double& dg, int tid) {
-  double part = eval_partial(C, E, g, tid);
+  double dgp = 0.0;
+  double part = eval_partial(C, E, g, d, dgp, tid);
   double v[2];
   if (STRICT) {
     __syncthreads();
@@ -325,9 +332,7 @@ __device__ __forceinline__ void eval_cost(const VigoConst& C, const EvalCtx& E, 
     block_bcast<2>(R, v, tid);
   } else {
     v[0] = part;
-    v[1] = 0.0;
-    if (d)
-      for (int e = tid; e < E.n; e += TP_LB_THREADS) v[1] += g[e] * d[e];
+    v[1] = dgp;
     block_sum<2>(R, v, tid);
   }
   f = v[0];

@@ -27,11 +27,12 @@
 // per-warp working set
 struct Worker {
   ANode* nodes;
-  HeapEnt* heap_sm;  // shared, TP_HEAP_SMEM entries
-  HeapEnt* heap_gl;  // HBM spill for entries >= TP_HEAP_SMEM
-  double* path;      // xyz, path_cap points
-  double* sc;        // max_seg x TP_SC_CAP x 3
-  int* sc_len;       // max_seg
+  AStarSmem* sm;       // shared: heap arrays, per-axis tables, staging
+  double* heap_k_gl;   // HBM spill for heap entries >= TP_HEAP_SMEM
+  uint32_t* heap_n_gl;
+  double* path;        // xyz, path_cap points
+  double* sc;          // max_seg x TP_SC_CAP x 3
+  int* sc_len;         // max_seg
   uint32_t* round_ptr;
   int lane;
 };
@@ -71,64 +72,235 @@ __device__ __forceinline__ double as_heu(int i, int j, int k, int ei, int ej, in
   return tie * h;
 }
 
+// ---- shared-memory accessors on 32-bit shared-window addresses (keeps the sift loops free of
+// generic-pointer arithmetic)
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// packed node id: (i << 16) | (j << 8) | kk, kk = k - k_lo (kk == 255: the spare slot of the start cell)
+#define AS_SPARE_KK 255u
+
 // ---- libstdc++ heap mechanics (std::priority_queue without decrease-key, astarOcc.cpp:150-228).
-// comp(a,b) = a->fScore > b->fScore with keys read at comparison time; here the key lives in the
-// heap entry and is patched whenever the reference mutates fScore in place, so every comparison
-// sees exactly the value the reference would read through the node pointer.
+// comp(a,b) = a->fScore > b->fScore with keys read at comparison time; here the key is cached beside
+// the node id and patched whenever the reference mutates fScore in place, so every comparison sees
+// exactly the value the reference would read through the node pointer.
 struct Heap {
-  HeapEnt* sm;
-  HeapEnt* gl;
+  uint32_t sk, sn;     // shared-window addresses of the key / id arrays
+  double* gk;          // HBM spill (entries >= TP_HEAP_SMEM)
+  uint32_t* gn;
   ANode* nodes;
+  uint32_t PY, KL, spare;
   int size;
-  __device__ __forceinline__ HeapEnt get(int i) const { return i < TP_HEAP_SMEM ? sm[i] : gl[i - TP_HEAP_SMEM]; }
-  __device__ __forceinline__ double key(int i) const { return i < TP_HEAP_SMEM ? sm[i].f : gl[i - TP_HEAP_SMEM].f; }
-  __device__ __forceinline__ void put(int i, const HeapEnt& e) {
-    if (i < TP_HEAP_SMEM) sm[i] = e; else gl[i - TP_HEAP_SMEM] = e;
-    nodes[e.node].heap_pos = (uint32_t)i;
+  __device__ __forceinline__ uint32_t lin_of(uint32_t id) const {
+    const uint32_t kk = id & 255u;
+    return kk == AS_SPARE_KK ? spare : ((id >> 16) * PY + ((id >> 8) & 255u)) * KL + kk;
   }
-  __device__ __forceinline__ void set_key(int i, double f) {
-    if (i < TP_HEAP_SMEM) sm[i].f = f; else gl[i - TP_HEAP_SMEM].f = f;
+  __device__ __forceinline__ double key(int i) const { return i < TP_HEAP_SMEM ? lds_f64(sk + 8u * i) : gk[i - TP_HEAP_SMEM]; }
+  __device__ __forceinline__ uint32_t node(int i) const { return i < TP_HEAP_SMEM ? lds_u32(sn + 4u * i) : gn[i - TP_HEAP_SMEM]; }
+  __device__ __forceinline__ void set(int i, double k, uint32_t n) {
+    if (i < TP_HEAP_SMEM) { sts_f64(sk + 8u * i, k); sts_u32(sn + 4u * i, n); }
+    else { gk[i - TP_HEAP_SMEM] = k; gn[i - TP_HEAP_SMEM] = n; }
+    nodes[lin_of(n)].heap_pos = (uint32_t)i;
+  }
+  __device__ __forceinline__ void set_key(int i, double k) {
+    if (i < TP_HEAP_SMEM) sts_f64(sk + 8u * i, k); else gk[i - TP_HEAP_SMEM] = k;
+  }
+  // all-shared fast variant (valid while every index touched is < TP_HEAP_SMEM)
+  __device__ __forceinline__ void set_s(int i, double k, uint32_t n) {
+    sts_f64(sk + 8u * i, k);
+    sts_u32(sn + 4u * i, n);
+    nodes[lin_of(n)].heap_pos = (uint32_t)i;
   }
   // std::__push_heap
-  __device__ __forceinline__ void sift_up(int hole, int top, const HeapEnt& value) {
-    int parent = (hole - 1) / 2;
-    while (hole > top && key(parent) > value.f) {
-      put(hole, get(parent));
-      hole = parent;
-      parent = (hole - 1) / 2;
+  __device__ __forceinline__ void sift_up(int hole, double vk, uint32_t vn) {
+    if (hole < TP_HEAP_SMEM) {
+      while (hole > 0) {
+        const int parent = (hole - 1) >> 1;
+        const double pk = lds_f64(sk + 8u * parent);
+        if (!(pk > vk)) break;
+        set_s(hole, pk, lds_u32(sn + 4u * parent));
+        hole = parent;
+      }
+      set_s(hole, vk, vn);
+      return;
     }
-    put(hole, value);
+    while (hole > 0) {
+      const int parent = (hole - 1) >> 1;
+      const double pk = key(parent);
+      if (!(pk > vk)) break;
+      set(hole, pk, node(parent));
+      hole = parent;
+    }
+    set(hole, vk, vn);
   }
-  __device__ __forceinline__ void push(uint32_t node, double f) {
-    HeapEnt e;
-    e.f = f; e.node = node; e.pad = 0;
-    sift_up(size, 0, e);
+  __device__ __forceinline__ void push(uint32_t n, double f) {
+    sift_up(size, f, n);
     ++size;
   }
   // top() + std::pop_heap (= __adjust_heap on the hole at the root, then __push_heap) + pop_back
   __device__ __forceinline__ uint32_t pop() {
-    const uint32_t top = get(0).node;
+    const uint32_t top = node(0);
     if (size > 1) {
-      const HeapEnt value = get(size - 1);
       const int len = size - 1;
+      const double vk = key(len);
+      const uint32_t vn = node(len);
       int hole = 0, second = 0;
-      while (second < (len - 1) / 2) {
-        second = 2 * (second + 1);
-        if (key(second) > key(second - 1)) second--;
-        put(hole, get(second));
-        hole = second;
+      const int lim = (len - 1) / 2;
+      if (size <= TP_HEAP_SMEM) {
+        while (second < lim) {
+          second = 2 * (second + 1);
+          double kr = lds_f64(sk + 8u * second);
+          const double kl = lds_f64(sk + 8u * second - 8u);
+          if (kr > kl) { --second; kr = kl; }
+          set_s(hole, kr, lds_u32(sn + 4u * second));
+          hole = second;
+        }
+      } else {
+        while (second < lim) {
+          second = 2 * (second + 1);
+          double kr = key(second);
+          const double kl = key(second - 1);
+          if (kr > kl) { --second; kr = kl; }
+          set(hole, kr, node(second));
+          hole = second;
+        }
       }
       if ((len & 1) == 0 && second == (len - 2) / 2) {
         second = 2 * (second + 1);
-        put(hole, get(second - 1));
+        set(hole, key(second - 1), node(second - 1));
         hole = second - 1;
       }
-      sift_up(hole, 0, value);
+      sift_up(hole, vk, vn);
     }
     --size;
     return top;
   }
 };
+
+// Reachability shortcut for searches that are about to exhaust their pool.  AstarSearch pops every
+// cell reachable from the start exactly once before it gives up (nodes are pushed once and never
+// re-opened, astarOcc.cpp:209-228), so when the goal is NOT in the start's connected component the
+// search's outcome (failure) and its expansion count (= component size) are known without running
+// it.  The component is flooded with a lane-per-cell worklist over two bitmaps that temporarily
+// take over the heap's shared memory (the heap is parked in the tail of its HBM spill area).
+// Returns -1 when the goal is reachable (the search resumes), else the component size.
+#define TP_FLOOD_TRIGGER 1536
+__device__ int flood_component(const DevMap& map, const VigoConst& C, Worker& W, int heap_size, int si, int sj, int sk,
+                               int ei, int ej, int ek, int k_lo) {
+  AStarSmem& S = *W.sm;
+  const int lane = W.lane;
+  const int PX = C.pool[0], PY = C.pool[1], PZ = C.pool[2], KL = C.pool_kl;
+  const int ncell = PX * PY * KL;
+  const int nw = (ncell + 31) >> 5;
+  // shared-memory plan (the heap's 24 KB): V bitmap [nw] | head, tail | worklist ring Q[qcap]
+  uint32_t* V = reinterpret_cast<uint32_t*>(S.hk);   // seen: visited-free or known-blocked
+  volatile uint32_t* ctr = V + nw;                    // [0] head, [1] tail (monotonic)
+  uint32_t* Q = V + nw + 2;
+  const int qcap = (int)((sizeof(S.hk) + sizeof(S.hn)) / 4) - nw - 2;
+  if (qcap < 32 * 26 + 64 || C.heap_cap < 3 * TP_HEAP_SMEM) return -1;
+  // park the heap
+  const int keep = heap_size < TP_HEAP_SMEM ? heap_size : TP_HEAP_SMEM;
+  double* pk = W.heap_k_gl + (C.heap_cap - TP_HEAP_SMEM);
+  uint32_t* pn = W.heap_n_gl + (C.heap_cap - TP_HEAP_SMEM);
+  for (int i = lane; i < keep; i += 32) { pk[i] = S.hk[i]; pn[i] = S.hn[i]; }
+  __syncwarp();
+  for (int i = lane; i < nw + 2; i += 32) V[i] = 0u;
+  __syncwarp();
+  const int klo_c = k_lo > 1 ? k_lo : 1;                                  // neighbour layers that can be entered
+  const int khi_c = (k_lo + KL - 1) < (PZ - 2) ? (k_lo + KL - 1) : (PZ - 2);
+  // expand one cell: mark its unseen neighbours, enqueue the free ones.  The three vertical neighbours of
+  // a column are three consecutive bits of V and (almost always) one word of the z-fastest map.
+  auto expand = [&](int ci, int cj, int ck) {
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int ni = ci + dx;
+      if (ni < 1 || ni >= PX - 1) continue;
+      for (int dy = -1; dy <= 1; ++dy) {
+        const int nj = cj + dy;
+        if (nj < 1 || nj >= PY - 1) continue;
+        const int ix = S.tx[ni], iy = S.ty[nj];
+        const size_t col = ((size_t)(ix < 0 ? 0 : ix) * map.dim[1] + (iy < 0 ? 0 : iy)) * map.wz;
+        int cached_w = -1;
+        uint32_t mw = 0u;
+        for (int dz = -1; dz <= 1; ++dz) {
+          const int nk = ck + dz;
+          if (nk < klo_c || nk > khi_c || !S.band[nk]) continue;
+          if (dx == 0 && dy == 0 && dz == 0) continue;
+          if (ni == si && nj == sj && nk == sk) continue;
+          const int b = (ni * PY + nj) * KL + (nk - k_lo);
+          const uint32_t bit = 1u << (b & 31);
+          if (V[b >> 5] & bit) continue;
+          bool blocked = true;
+          const int iz = S.tz[nk];
+          if (ix >= 0 && iy >= 0 && iz >= 0) {
+            if ((iz >> 5) != cached_w) {
+              cached_w = iz >> 5;
+              mw = __ldg(&map.inflated[col + cached_w]);
+            }
+            blocked = (mw >> (iz & 31)) & 1u;
+          }
+          const uint32_t old = atomicOr(&V[b >> 5], bit);
+          if (!(old & bit) && !blocked) {
+            const uint32_t pos = atomicAdd((uint32_t*)&ctr[1], 1u);
+            Q[pos % (uint32_t)qcap] = (uint32_t)b;
+          }
+        }
+      }
+    }
+  };
+  if (lane == 0) expand(si, sj, sk);
+  __syncwarp();
+  bool bail = false;
+  for (;;) {
+    const uint32_t h = ctr[0], t = ctr[1];
+    __syncwarp();
+    int n = (int)(t - h);
+    if (n == 0) break;
+    if (n > qcap - 32 * 26) { bail = true; break; }   // the ring could overflow during this round
+    if (n > 32) n = 32;
+    uint32_t cell = 0xFFFFFFFFu;
+    if (lane < n) cell = Q[(h + (uint32_t)lane) % (uint32_t)qcap];
+    if (lane == 0) ctr[0] = h + (uint32_t)n;
+    __syncwarp();
+    if (cell != 0xFFFFFFFFu) {
+      const int kk = (int)(cell % (uint32_t)KL), r = (int)(cell / (uint32_t)KL);
+      expand(r / PY, r % PY, kk + k_lo);
+    }
+    __syncwarp();
+  }
+  const int count = (int)ctr[1] + 1;  // every free cell was enqueued exactly once, plus the start cell
+  // is the goal in the component?
+  bool reach = false;
+  if (!bail) {
+    if (ei == si && ej == sj && ek == sk) reach = true;
+    else if (ek >= klo_c && ek <= khi_c && ei >= 1 && ei < PX - 1 && ej >= 1 && ej < PY - 1 && S.band[ek]) {
+      const int b = (ei * PY + ej) * KL + (ek - k_lo);
+      if ((V[b >> 5] >> (b & 31)) & 1u) {   // seen: free (enqueued) or blocked -> ask the map
+        const int ix = S.tx[ei], iy = S.ty[ej], iz = S.tz[ek];
+        bool blocked = true;
+        if (ix >= 0 && iy >= 0 && iz >= 0) {
+          const uint32_t w = __ldg(&map.inflated[((size_t)ix * map.dim[1] + iy) * map.wz + (iz >> 5)]);
+          blocked = (w >> (iz & 31)) & 1u;
+        }
+        reach = !blocked;
+      }
+    }
+  }
+  __syncwarp();
+  // restore the heap
+  for (int i = lane; i < keep; i += 32) { S.hk[i] = pk[i]; S.hn[i] = pn[i]; }
+  __syncwarp();
+  return (bail || reach) ? -1 : count;
+}
 
 // AStar::AstarSearch + getPath.  Returns the number of path points written to W.path (cell centres
 // start -> goal) or -1.  All 32 lanes call it with identical arguments.
@@ -138,10 +310,12 @@ struct Heap {
 // state is consulted (astarOcc.cpp:202) — plus one spare slot for the start cell, which the
 // reference expands from even when it lies outside the band.  Per expansion the warp makes ONE
 // round of global loads (current node, <= 26 neighbour nodes as LDG.128, <= 26 map words, all in
-// flight together); the open-set heap lives in shared memory.
+// flight together); the open-set heap, the per-axis map-index tables and the serial pass's staging
+// live in shared memory; no FP64 division or integer division is on the per-expansion path.
 __device__ int astar_search(const DevMap& map, const VigoConst& C, Worker& W, const D3& start_in, const D3& end_in,
                             int& expansions, int& err) {
   const int lane = W.lane;
+  AStarSmem& S = *W.sm;
   AStarFrame F;
   F.step = map.res;
   F.inv_step = 1 / map.res;
@@ -185,25 +359,35 @@ __device__ int astar_search(const DevMap& map, const VigoConst& C, Worker& W, co
   if (!ok) return -1;
   si = __shfl_sync(0xffffffffu, si, 0); sj = __shfl_sync(0xffffffffu, sj, 0); sk = __shfl_sync(0xffffffffu, sk, 0);
   ei = __shfl_sync(0xffffffffu, ei, 0); ej = __shfl_sync(0xffffffffu, ej, 0); ek = __shfl_sync(0xffffffffu, ek, 0);
-  const int PY = C.pool[1], KL = C.pool_kl;
-  const uint32_t spare = (uint32_t)((size_t)C.pool[0] * PY * KL);
+  const int PX = C.pool[0], PY = C.pool[1], PZ = C.pool[2], KL = C.pool_kl;
   const int k_lo = F.k_lo;
-  auto lin_of = [&](int i, int j, int k) -> uint32_t {
-    if (i == si && j == sj && k == sk) return spare;
-    return (uint32_t)(((size_t)i * PY + j) * KL + (k - k_lo));
-  };
-  auto ijk_of = [&](uint32_t lin, int& i, int& j, int& k) {
-    if (lin == spare) { i = si; j = sj; k = sk; return; }
-    k = (int)(lin % (uint32_t)KL) + k_lo;
-    const uint32_t r = lin / (uint32_t)KL;
-    j = (int)(r % (uint32_t)PY);
-    i = (int)(r / (uint32_t)PY);
-  };
+  // ---- per-axis tables: map cell of pool index (Index2Coord -> posToIndex, evaluated once per axis)
+  for (int t = lane; t < PX; t += 32) {
+    const double f = floor(((double)(t - PX / 2) * F.step + F.center.x - map.mn[0]) / map.res);
+    S.tx[t] = (f >= 0.0 && f < (double)map.dim[0]) ? (short)(int)f : (short)-1;
+  }
+  for (int t = lane; t < PY; t += 32) {
+    const double f = floor(((double)(t - PY / 2) * F.step + F.center.y - map.mn[1]) / map.res);
+    S.ty[t] = (f >= 0.0 && f < (double)map.dim[1]) ? (short)(int)f : (short)-1;
+  }
+  for (int t = lane; t < PZ; t += 32) {
+    const double z = (double)(t - PZ / 2) * F.step + F.center.z;
+    const double f = floor((z - map.mn[2]) / map.res);
+    S.tz[t] = (f >= 0.0 && f < (double)map.dim[2]) ? (short)(int)f : (short)-1;
+    S.band[t] = !(z > C.p.max_height || z < C.p.min_height) ? 1 : 0;
+  }
+  const uint32_t spare = (uint32_t)((size_t)PX * PY * KL);
+  const uint32_t start_id = ((uint32_t)si << 16) | ((uint32_t)sj << 8) | AS_SPARE_KK;
   ANode* nodes = W.nodes;
   Heap H;
-  H.sm = W.heap_sm;
-  H.gl = W.heap_gl;
+  H.sk = (uint32_t)__cvta_generic_to_shared(S.hk);
+  H.sn = (uint32_t)__cvta_generic_to_shared(S.hn);
+  H.gk = W.heap_k_gl;
+  H.gn = W.heap_n_gl;
   H.nodes = nodes;
+  H.PY = (uint32_t)PY;
+  H.KL = (uint32_t)KL;
+  H.spare = spare;
   H.size = 0;
   if (lane == 0) {
     ANode nd;
@@ -212,12 +396,19 @@ __device__ int astar_search(const DevMap& map, const VigoConst& C, Worker& W, co
     nd.g = 0;
     nd.heap_pos = 0; nd.pad0 = 0; nd.pad1 = 0;
     nodes[spare] = nd;
-    H.push(spare, as_heu(si, sj, sk, ei, ej, ek));
+    H.push(start_id, as_heu(si, sj, sk, ei, ej, ek));
   }
   __syncwarp();
+  const double gstep1 = 1.0, gstep2 = sqrt(2.0), gstep3 = sqrt(3.0);
   int result = -1;
   int num_iter = 0;
-  uint32_t goal_lin = NODE_NONE;
+  uint32_t goal_id = NODE_NONE;
+#ifdef TP_ASTAR_TIMING
+  long long tA = 0, tB = 0, tC = 0, t0 = clock64(), t1;
+#define TICK(acc) { t1 = clock64(); acc += t1 - t0; t0 = t1; }
+#else
+#define TICK(acc)
+#endif
   for (;;) {
     // ---- pop (lane 0, shared memory)
     uint32_t cur = NODE_NONE;
@@ -225,36 +416,44 @@ __device__ int astar_search(const DevMap& map, const VigoConst& C, Worker& W, co
     cur = __shfl_sync(0xffffffffu, cur, 0);
     if (cur == NODE_NONE) break;  // open set empty
     ++num_iter;
-    int ci, cj, ck;
-    ijk_of(cur, ci, cj, ck);
+    const int ci = (int)(cur >> 16), cj = (int)((cur >> 8) & 255u);
+    const int ck = (cur & 255u) == AS_SPARE_KK ? sk : (int)(cur & 255u) + k_lo;
     if (ci == ei && cj == ej && ck == ek) {
-      goal_lin = cur;
+      goal_id = cur;
       result = 0;
       break;
     }
-    const double gcur = nodes[cur].g;  // uniform address: one broadcast load, overlaps the loads below
-    if (lane == 0) nodes[cur].stamp_state = (round << 2) | ST_CLOSED;
+    TICK(tA)
+    const uint32_t cur_lin = H.lin_of(cur);
+    const double gcur = nodes[cur_lin].g;  // uniform address: one broadcast load, overlaps the loads below
+    if (lane == 0) nodes[cur_lin].stamp_state = (round << 2) | ST_CLOSED;
     // ---- lane-parallel neighbour evaluation (astarOcc.cpp:173-229); lane L <-> (dx,dy,dz) in the
     // reference's loop order
     int kind = 0;  // 0 skip, 1 push (new node), 2 in-place update
-    uint32_t nl = NODE_NONE;
-    double tentative = 0, fnew = 0;
     if (lane < 27 && lane != 13) {
       const int dx = lane / 9 - 1, dy = (lane / 3) % 3 - 1, dz = lane % 3 - 1;
       const int ni = ci + dx, nj = cj + dy, nk = ck + dz;
-      const bool inb = !(ni < 1 || ni >= C.pool[0] - 1 || nj < 1 || nj >= PY - 1 || nk < 1 || nk >= C.pool[2] - 1);
+      const bool inb = !(ni < 1 || ni >= PX - 1 || nj < 1 || nj >= PY - 1 || nk < 1 || nk >= PZ - 1);
       if (inb) {
-        const D3 pc = as_index2coord(C, F, ni, nj, nk);
         const bool is_start = (ni == si && nj == sj && nk == sk);
-        const bool band = !(pc.z > C.p.max_height || pc.z < C.p.min_height);
+        const bool band = S.band[nk] != 0;
         const bool layer_ok = nk >= k_lo && nk < k_lo + KL;
         if (band && !layer_ok && !is_start) err |= ERR_BAND;  // cannot happen (pool_kl has slack)
         // cells outside the band are rejected by :202 whatever their node state says, except that a
         // CLOSED start node is skipped one line earlier — same outcome (skip) either way.
         if ((band && layer_ok) || is_start) {
-          nl = lin_of(ni, nj, nk);
+          const uint32_t nid = is_start ? start_id : (((uint32_t)ni << 16) | ((uint32_t)nj << 8) | (uint32_t)(nk - k_lo));
+          const uint32_t nl = is_start ? spare : (uint32_t)((ni * PY + nj) * KL + (nk - k_lo));
           const uint4 raw = *reinterpret_cast<const uint4*>(&nodes[nl]);  // stamp_state, parent, g
-          const bool blocked_map = band ? dm_inflated(map, pc) : true;   // issued before `raw` is consumed
+          const uint32_t hpos = nodes[nl].heap_pos;                         // same sector, speculative
+          bool blocked_map = true;   // the map gather is issued before `raw` is consumed
+          if (band) {
+            const int ix = S.tx[ni], iy = S.ty[nj], iz = S.tz[nk];
+            if (ix >= 0 && iy >= 0 && iz >= 0) {
+              const uint32_t w = __ldg(&map.inflated[((size_t)ix * map.dim[1] + iy) * map.wz + (iz >> 5)]);
+              blocked_map = (w >> (iz & 31)) & 1u;
+            }
+          }
           const bool explored = (raw.x >> 2) == round;
           const uint32_t state = raw.x & 3u;
           if (!(explored && state == ST_CLOSED)) {
@@ -263,11 +462,11 @@ __device__ int astar_search(const DevMap& map, const VigoConst& C, Worker& W, co
               // as the reference's stale-state handling: the cell is skipped on every visit)
               nodes[nl].stamp_state = (round << 2) | ST_CLOSED;
             } else {
-              tentative = gcur + sqrt((double)(dx * dx + dy * dy + dz * dz));
+              const int d2 = dx * dx + dy * dy + dz * dz;
+              const double tentative = gcur + (d2 == 1 ? gstep1 : (d2 == 2 ? gstep2 : gstep3));
               const double gold = __hiloint2double((int)raw.w, (int)raw.z);
               if (!explored) {
                 kind = 1;
-                fnew = tentative + as_heu(ni, nj, nk, ei, ej, ek);
                 uint4 w;
                 w.x = (round << 2) | ST_OPEN;
                 w.y = cur;
@@ -276,7 +475,12 @@ __device__ int astar_search(const DevMap& map, const VigoConst& C, Worker& W, co
                 *reinterpret_cast<uint4*>(&nodes[nl]) = w;
               } else if (tentative < gold) {
                 kind = 2;
-                fnew = tentative + as_heu(ni, nj, nk, ei, ej, ek);
+              }
+              if (kind) {
+                S.st_pos[lane] = hpos;
+                S.st_id[lane] = nid;
+                S.st_g[lane] = tentative;
+                S.st_f[lane] = tentative + as_heu(ni, nj, nk, ei, ej, ek);
               }
             }
           }
@@ -285,58 +489,78 @@ __device__ int astar_search(const DevMap& map, const VigoConst& C, Worker& W, co
     }
     __syncwarp();
     // ---- serial pass in the reference's neighbour order: in-place key updates and pushes
-    unsigned mask = __ballot_sync(0xffffffffu, kind != 0);
+    unsigned mask_new = __ballot_sync(0xffffffffu, kind == 1);
+    unsigned mask_upd = __ballot_sync(0xffffffffu, kind == 2);
+    TICK(tB)
     int overflow = 0;
-    while (mask) {
-      const int L = __ffs(mask) - 1;
-      mask &= mask - 1;
-      const int kL = __shfl_sync(0xffffffffu, kind, L);
-      const uint32_t nL = __shfl_sync(0xffffffffu, nl, L);
-      const double fL = __shfl_sync(0xffffffffu, fnew, L);
-      if (kL == 2) {
-        const double tL = __shfl_sync(0xffffffffu, tentative, L);
-        if (lane == 0) {
-          nodes[nL].parent = cur;
-          nodes[nL].g = tL;
-          H.set_key((int)nodes[nL].heap_pos, fL);
+    if (lane == 0) {
+      // heap_pos values staged above can be stale for entries moved by THIS expansion's earlier
+      // pushes; re-read those through the node record (only when an update follows a push).
+      unsigned m = mask_new | mask_upd;
+      bool pushed = false;
+      while (m) {
+        const int L = __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t nid = S.st_id[L];
+        if ((mask_upd >> L) & 1u) {
+          const uint32_t nl = H.lin_of(nid);
+          nodes[nl].parent = cur;
+          nodes[nl].g = S.st_g[L];
+          const uint32_t pos = pushed ? nodes[nl].heap_pos : S.st_pos[L];
+          H.set_key((int)pos, S.st_f[L]);
+        } else {
+          if (H.size >= C.heap_cap) { overflow = 1; break; }
+          H.push(nid, S.st_f[L]);
+          pushed = true;
         }
-      } else if (lane == 0) {
-        if (H.size >= C.heap_cap) overflow = 1;
-        else H.push(nL, fL);
       }
-      __syncwarp();
     }
+    __syncwarp();
+    TICK(tC)
     if (__any_sync(0xffffffffu, overflow != 0 || (err & ERR_BAND) != 0)) {
       err |= ERR_HEAP_OVERFLOW;
       break;
     }
     if (C.p.astar_max_expansions > 0 && num_iter >= C.p.astar_max_expansions) break;
+    if (num_iter == TP_FLOOD_TRIGGER) {
+      const int hs = __shfl_sync(0xffffffffu, H.size, 0);
+      const int comp = flood_component(map, C, W, hs, si, sj, sk, ei, ej, ek, k_lo);
+      if (comp >= 0) {  // goal unreachable: the search would pop the whole component and fail
+        num_iter = (C.p.astar_max_expansions > 0 && comp > C.p.astar_max_expansions) ? C.p.astar_max_expansions : comp;
+        break;
+      }
+    }
   }
   expansions = num_iter;
+#ifdef TP_ASTAR_TIMING
+  if (lane == 0 && num_iter > 200)
+    printf("[astar] exp %d heap %d cycles/exp: pop %.0f classify %.0f push %.0f\n", num_iter, H.size, (double)tA / num_iter,
+           (double)tB / num_iter, (double)tC / num_iter);
+#endif
   if (result < 0) return -1;
   // ---- retrievePath + getPath (astarOcc.cpp:77-88, 246-254), lane 0
   int len = 0;
   if (lane == 0) {
-    uint32_t p = goal_lin;
+    uint32_t p = goal_id;
     while (p != NODE_NONE) {
       ++len;
-      p = nodes[p].parent;
+      p = nodes[H.lin_of(p)].parent;
     }
     if (len + 1 > C.path_cap) {
       err |= ERR_PATH_OVERFLOW;
       len = -1;
     } else {
-      p = goal_lin;
+      p = goal_id;
       int w = len - 1;
       while (p != NODE_NONE) {
-        int i, j, k;
-        ijk_of(p, i, j, k);
+        const int i = (int)(p >> 16), j = (int)((p >> 8) & 255u);
+        const int k = (p & 255u) == AS_SPARE_KK ? sk : (int)(p & 255u) + k_lo;
         const D3 c = as_index2coord(C, F, i, j, k);
         W.path[3 * w] = c.x;
         W.path[3 * w + 1] = c.y;
         W.path[3 * w + 2] = c.z;
         --w;
-        p = nodes[p].parent;
+        p = nodes[H.lin_of(p)].parent;
       }
     }
   }

@@ -242,17 +242,18 @@ __global__ void __launch_bounds__(TP_LB_THREADS) k_reparam(BatchView bv, VigoCon
 
 // ---- outer loop: one warp (= one block) per worker, trajectories pulled from a queue
 struct PlanSmem {
-  HeapEnt heap[TP_HEAP_SMEM];
+  AStarSmem as;
   uint8_t hit[TP_MAX_CTRL];
   uint8_t line[TP_MAX_CTRL];
   int segA[TP_MAX_SEG_HARD][2];
   int segB[TP_MAX_SEG_HARD][2];
 };
-__device__ __forceinline__ Worker make_worker(const VigoConst& C, const AStarPools& P, int w, int lane, HeapEnt* heap_sm) {
+__device__ __forceinline__ Worker make_worker(const VigoConst& C, const AStarPools& P, int w, int lane, AStarSmem* as) {
   Worker W;
   W.nodes = P.nodes + (size_t)w * (P.pool_nodes + 1);
-  W.heap_sm = heap_sm;
-  W.heap_gl = P.heaps + (size_t)w * C.heap_cap;
+  W.sm = as;
+  W.heap_k_gl = P.heap_k + (size_t)w * C.heap_cap;
+  W.heap_n_gl = P.heap_n + (size_t)w * C.heap_cap;
   W.path = P.paths + (size_t)w * C.path_cap * 3;
   W.sc = P.sc + (size_t)w * C.max_seg * TP_SC_CAP * 3;
   W.sc_len = P.sc_len + (size_t)w * C.max_seg;
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(32) k_plan_init(BatchView bv, VigoConst C, Dev
                                                   int* active_out, int* n_active_out) {
   __shared__ PlanSmem S;
   const int lane = threadIdx.x;
-  Worker W = make_worker(C, P, blockIdx.x, lane, S.heap);
+  Worker W = make_worker(C, P, blockIdx.x, lane, &S.as);
   for (;;) {
     int b = 0;
     if (lane == 0) b = atomicAdd(queue, 1);
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(32) k_plan_step(BatchView bv, VigoConst C, Dev
   __shared__ PlanSmem S;
   __shared__ int prevSeg[TP_MAX_SEG_HARD][2];
   const int lane = threadIdx.x;
-  Worker W = make_worker(C, P, blockIdx.x, lane, S.heap);
+  Worker W = make_worker(C, P, blockIdx.x, lane, &S.as);
   const int n_in = *n_active_in;
   for (;;) {
     int q = 0;
@@ -412,9 +413,9 @@ __global__ void __launch_bounds__(32) k_plan_step(BatchView bv, VigoConst C, Dev
 __global__ void __launch_bounds__(32) k_astar(VigoConst C, DevMap map, AStarPools P, int* queue, int S_,
                                               const double* __restrict__ starts, const double* __restrict__ ends,
                                               int* path_len, double* paths, int* expansions) {
-  __shared__ HeapEnt heap_sm[TP_HEAP_SMEM];
+  __shared__ AStarSmem as_sm;
   const int lane = threadIdx.x;
-  Worker W = make_worker(C, P, blockIdx.x, lane, heap_sm);
+  Worker W = make_worker(C, P, blockIdx.x, lane, &as_sm);
   for (;;) {
     int s = 0;
     if (lane == 0) s = atomicAdd(queue, 1);
@@ -515,7 +516,7 @@ struct tp_engine {
   double tab_check_ts = -1, tab_ts = -1, tab_res = -1;
   // A* pools
   AStarPools pools;
-  DevBuf pool_nodes, pool_heaps, pool_paths, pool_sc, pool_sclen, pool_rounds;
+  DevBuf pool_nodes, pool_heaps, pool_heapn, pool_paths, pool_sc, pool_sclen, pool_rounds;
   int pools_key[8] = {0};
   // batch buffers
   DevBuf off, ctrl, st, pairs, cp_head, cp_tail, active[2], counters, results, dyn, scratch_a, scratch_b, scratch_c;
@@ -596,6 +597,7 @@ static void make_const(const tp_engine* e, const tp_vigo_params* p, VigoConst& C
   for (int a = 0; a < 3; ++a) C.pool[a] = 2 * (int)(p->max_obstacle_size[a] / e->map_res);  // :191-193
   int kl = (int)((p->max_height - p->min_height) / e->map_res) + 3;
   if (kl > C.pool[2]) kl = C.pool[2];
+  if (kl > 254) kl = 254;   // packed node ids keep the layer in 8 bits (255 = spare slot)
   if (kl < 1) kl = 1;
   C.pool_kl = kl;
   C.max_seg = e->cfg.max_segments;
@@ -656,7 +658,7 @@ static int ensure_pools(tp_engine* e, const VigoConst& C) {
   const int key[8] = {C.pool[0], C.pool[1], C.pool_kl, C.heap_cap, C.path_cap, C.max_seg, 0, 0};
   if (memcmp(key, e->pools_key, sizeof(key)) == 0 && e->pools.workers > 0) return TP_OK;
   const size_t pool_nodes = (size_t)C.pool[0] * C.pool[1] * C.pool_kl;
-  const size_t per_worker = (pool_nodes + 1) * sizeof(ANode) + (size_t)C.heap_cap * sizeof(HeapEnt) + (size_t)C.path_cap * 24 +
+  const size_t per_worker = (pool_nodes + 1) * sizeof(ANode) + (size_t)C.heap_cap * 12 + (size_t)C.path_cap * 24 +
                             (size_t)C.max_seg * TP_SC_CAP * 24 + (size_t)C.max_seg * 4 + 4;
   int workers = e->cfg.astar_workers;
   if (workers <= 0) {
@@ -670,7 +672,8 @@ static int ensure_pools(tp_engine* e, const VigoConst& C) {
   }
   if (workers < 1) workers = 1;
   if (e->pool_nodes.ensure((size_t)workers * (pool_nodes + 1) * sizeof(ANode)) != TP_OK) return TP_ERR_CUDA;
-  if (e->pool_heaps.ensure((size_t)workers * C.heap_cap * sizeof(HeapEnt)) != TP_OK) return TP_ERR_CUDA;
+  if (e->pool_heaps.ensure((size_t)workers * C.heap_cap * 8) != TP_OK) return TP_ERR_CUDA;
+  if (e->pool_heapn.ensure((size_t)workers * C.heap_cap * 4) != TP_OK) return TP_ERR_CUDA;
   if (e->pool_paths.ensure((size_t)workers * C.path_cap * 24) != TP_OK) return TP_ERR_CUDA;
   if (e->pool_sc.ensure((size_t)workers * C.max_seg * TP_SC_CAP * 24) != TP_OK) return TP_ERR_CUDA;
   if (e->pool_sclen.ensure((size_t)workers * C.max_seg * 4) != TP_OK) return TP_ERR_CUDA;
@@ -679,7 +682,8 @@ static int ensure_pools(tp_engine* e, const VigoConst& C) {
   CK(cudaMemsetAsync(e->pool_rounds.p, 0, (size_t)workers * 4, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   e->pools.nodes = e->pool_nodes.as<ANode>();
-  e->pools.heaps = e->pool_heaps.as<HeapEnt>();
+  e->pools.heap_k = e->pool_heaps.as<double>();
+  e->pools.heap_n = e->pool_heapn.as<uint32_t>();
   e->pools.paths = e->pool_paths.as<double>();
   e->pools.sc = e->pool_sc.as<double>();
   e->pools.sc_len = e->pool_sclen.as<int>();
@@ -697,6 +701,13 @@ static int check_params(const tp_engine* e, const tp_vigo_params* p) {
       p->lbfgs_max_linesearch < 1) {
     tp_set_error("invalid ViGO parameters");
     return TP_ERR_INVALID_ARG;
+  }
+  for (int a = 0; a < 3; ++a) {
+    const int pool = 2 * (int)(p->max_obstacle_size[a] / e->map_res);
+    if (pool < 4 || pool > TP_AXIS_MAX) {
+      tp_set_error("A* pool of %d cells along axis %d (2*int(max_obstacle_size/res)) is outside [4, %d]", pool, a, TP_AXIS_MAX);
+      return TP_ERR_CAPACITY;
+    }
   }
   return TP_OK;
 }
@@ -909,7 +920,7 @@ void tp_engine_destroy(tp_engine_t* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
-  DevBuf* bufs[] = {&e->map_infl, &e->map_known, &e->t_check, &e->t_reparam, &e->a_line, &e->pool_nodes, &e->pool_heaps,
+  DevBuf* bufs[] = {&e->map_infl, &e->map_known, &e->t_check, &e->t_reparam, &e->a_line, &e->pool_nodes, &e->pool_heaps, &e->pool_heapn,
                     &e->pool_paths, &e->pool_sc, &e->pool_sclen, &e->pool_rounds, &e->off, &e->ctrl, &e->st, &e->pairs,
                     &e->cp_head, &e->cp_tail, &e->active[0], &e->active[1], &e->counters, &e->results, &e->dyn,
                     &e->scratch_a, &e->scratch_b, &e->scratch_c};

@@ -58,20 +58,29 @@ struct VigoConst {
 
 struct ANode {  // one A* grid node (astarOcc.h:16-31), 32 B = one sector; first 16 B = one LDG.128
   uint32_t stamp_state;  // (round << 2) | state
-  uint32_t parent;
+  uint32_t parent;       // packed id of cameFrom
   double g;
   uint32_t heap_pos;     // position of this node's entry in the open-set heap (valid while OPEN)
   uint32_t pad0;
   uint64_t pad1;
 };
-// open-set heap entry: the key is cached beside the node id so that the sift loops never leave
-// shared memory; in-place key updates (astarOcc.cpp:223-228) patch the cached copy via heap_pos.
-struct HeapEnt {
-  double f;
-  uint32_t node;
-  uint32_t pad;
+// Open-set heap: keys (fScore) and node ids in two dense shared-memory arrays, so that a sift level
+// costs one LDS pair + one compare; entries beyond TP_HEAP_SMEM spill to HBM.  In-place key updates
+// (astarOcc.cpp:223-228) patch the cached key through the node's heap_pos, which every sift keeps
+// current with fire-and-forget stores and the neighbour evaluation loads speculatively.
+#define TP_HEAP_SMEM 2048
+#define TP_AXIS_MAX 256   // A* pool cells per axis (2*int(max_obstacle_size/res)) the tables accept
+struct AStarSmem {
+  double hk[TP_HEAP_SMEM];
+  uint32_t hn[TP_HEAP_SMEM];
+  // per-search lookup tables: map cell index of pool index i/j/k along each axis (-1 = outside the
+  // map), computed once with the reference's own FP expressions (Index2Coord -> posToIndex)
+  short tx[TP_AXIS_MAX], ty[TP_AXIS_MAX], tz[TP_AXIS_MAX];
+  unsigned char band[TP_AXIS_MAX];  // cell centre z inside [min_height, max_height] (astarOcc.cpp:202)
+  // staging of one expansion's accepted neighbours for the serial pass
+  double st_f[32], st_g[32];
+  uint32_t st_id[32], st_pos[32];
 };
-#define TP_HEAP_SMEM 1024  // heap entries kept in shared memory per search; the rest spills to HBM
 
 struct BatchView {
   int B;
@@ -92,8 +101,9 @@ struct BatchView {
 };
 
 struct AStarPools {
-  ANode* nodes;        // [workers * pool_nodes]
-  HeapEnt* heaps;      // [workers * heap_cap]   spill area for heap entries >= TP_HEAP_SMEM
+  ANode* nodes;        // [workers * (pool_nodes + 1)]
+  double* heap_k;      // [workers * heap_cap]   spill area for heap entries >= TP_HEAP_SMEM
+  uint32_t* heap_n;    // [workers * heap_cap]
   double* paths;       // [workers * path_cap * 3]
   double* sc;          // [workers * max_seg * TP_SC_CAP * 3]   shortcut paths
   int* sc_len;         // [workers * max_seg]
