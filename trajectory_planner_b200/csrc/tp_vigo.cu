@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "tp_lbfgs.cuh"
+#include "tp_lbfgs_fast.cuh"
 #include "tp_map.h"
 #include "tp_outer.cuh"
 
@@ -78,6 +79,27 @@ __global__ void __launch_bounds__(TP_LB_THREADS) k_cost(BatchView bv, VigoConst 
     if (tid == 0) f_out[b] = 0.0;
     return;
   }
+  if (!STRICT) {
+    // the throughput form of the evaluation (tp_lbfgs_fast.cuh) — what the default solve kernel runs
+    VfCtx V;
+    V.N = N; V.n = n; V.sm = sm; V.L = vf_layout(N);
+    V.pairs = bv.pairs + (size_t)b * C.gcap; V.head = bv.cp_head + st.off; V.n_pairs = st.n_pairs; V.pairs_in_sm = false;
+    V.w_dist = st.w_dist; V.w_dyn = st.w_dyn;
+    V.n_dyn = bv.n_dyn; V.dyn_pos = bv.dyn_pos; V.dyn_vel = bv.dyn_vel; V.dyn_size = bv.dyn_size;
+    for (int e = tid; e < 3 * N; e += TP_LB_THREADS) sm[V.L.cp + e] = bv.ctrl[3 * (size_t)st.off + e];
+    __syncthreads();
+    vf_stage_pairs(V, tid);
+    __syncthreads();
+    Red R2;
+    R2.buf = sm + V.L.red;
+    R2.flip = 0;
+    double f, dg, gg, xx;
+    vf_eval(C, V, R2, false, f, dg, gg, xx, tid);
+    if (tid == 0) f_out[b] = f;
+    double* go = grad_out + 3 * ((size_t)st.off - (size_t)2 * TP_DEGREE * b);
+    for (int e = tid; e < n; e += TP_LB_THREADS) go[e] = sm[V.L.g + e];
+    return;
+  }
   double* cp = sm;
   double* g = cp + 3 * N;
   Red R;
@@ -98,9 +120,10 @@ __global__ void __launch_bounds__(TP_LB_THREADS) k_cost(BatchView bv, VigoConst 
   for (int e = tid; e < n; e += TP_LB_THREADS) go[e] = g[e];
 }
 
-// ---- optimize(): fused cost + L-BFGS, one block per ACTIVE trajectory
-template <bool STRICT>
-__global__ void __launch_bounds__(TP_LB_THREADS) k_lbfgs(BatchView bv, VigoConst C, const int* __restrict__ active,
+// ---- optimize(): fused cost + L-BFGS, one block per ACTIVE trajectory.
+// MODE 0: classic two-loop, tree reductions; 1: classic, serial-order (bit-faithful); 2: vector-free (tp_lbfgs_fast.cuh)
+template <int MODE>
+__global__ void __launch_bounds__(TP_LB_THREADS, 4) k_lbfgs(BatchView bv, VigoConst C, const int* __restrict__ active,
                                                          const int* __restrict__ n_active, tp_lbfgs_result* res_out,
                                                          double* xfinal_out, double* counters) {
   extern __shared__ double sm[];
@@ -122,7 +145,16 @@ __global__ void __launch_bounds__(TP_LB_THREADS) k_lbfgs(BatchView bv, VigoConst
     E.w_dist = st.w_dist; E.w_dyn = st.w_dyn;
     E.n_dyn = bv.n_dyn; E.dyn_pos = bv.dyn_pos; E.dyn_vel = bv.dyn_vel; E.dyn_size = bv.dyn_size;
     double* xf = xfinal_out ? xfinal_out + 3 * ((size_t)st.off - (size_t)2 * TP_DEGREE * b) : nullptr;
-    lbfgs_run<STRICT>(C, E, cp + 3 * N, r, xf, tid);
+    if (MODE == 2) {
+      VfCtx V;
+      V.N = N; V.n = n; V.sm = sm; V.L = vf_layout(N);
+      V.pairs = E.pairs; V.head = E.head; V.n_pairs = st.n_pairs; V.pairs_in_sm = false;
+      V.w_dist = E.w_dist; V.w_dyn = E.w_dyn;
+      V.n_dyn = E.n_dyn; V.dyn_pos = E.dyn_pos; V.dyn_vel = E.dyn_vel; V.dyn_size = E.dyn_size;
+      lbfgs_run_fast(C, V, r, xf, tid);
+    } else {
+      lbfgs_run<MODE == 1>(C, E, cp + 3 * N, r, xf, tid);
+    }
     // the control points keep the last evaluated point (bsplineTraj.cpp:803)
     for (int e = tid; e < n; e += TP_LB_THREADS) gctrl[3 * TP_DEGREE + e] = cp[3 * TP_DEGREE + e];
   }
@@ -144,27 +176,15 @@ __global__ void __launch_bounds__(TP_LB_THREADS) k_lbfgs(BatchView bv, VigoConst
   }
 }
 
-// ---- hasCollisionTrajectory (+ hasDynamicCollisionTrajectory), one block per active trajectory
+// ---- hasCollisionTrajectory (+ hasDynamicCollisionTrajectory), block-wide on control points in shared memory
 struct SmemCP {
   const double* p;
   __device__ __forceinline__ D3 operator()(int i) const { return d3(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }
 };
-__global__ void __launch_bounds__(TP_LB_THREADS) k_has_collision(BatchView bv, VigoConst C, DevMap map,
-                                                                 const int* __restrict__ active,
-                                                                 const int* __restrict__ n_active, uint8_t* hit_out,
-                                                                 double* counters) {
-  extern __shared__ double sm[];
-  if ((int)blockIdx.x >= *n_active) return;
-  const int b = active[blockIdx.x], tid = threadIdx.x;
-  TrajState& st = bv.st[b];
-  const int N = st.N;
-  if (N < 4) {
-    if (tid == 0) { st.has_col = 1; if (hit_out) hit_out[b] = 1; }
-    return;
-  }
-  for (int e = tid; e < 3 * N; e += TP_LB_THREADS) sm[e] = bv.ctrl[3 * (size_t)st.off + e];
-  __syncthreads();
-  SmemCP cp{sm};
+// returns static | dynamic << 1 to every thread (contains a block barrier)
+__device__ __forceinline__ int dev_has_collision(const double* cps, int N, const BatchView& bv, const VigoConst& C,
+                                                 const DevMap& map, int tid) {
+  SmemCP cp{cps};
   const double cts = C.p.ctrl_pt_ts;
   const double duration = (double)(N - TP_DEGREE) * cts;          // knots_(N), bspline.cpp:27
   const double limit = (1.0 - C.p.not_check_ratio) * duration;    // bsplineTraj.h:313
@@ -181,28 +201,37 @@ __global__ void __launch_bounds__(TP_LB_THREADS) k_has_collision(BatchView bv, V
       if (dist < 0) dyn = 1;
     }
   }
-  const int any = __syncthreads_or(hit | (dyn << 1));
+  return __syncthreads_or(hit | (dyn << 1));
+}
+__global__ void __launch_bounds__(TP_LB_THREADS) k_has_collision(BatchView bv, VigoConst C, DevMap map,
+                                                                 const int* __restrict__ active,
+                                                                 const int* __restrict__ n_active, uint8_t* hit_out,
+                                                                 double* counters) {
+  extern __shared__ double sm[];
+  if ((int)blockIdx.x >= *n_active) return;
+  const int b = active[blockIdx.x], tid = threadIdx.x;
+  TrajState& st = bv.st[b];
+  const int N = st.N;
+  if (N < 4) {
+    if (tid == 0) { st.has_col = 1; if (hit_out) hit_out[b] = 1; }
+    return;
+  }
+  for (int e = tid; e < 3 * N; e += TP_LB_THREADS) sm[e] = bv.ctrl[3 * (size_t)st.off + e];
+  __syncthreads();
+  const int any = dev_has_collision(sm, N, bv, C, map, tid);
   if (tid == 0) {
     st.has_col = any;
     if (hit_out) hit_out[b] = (uint8_t)(any & 1);
-    if (counters) atomicAdd(&counters[3], floor(duration / C.check_ts) + 1.0);
+    if (counters) atomicAdd(&counters[3], floor((double)(N - TP_DEGREE) * C.p.ctrl_pt_ts / C.check_ts) + 1.0);
   }
 }
 
-// ---- linearFeasibilityReparam (bsplineTraj.cpp:1116-1137), one block per trajectory
-__global__ void __launch_bounds__(TP_LB_THREADS) k_reparam(BatchView bv, VigoConst C) {
-  extern __shared__ double sm[];
-  __shared__ double redv[TP_LB_WARPS], reda[TP_LB_WARPS];
-  const int b = blockIdx.x, tid = threadIdx.x;
-  TrajState& st = bv.st[b];
-  if (st.status != TP_STATUS_SUCCESS) return;
-  const int N = st.N;
-  double* cp = sm;
-  double* q = cp + 3 * N;        // velocity spline control points (N-1), bspline.cpp:64-72
-  double* r = q + 3 * (N - 1);   // acceleration spline control points (N-2)
+// ---- linearFeasibilityReparam (bsplineTraj.cpp:1116-1137), block-wide.  cp: control points (shared),
+// q / r: scratch for the velocity / acceleration spline control points (3(N-1), 3(N-2) doubles, shared),
+// red: 2 * TP_LB_WARPS doubles (shared).  Returns the factor to thread 0.
+__device__ __forceinline__ double dev_reparam(const double* cp, double* q, double* r, double* red, int N, const BatchView& bv,
+                                              const VigoConst& C, int tid) {
   const double ts = C.p.ctrl_pt_ts;
-  for (int e = tid; e < 3 * N; e += TP_LB_THREADS) cp[e] = bv.ctrl[3 * (size_t)st.off + e];
-  __syncthreads();
   for (int e = tid; e < 3 * (N - 1); e += TP_LB_THREADS) {
     const int i = e / 3;
     const double den = (double)(i + 3 + 1 - 3) * ts - (double)(i + 1 - 3) * ts;  // knots_(i+p+1) - knots_(i+1), p = 3
@@ -230,23 +259,39 @@ __global__ void __launch_bounds__(TP_LB_THREADS) k_reparam(BatchView bv, VigoCon
     mv = fmax(mv, __shfl_xor_sync(0xffffffffu, mv, o));
     ma = fmax(ma, __shfl_xor_sync(0xffffffffu, ma, o));
   }
-  if ((tid & 31) == 0) { redv[tid >> 5] = mv; reda[tid >> 5] = ma; }
+  if ((tid & 31) == 0) { red[tid >> 5] = mv; red[TP_LB_WARPS + (tid >> 5)] = ma; }
   __syncthreads();
+  double f = 1.0;
   if (tid == 0) {
-    for (int w = 1; w < TP_LB_WARPS; ++w) { mv = fmax(mv, redv[w]); ma = fmax(ma, reda[w]); }
+    for (int w = 1; w < TP_LB_WARPS; ++w) { mv = fmax(mv, red[w]); ma = fmax(ma, red[TP_LB_WARPS + w]); }
     const double fv = C.p.max_vel / mv;
     const double fa = sqrt(C.p.max_acc / ma);
-    st.linear_factor = fmin(fv, fa);
+    f = fmin(fv, fa);
   }
+  return f;
+}
+__global__ void __launch_bounds__(TP_LB_THREADS) k_reparam(BatchView bv, VigoConst C) {
+  extern __shared__ double sm[];
+  __shared__ double red[2 * TP_LB_WARPS];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  TrajState& st = bv.st[b];
+  if (st.status != TP_STATUS_SUCCESS) return;
+  const int N = st.N;
+  double* cp = sm;
+  for (int e = tid; e < 3 * N; e += TP_LB_THREADS) cp[e] = bv.ctrl[3 * (size_t)st.off + e];
+  __syncthreads();
+  const double f = dev_reparam(cp, cp + 3 * N, cp + 3 * N + 3 * (N - 1), red, N, bv, C, tid);
+  if (tid == 0) st.linear_factor = f;
 }
 
-// ---- outer loop: one warp (= one block) per worker, trajectories pulled from a queue
+// ---- outer loop pieces, one warp per trajectory
 struct PlanSmem {
   AStarSmem as;
   uint8_t hit[TP_MAX_CTRL];
   uint8_t line[TP_MAX_CTRL];
   int segA[TP_MAX_SEG_HARD][2];
   int segB[TP_MAX_SEG_HARD][2];
+  int prevSeg[TP_MAX_SEG_HARD][2];
 };
 __device__ __forceinline__ Worker make_worker(const VigoConst& C, const AStarPools& P, int w, int lane, AStarSmem* as) {
   Worker W;
@@ -262,7 +307,131 @@ __device__ __forceinline__ Worker make_worker(const VigoConst& C, const AStarPoo
   return W;
 }
 
-// makePlan steps 1-3 (bsplineTraj.cpp:341-352)
+// makePlan steps 1-3 (bsplineTraj.cpp:341-352) for trajectory b; `bv.ctrl + 3*st.off` are its control points
+// (global or shared).  Leaves st.status == TS_ACTIVE when the solve goes on.
+__device__ void dev_plan_init(const BatchView& bv, const VigoConst& C, const DevMap& map, TrajState& st, Worker& W,
+                              PlanSmem& S, int b, int lane) {
+  int err = 0;
+  if (st.N < 2 * TP_DEGREE + 1 || st.N > TP_MAX_CTRL) {
+    if (lane == 0) st.status = TP_STATUS_INVALID;
+    __syncwarp();
+    return;
+  }
+  int nseg = find_collision_seg(map, C, bv, st, S.hit, S.line, S.segA, lane, err);
+  const int npaths = path_search(map, C, bv, st, W, S.segA, nseg, err);
+  if (lane == 0) {
+    st.nseg = nseg;
+    for (int i = 0; i < nseg; ++i) { st.seg[i][0] = S.segA[i][0]; st.seg[i][1] = S.segA[i][1]; }
+    if (npaths < 0) st.status = TP_STATUS_FAIL_ASTAR;
+    else assign_guides(map, C, bv, b, st, W, S.segA, nseg, npaths);
+    st.err |= err;
+  }
+  __syncwarp();
+}
+
+// body of optimizeTrajectory's loop after the collision check (bsplineTraj.cpp:628-679).  Sets st.status to a
+// final value or leaves TS_ACTIVE (another optimize() follows).
+__device__ void dev_plan_step(const BatchView& bv, const VigoConst& C, const DevMap& map, TrajState& st, Worker& W,
+                              PlanSmem& S, int b, int lane) {
+  int err = 0;
+  const int hasCol = st.has_col & 1, hasDyn = (st.has_col >> 1) & 1;
+  if (!hasCol && !hasDyn) {  // :628-630 -> :682-684
+    if (lane == 0) {
+      st.w_dist = C.p.w_distance;
+      st.w_dyn = C.p.w_dyn;
+      st.status = TP_STATUS_SUCCESS;
+    }
+    __syncwarp();
+    return;
+  }
+  if (st.round == 0 && lane == 0) st.vclock = 0;  // the reference starts its timer after the first optimize() (:618)
+  __syncwarp();
+  // deterministic replacements of the 0.03 s wall clock (:632-638): virtual clock + round cap
+  if (st.round >= C.p.max_outer_rounds || (C.p.vclock_budget > 0 && st.vclock > (long long)C.p.vclock_budget)) {
+    if (lane == 0) {
+      st.w_dist = C.p.w_distance;
+      st.w_dyn = C.p.w_dyn;
+      st.status = TP_STATUS_FAIL_OPTIMIZE;
+    }
+    __syncwarp();
+    return;
+  }
+  const int fail_in = st.fail_count;
+  if (fail_in >= 4) {  // :640-648
+    int nseg = find_collision_seg(map, C, bv, st, S.hit, S.line, S.segA, lane, err);
+    const int np = path_search(map, C, bv, st, W, S.segA, nseg, err);
+    if (np >= 0 && lane == 0) assign_guides(map, C, bv, b, st, W, S.segA, nseg, np);
+    __syncwarp();
+  }
+  if (fail_in >= 8) {  // :650-654
+    if (lane == 0) {
+      st.round += 1;
+      st.w_dist = C.p.w_distance;
+      st.w_dyn = C.p.w_dyn;
+      st.status = TP_STATUS_FAIL_OPTIMIZE;
+      st.err |= err;
+    }
+    __syncwarp();
+    return;
+  }
+  int add_fail = 0;
+  if (hasCol) {
+    // ---- isReguideRequired (:573-608)
+    const int nprev = st.nseg;
+    for (int i = lane; i < nprev; i += 32) { S.prevSeg[i][0] = st.seg[i][0]; S.prevSeg[i][1] = st.seg[i][1]; }
+    __syncwarp();
+    const int nnew = find_collision_seg(map, C, bv, st, S.hit, S.line, S.segA, lane, err);
+    int nre = 0;
+    if (lane == 0) {
+      st.nseg = nnew;
+      for (int i = 0; i < nnew; ++i) { st.seg[i][0] = S.segA[i][0]; st.seg[i][1] = S.segA[i][1]; }
+      // compareCollisionSeg (bsplineTraj.h:379-403) + set<int> of segment indices
+      unsigned long long need = 0ull;  // bit i: segment i needs a re-guide (max_seg <= 64)
+      for (int sidx = 0; sidx < nnew; ++sidx) {
+        const int s0 = S.segA[sidx][0], s1 = S.segA[sidx][1];
+        auto visit = [&](int i) {
+          const bool overl = index_in_seg(S.prevSeg, nprev, i);
+          if (!overl || cp_requires_new_guide(C, bv, b, st, i)) {
+            const int k = find_seg_index(S.segA, nnew, i);
+            if (k >= 0) need |= (1ull << k);
+          }
+        };
+        for (int i = s0 + 1; i <= s1 - 1; ++i) visit(i);
+        if (s1 - s0 - 1 == 0)
+          for (int i = s0; i <= s1; ++i) visit(i);
+      }
+      for (int k = 0; k < nnew; ++k)
+        if ((need >> k) & 1ull) {
+          S.segB[nre][0] = S.segA[k][0];
+          S.segB[nre][1] = S.segA[k][1];
+          ++nre;
+        }
+    }
+    nre = __shfl_sync(0xffffffffu, nre, 0);
+    __syncwarp();
+    if (nre > 0) {
+      int nre2 = nre;
+      const int np = path_search(map, C, bv, st, W, S.segB, nre2, err);
+      if (np >= 0) {
+        if (lane == 0) assign_guides(map, C, bv, b, st, W, S.segB, nre2, np);
+      } else
+        add_fail = 1;
+    } else
+      add_fail = 1;
+  }
+  if (lane == 0) {
+    st.round += 1;
+    if (add_fail) {
+      st.w_dist *= 2.0;
+      st.fail_count += 1;
+    }
+    if (hasDyn) st.w_dyn *= 2.0;
+    st.err |= err;
+  }
+  __syncwarp();
+}
+
+// standalone steps 1-3 (parity entry tp_vigo_init_guides_batch): one warp per worker, trajectories from a queue
 __global__ void __launch_bounds__(32) k_plan_init(BatchView bv, VigoConst C, DevMap map, AStarPools P, int* queue,
                                                   int* active_out, int* n_active_out) {
   __shared__ PlanSmem S;
@@ -274,138 +443,154 @@ __global__ void __launch_bounds__(32) k_plan_init(BatchView bv, VigoConst C, Dev
     b = __shfl_sync(0xffffffffu, b, 0);
     if (b >= bv.B) break;
     TrajState& st = bv.st[b];
-    int err = 0;
-    if (st.N < 2 * TP_DEGREE + 1 || st.N > TP_MAX_CTRL) {
-      if (lane == 0) st.status = TP_STATUS_INVALID;
-      continue;
-    }
-    int nseg = find_collision_seg(map, C, bv, st, S.hit, S.line, S.segA, lane, err);
-    const int npaths = path_search(map, C, bv, st, W, S.segA, nseg, err);
-    if (lane == 0) {
-      st.nseg = nseg;
-      for (int i = 0; i < nseg; ++i) { st.seg[i][0] = S.segA[i][0]; st.seg[i][1] = S.segA[i][1]; }
-      if (npaths < 0) {
-        st.status = TP_STATUS_FAIL_ASTAR;
-      } else {
-        assign_guides(map, C, bv, b, st, W, S.segA, nseg, npaths);
-        active_out[atomicAdd(n_active_out, 1)] = b;
-      }
-      st.err |= err;
-    }
+    dev_plan_init(bv, C, map, st, W, S, b, lane);
+    if (lane == 0 && st.status == TS_ACTIVE) active_out[atomicAdd(n_active_out, 1)] = b;
     __syncwarp();
   }
 }
 
-// body of optimizeTrajectory's loop after the collision check (bsplineTraj.cpp:628-679)
-__global__ void __launch_bounds__(32) k_plan_step(BatchView bv, VigoConst C, DevMap map, AStarPools P, int* queue,
-                                                  const int* __restrict__ active_in, const int* __restrict__ n_active_in,
-                                                  int* active_out, int* n_active_out) {
-  __shared__ PlanSmem S;
-  __shared__ int prevSeg[TP_MAX_SEG_HARD][2];
-  const int lane = threadIdx.x;
-  Worker W = make_worker(C, P, blockIdx.x, lane, &S.as);
-  const int n_in = *n_active_in;
-  for (;;) {
-    int q = 0;
-    if (lane == 0) q = atomicAdd(queue, 1);
-    q = __shfl_sync(0xffffffffu, q, 0);
-    if (q >= n_in) break;
-    const int b = active_in[q];
-    TrajState& st = bv.st[b];
-    int err = 0;
-    const int hasCol = st.has_col & 1, hasDyn = (st.has_col >> 1) & 1;
-    if (!hasCol && !hasDyn) {  // :628-630 -> :682-684
-      if (lane == 0) {
-        st.w_dist = C.p.w_distance;
-        st.w_dyn = C.p.w_dyn;
-        st.status = TP_STATUS_SUCCESS;
+// ---- THE batched entry point's kernel: bsplineTraj::makePlan (bsplineTraj.cpp:333-385) for one trajectory
+// per thread block, start to finish: segments -> A* detours -> guide points -> [fused cost+L-BFGS ->
+// collision check -> re-guide / weight doubling]* -> time re-parameterisation.  Trajectories progress
+// independently (no lock-step rounds, no host round trips): a long A* search or a 15-round solve delays
+// only its own block while the hardware block scheduler back-fills the SM.  Warp 0 runs the serial
+// outer-loop logic (lane-parallel map queries); all four warps run the solver, the collision check and
+// the re-parameterisation.  Shared memory: control points + trajectory state persist; the solver state
+// and the A* heap / tables alias each other (they are never live at the same time).
+// Blocks are issued longest trajectory first (`order`); the launch is per size class so that the
+// shared-memory footprint (and with it the blocks resident per SM) follows the trajectories' length.
+struct SolveLayout {
+  int st;      // TrajState (doubles offset)
+  int vf;      // start of the solver region (cp first)
+  int plan;    // PlanSmem (aliases the solver region after cp)
+  int total;   // doubles
+};
+__host__ __device__ inline SolveLayout solve_layout(int N, int mode, int m) {
+  SolveLayout L;
+  int o = 0;
+  L.st = o; o += (int)((sizeof(TrajState) + 7) / 8);
+  L.vf = o;
+  const int cp_d = 3 * N + (N & 1);
+  const int solver = mode == 2 ? vf_layout(N).total : (int)lbfgs_smem_doubles(N, m) + (N & 1);
+  L.plan = L.vf + cp_d;
+  const int plan_end = L.plan + (int)((sizeof(PlanSmem) + 7) / 8);
+  const int rp_end = L.plan + 3 * (N - 1) + 3 * (N - 2) + 2 * TP_LB_WARPS + 4;
+  int end = L.vf + solver;
+  if (plan_end > end) end = plan_end;
+  if (rp_end > end) end = rp_end;
+  L.total = end;
+  return L;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(TP_LB_THREADS, 4) k_solve(BatchView bv, VigoConst C, DevMap map, AStarPools P,
+                                                            const int* __restrict__ order, int class_max_n,
+                                                            int* slot_flags, double* counters) {
+  extern __shared__ double sm[];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int b = order[blockIdx.x];
+  const SolveLayout SL = solve_layout(class_max_n, MODE, C.p.lbfgs_m);
+  TrajState& st = *reinterpret_cast<TrajState*>(sm + SL.st);
+  double* cp = sm + SL.vf;
+  PlanSmem& PS = *reinterpret_cast<PlanSmem*>(sm + SL.plan);
+  // ---- load state + control points
+  {
+    const int* src = reinterpret_cast<const int*>(&bv.st[b]);
+    int* dst = reinterpret_cast<int*>(&st);
+    for (int i = tid; i < (int)(sizeof(TrajState) / 4); i += TP_LB_THREADS) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int N = st.N, n = 3 * (N - 2 * TP_DEGREE);
+  double* gctrl = bv.ctrl + 3 * (size_t)st.off;
+  for (int e = tid; e < 3 * N; e += TP_LB_THREADS) cp[e] = gctrl[e];
+  // ---- claim an A* node pool (one per resident block)
+  if (tid == 0) {
+    const int W_ = P.workers;
+    int sidx = (int)(((unsigned)blockIdx.x * 2654435761u) % (unsigned)W_);
+    while (atomicCAS(&slot_flags[sidx], 0, 1) != 0) sidx = sidx + 1 == W_ ? 0 : sidx + 1;
+    st.pad = sidx;
+  }
+  __syncthreads();
+  const int s_slot = st.pad;
+  BatchView lbv = bv;                      // the outer-loop code reads control points through bv.ctrl + 3*off
+  lbv.ctrl = cp - 3 * (size_t)st.off;
+  Worker W = make_worker(C, P, s_slot, lane, &PS.as);
+  // ---- makePlan steps 1-3
+  if (tid < 32) dev_plan_init(lbv, C, map, st, W, PS, b, lane);
+  __syncthreads();
+  double fl = 0.0, its = 0.0, evs = 0.0, smp = 0.0;
+  while (st.status == TS_ACTIVE) {
+    // ---- optimize()
+    tp_lbfgs_result r;
+    if (n <= 0) {
+      r.ret = LB_INVALID_N; r.iters = 0; r.evals = 0; r.reserved = 0; r.fx = 0;
+    } else if (MODE == 2) {
+      VfCtx V;
+      V.N = N; V.n = n; V.sm = cp; V.L = vf_layout(N);
+      V.pairs = bv.pairs + (size_t)b * C.gcap; V.head = bv.cp_head + st.off; V.n_pairs = st.n_pairs; V.pairs_in_sm = false;
+      V.w_dist = st.w_dist; V.w_dyn = st.w_dyn;
+      V.n_dyn = bv.n_dyn; V.dyn_pos = bv.dyn_pos; V.dyn_vel = bv.dyn_vel; V.dyn_size = bv.dyn_size;
+      lbfgs_run_fast(C, V, r, nullptr, tid);
+    } else {
+      EvalCtx E;
+      E.N = N; E.n = n; E.cp = cp;
+      E.pairs = bv.pairs + (size_t)b * C.gcap;
+      E.head = bv.cp_head + st.off;
+      E.w_dist = st.w_dist; E.w_dyn = st.w_dyn;
+      E.n_dyn = bv.n_dyn; E.dyn_pos = bv.dyn_pos; E.dyn_vel = bv.dyn_vel; E.dyn_size = bv.dyn_size;
+      lbfgs_run<MODE == 1>(C, E, cp + 3 * N + (N & 1), r, nullptr, tid);
+    }
+    if (tid == 0) {
+      st.lbfgs_runs += 1;
+      st.lbfgs_iters += r.iters;
+      st.lbfgs_evals += r.evals;
+      st.last_ret = r.ret;
+      st.final_cost = r.fx;
+      if (n > 0) {
+        st.vclock += (long long)r.evals * (10LL * N + 2LL * n);
+        // algorithmic FP64 flops: E(81N + 21G + 4n) + sum_k (8 b_k + 15) n
+        fl += (double)r.evals * (81.0 * N + 21.0 * st.n_pairs + 4.0 * n) + (8.0 * r.reserved + 15.0 * r.iters) * n;
+        its += r.iters;
+        evs += r.evals;
       }
-      continue;
     }
-    if (st.round == 0 && lane == 0) st.vclock = 0;  // the reference starts its timer after the first optimize() (:618)
-    __syncwarp();
-    // deterministic replacements of the 0.03 s wall clock (:632-638): virtual clock + round cap
-    if (st.round >= C.p.max_outer_rounds || (C.p.vclock_budget > 0 && st.vclock > (long long)C.p.vclock_budget)) {
-      if (lane == 0) {
-        st.w_dist = C.p.w_distance;
-        st.w_dyn = C.p.w_dyn;
-        st.status = TP_STATUS_FAIL_OPTIMIZE;
-      }
-      continue;
+    // ---- hasCollisionTrajectory
+    int any = 1;
+    if (N >= 4) any = dev_has_collision(cp, N, bv, C, map, tid);
+    if (tid == 0) {
+      st.has_col = any;
+      smp += floor((double)(N - TP_DEGREE) * C.p.ctrl_pt_ts / C.check_ts) + 1.0;
     }
-    const int fail_in = st.fail_count;
-    if (fail_in >= 4) {  // :640-648
-      int nseg = find_collision_seg(map, C, bv, st, S.hit, S.line, S.segA, lane, err);
-      const int np = path_search(map, C, bv, st, W, S.segA, nseg, err);
-      if (np >= 0 && lane == 0) assign_guides(map, C, bv, b, st, W, S.segA, nseg, np);
-      __syncwarp();
+    __syncthreads();
+    // ---- loop body: success / failure / re-guide / weight doubling
+    if (tid < 32) dev_plan_step(lbv, C, map, st, W, PS, b, lane);
+    __syncthreads();
+  }
+  // ---- linearFeasibilityReparam
+  if (st.status == TP_STATUS_SUCCESS) {
+    double* q = sm + SL.plan;
+    double* rr = q + 3 * (N - 1);
+    double* red = rr + 3 * (N - 2) + (N & 1);
+    const double f = dev_reparam(cp, q, rr, red, N, bv, C, tid);
+    if (tid == 0) st.linear_factor = f;
+  }
+  __syncthreads();
+  // ---- write back
+  for (int e = tid; e < 3 * N; e += TP_LB_THREADS) gctrl[e] = cp[e];
+  {
+    const int* src = reinterpret_cast<const int*>(&st);
+    int* dst = reinterpret_cast<int*>(&bv.st[b]);
+    for (int i = tid; i < (int)(sizeof(TrajState) / 4); i += TP_LB_THREADS) dst[i] = src[i];
+  }
+  if (tid == 0) {
+    if (counters) {
+      atomicAdd(&counters[0], fl);
+      atomicAdd(&counters[1], its);
+      atomicAdd(&counters[2], evs);
+      atomicAdd(&counters[3], smp);
     }
-    if (fail_in >= 8) {  // :650-654
-      if (lane == 0) {
-        st.round += 1;
-        st.w_dist = C.p.w_distance;
-        st.w_dyn = C.p.w_dyn;
-        st.status = TP_STATUS_FAIL_OPTIMIZE;
-        st.err |= err;
-      }
-      continue;
-    }
-    int add_fail = 0;
-    if (hasCol) {
-      // ---- isReguideRequired (:573-608)
-      const int nprev = st.nseg;
-      for (int i = lane; i < nprev; i += 32) { prevSeg[i][0] = st.seg[i][0]; prevSeg[i][1] = st.seg[i][1]; }
-      __syncwarp();
-      const int nnew = find_collision_seg(map, C, bv, st, S.hit, S.line, S.segA, lane, err);
-      int nre = 0;
-      if (lane == 0) {
-        st.nseg = nnew;
-        for (int i = 0; i < nnew; ++i) { st.seg[i][0] = S.segA[i][0]; st.seg[i][1] = S.segA[i][1]; }
-        // compareCollisionSeg (bsplineTraj.h:379-403) + set<int> of segment indices
-        unsigned long long need = 0ull;  // bit i: segment i needs a re-guide (max_seg <= 64)
-        for (int sidx = 0; sidx < nnew; ++sidx) {
-          const int s0 = S.segA[sidx][0], s1 = S.segA[sidx][1];
-          auto visit = [&](int i) {
-            const bool overl = index_in_seg(prevSeg, nprev, i);
-            if (!overl || cp_requires_new_guide(C, bv, b, st, i)) {
-              const int k = find_seg_index(S.segA, nnew, i);
-              if (k >= 0) need |= (1ull << k);
-            }
-          };
-          for (int i = s0 + 1; i <= s1 - 1; ++i) visit(i);
-          if (s1 - s0 - 1 == 0)
-            for (int i = s0; i <= s1; ++i) visit(i);
-        }
-        for (int k = 0; k < nnew; ++k)
-          if ((need >> k) & 1ull) {
-            S.segB[nre][0] = S.segA[k][0];
-            S.segB[nre][1] = S.segA[k][1];
-            ++nre;
-          }
-      }
-      nre = __shfl_sync(0xffffffffu, nre, 0);
-      __syncwarp();
-      if (nre > 0) {
-        int nre2 = nre;
-        const int np = path_search(map, C, bv, st, W, S.segB, nre2, err);
-        if (np >= 0) {
-          if (lane == 0) assign_guides(map, C, bv, b, st, W, S.segB, nre2, np);
-        } else
-          add_fail = 1;
-      } else
-        add_fail = 1;
-    }
-    if (lane == 0) {
-      st.round += 1;
-      if (add_fail) {
-        st.w_dist *= 2.0;
-        st.fail_count += 1;
-      }
-      if (hasDyn) st.w_dyn *= 2.0;
-      st.err |= err;
-      active_out[atomicAdd(n_active_out, 1)] = b;
-    }
-    __syncwarp();
+    __threadfence();
+    atomicExch(&slot_flags[s_slot], 0);
   }
 }
 
@@ -516,7 +701,11 @@ struct tp_engine {
   double tab_check_ts = -1, tab_ts = -1, tab_res = -1;
   // A* pools
   AStarPools pools;
-  DevBuf pool_nodes, pool_heaps, pool_heapn, pool_paths, pool_sc, pool_sclen, pool_rounds;
+  DevBuf pool_nodes, pool_heaps, pool_heapn, pool_paths, pool_sc, pool_sclen, pool_rounds, pool_flags;
+  cudaStream_t class_stream[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_stage = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool stage_busy = false;
+  bool solve_attr_set = false;
   int pools_key[8] = {0};
   // batch buffers
   DevBuf off, ctrl, st, pairs, cp_head, cp_tail, active[2], counters, results, dyn, scratch_a, scratch_b, scratch_c;
@@ -678,6 +867,8 @@ static int ensure_pools(tp_engine* e, const VigoConst& C) {
   if (e->pool_sc.ensure((size_t)workers * C.max_seg * TP_SC_CAP * 24) != TP_OK) return TP_ERR_CUDA;
   if (e->pool_sclen.ensure((size_t)workers * C.max_seg * 4) != TP_OK) return TP_ERR_CUDA;
   if (e->pool_rounds.ensure((size_t)workers * 4) != TP_OK) return TP_ERR_CUDA;
+  if (e->pool_flags.ensure((size_t)workers * 4) != TP_OK) return TP_ERR_CUDA;
+  CK(cudaMemsetAsync(e->pool_flags.p, 0, (size_t)workers * 4, e->stream));
   CK(cudaMemsetAsync(e->pool_nodes.p, 0, (size_t)workers * (pool_nodes + 1) * sizeof(ANode), e->stream));
   CK(cudaMemsetAsync(e->pool_rounds.p, 0, (size_t)workers * 4, e->stream));
   CK(cudaStreamSynchronize(e->stream));
@@ -830,14 +1021,32 @@ __global__ void k_resolve_unknown(BatchView bv, VigoConst C, DevMap map) {
   pr.unknown = dm_unknown(map, d3(pr.p[0], pr.p[1], pr.p[2])) ? 1 : 0;
 }
 
+// which fused cost+L-BFGS kernel runs: 1 strict (bit-faithful), 2 vector-free (default), 0 classic two-loop
+// with tree reductions (lbfgs_m != 16, or TP_LBFGS_CLASSIC=1 for A/B measurements)
+static int lbfgs_mode(const tp_vigo_params* p) {
+  if (p->strict_order) return 1;
+  static const bool classic = getenv("TP_LBFGS_CLASSIC") != nullptr;
+  return (p->lbfgs_m == VF_M && !classic) ? 2 : 0;
+}
+static size_t lbfgs_smem_bytes(const tp_vigo_params* p, int max_n) {
+  return lbfgs_mode(p) == 2 ? vf_smem_bytes(max_n) : lbfgs_smem_doubles(max_n, p->lbfgs_m) * 8;
+}
+template <class... A>
+static void launch_lbfgs(int mode, int grid, size_t smem, cudaStream_t s, A... args) {
+  if (mode == 1) k_lbfgs<1><<<grid, TP_LB_THREADS, smem, s>>>(args...);
+  else if (mode == 2) k_lbfgs<2><<<grid, TP_LB_THREADS, smem, s>>>(args...);
+  else k_lbfgs<0><<<grid, TP_LB_THREADS, smem, s>>>(args...);
+}
+
 static int set_lbfgs_smem(tp_engine* e, size_t bytes) {
   if ((int)bytes > e->max_smem_optin) {
     tp_set_error("L-BFGS state needs %zu B of shared memory (> %d B per block)", bytes, e->max_smem_optin);
     return TP_ERR_CAPACITY;
   }
   if (!e->lbfgs_attr_set) {
-    CK(cudaFuncSetAttribute(k_lbfgs<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
-    CK(cudaFuncSetAttribute(k_lbfgs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
+    CK(cudaFuncSetAttribute(k_lbfgs<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
+    CK(cudaFuncSetAttribute(k_lbfgs<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
+    CK(cudaFuncSetAttribute(k_lbfgs<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
     CK(cudaFuncSetAttribute(k_cost<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
     CK(cudaFuncSetAttribute(k_cost<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
     e->lbfgs_attr_set = true;
@@ -921,12 +1130,18 @@ void tp_engine_destroy(tp_engine_t* e) {
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
   DevBuf* bufs[] = {&e->map_infl, &e->map_known, &e->t_check, &e->t_reparam, &e->a_line, &e->pool_nodes, &e->pool_heaps, &e->pool_heapn,
-                    &e->pool_paths, &e->pool_sc, &e->pool_sclen, &e->pool_rounds, &e->off, &e->ctrl, &e->st, &e->pairs,
+                    &e->pool_paths, &e->pool_sc, &e->pool_sclen, &e->pool_rounds, &e->pool_flags, &e->off, &e->ctrl, &e->st, &e->pairs,
                     &e->cp_head, &e->cp_tail, &e->active[0], &e->active[1], &e->counters, &e->results, &e->dyn,
                     &e->scratch_a, &e->scratch_b, &e->scratch_c};
   for (DevBuf* b : bufs) b->release();
   if (e->h_counters) cudaFreeHost(e->h_counters);
   if (e->h_stage) cudaFreeHost(e->h_stage);
+  for (int i = 0; i < 4; ++i) {
+    if (e->class_stream[i]) cudaStreamDestroy(e->class_stream[i]);
+    if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
+  }
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_stage) cudaEventDestroy(e->ev_stage);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -1032,7 +1247,7 @@ int tp_vigo_cost_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, const
   k_resolve_unknown<<<(int)(((long)B * bs.C.gcap + 255) / 256), 256, 0, s>>>(bs.bv, bs.C, e->dmap);
   const size_t nvar = (size_t)std::max<long>(3 * (bs.total - 6L * B), 1);
   if (e->scratch_a.ensure((size_t)B * 8) != TP_OK || e->scratch_b.ensure(nvar * 8) != TP_OK) return TP_ERR_CUDA;
-  const size_t smem = ((size_t)3 * bs.max_n + 3 * (size_t)bs.max_n + 40) * 8;
+  const size_t smem = p->strict_order ? ((size_t)3 * bs.max_n + 3 * (size_t)bs.max_n + 40) * 8 : vf_smem_bytes(bs.max_n);
   rc = set_lbfgs_smem(e, smem);
   if (rc != TP_OK) return rc;
   if (p->strict_order) k_cost<true><<<B, TP_LB_THREADS, smem, s>>>(bs.bv, bs.C, e->scratch_a.as<double>(), e->scratch_b.as<double>());
@@ -1062,17 +1277,13 @@ int tp_vigo_optimize_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, c
   const size_t nvar = (size_t)std::max<long>(3 * (bs.total - 6L * B), 1);
   if (e->results.ensure((size_t)B * sizeof(tp_lbfgs_result)) != TP_OK || e->scratch_b.ensure(nvar * 8) != TP_OK) return TP_ERR_CUDA;
   CK(cudaMemsetAsync(e->results.p, 0, (size_t)B * sizeof(tp_lbfgs_result), s));
-  const size_t smem = lbfgs_smem_doubles(bs.max_n, p->lbfgs_m) * 8;
+  const size_t smem = lbfgs_smem_bytes(p, bs.max_n);
   rc = set_lbfgs_smem(e, smem);
   if (rc != TP_OK) return rc;
   rc = make_identity_active(e, B, s);
   if (rc != TP_OK) return rc;
-  if (p->strict_order)
-    k_lbfgs<true><<<B, TP_LB_THREADS, smem, s>>>(bs.bv, bs.C, e->active[0].as<int>(), e->counters.as<int>(),
-                                                  e->results.as<tp_lbfgs_result>(), x_final ? e->scratch_b.as<double>() : nullptr, nullptr);
-  else
-    k_lbfgs<false><<<B, TP_LB_THREADS, smem, s>>>(bs.bv, bs.C, e->active[0].as<int>(), e->counters.as<int>(),
-                                                   e->results.as<tp_lbfgs_result>(), x_final ? e->scratch_b.as<double>() : nullptr, nullptr);
+  launch_lbfgs(lbfgs_mode(p), B, smem, s, bs.bv, bs.C, (const int*)e->active[0].as<int>(), (const int*)e->counters.as<int>(),
+               e->results.as<tp_lbfgs_result>(), x_final ? e->scratch_b.as<double>() : (double*)nullptr, (double*)nullptr);
   e->launches += 2;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(ctrl, bs.bv.ctrl, (size_t)bs.total * 24, cudaMemcpyDeviceToHost, s));
@@ -1250,62 +1461,73 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
     bs.bv.dyn_vel = d + 3 * (size_t)n_dyn;
     bs.bv.dyn_size = d + 6 * (size_t)n_dyn;
   }
-  const size_t smem_lb = lbfgs_smem_doubles(bs.max_n, p->lbfgs_m) * 8;
-  rc = set_lbfgs_smem(e, smem_lb);
+  rc = ensure_pools(e, bs.C);
   if (rc != TP_OK) return rc;
-  const size_t smem_cp = (size_t)3 * bs.max_n * 8;
-  const size_t smem_rp = (size_t)9 * bs.max_n * 8;
-  // ---- steps 1-3: collision segments, A*, guide points  -> active list 0, count in counters[0]
-  rc = run_plan_init(e, bs, s);
-  if (rc != TP_OK) return rc;
-  int* cnt = e->counters.as<int>();
-  // counters layout: [0] n_active(list0) [1] init queue; per round r: [2+4r..] = n_active_next, queue
-  int cur = 0;
-  int* n_cur = cnt + 0;
-  const int max_rounds = p->max_outer_rounds + 2;
-  CK(cudaMemcpyAsync(e->h_counters, n_cur, 4, cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
-  int n_active = e->h_counters[0];
-  for (int r = 0; r < max_rounds && n_active > 0; ++r) {
-    // optimize()
-    {
-      ProfScope ps(e, 0, s, n_active);
-      if (p->strict_order)
-        k_lbfgs<true><<<n_active, TP_LB_THREADS, smem_lb, s>>>(bs.bv, bs.C, e->active[cur].as<int>(), n_cur, nullptr, nullptr, e->counters_ptr());
-      else
-        k_lbfgs<false><<<n_active, TP_LB_THREADS, smem_lb, s>>>(bs.bv, bs.C, e->active[cur].as<int>(), n_cur, nullptr, nullptr, e->counters_ptr());
+  const int mode = lbfgs_mode(p);
+  if (!e->solve_attr_set) {
+    CK(cudaFuncSetAttribute(k_solve<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
+    CK(cudaFuncSetAttribute(k_solve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
+    CK(cudaFuncSetAttribute(k_solve<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
+    CK(cudaFuncSetAttribute(k_solve<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK(cudaFuncSetAttribute(k_solve<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK(cudaFuncSetAttribute(k_solve<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    for (int i = 0; i < 4; ++i) {
+      CK(cudaStreamCreateWithFlags(&e->class_stream[i], cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming));
     }
-    // hasCollisionTrajectory
-    {
-      ProfScope ps(e, 1, s, n_active);
-      k_has_collision<<<n_active, TP_LB_THREADS, smem_cp, s>>>(bs.bv, bs.C, e->dmap, e->active[cur].as<int>(), n_cur, nullptr, e->counters_ptr());
+    CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->ev_stage, cudaEventDisableTiming));
+    e->solve_attr_set = true;
+  }
+  // ---- issue order: longest trajectory first; size classes so that shared memory per block (hence
+  // resident blocks per SM) follows the trajectory length.  One launch per non-empty class, on
+  // sibling streams so that a class's tail overlaps the next class's start.
+  std::vector<int> order((size_t)B);
+  for (int b = 0; b < B; ++b) order[b] = b;
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+    return (bs.h_off[x + 1] - bs.h_off[x]) > (bs.h_off[y + 1] - bs.h_off[y]);
+  });
+  if (e->stage_busy) CK(cudaEventSynchronize(e->ev_stage));   // the previous call's copy out of the staging buffer
+  if (ensure_stage(e, (size_t)B * 4) != TP_OK) return TP_ERR_CUDA;
+  memcpy(e->h_stage, order.data(), (size_t)B * 4);
+  CK(cudaMemcpyAsync(e->active[0].p, e->h_stage, (size_t)B * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaEventRecord(e->ev_stage, s));
+  e->stage_busy = true;
+  CK(cudaEventRecord(e->ev_fork, s));
+  static const int class_lim[4] = {TP_MAX_CTRL, 104, 64, 40};   // upper N bound of each class, largest first
+  int pos = 0, used = 0;
+  for (int c = 0; c < 4 && pos < B; ++c) {
+    const int lo = c + 1 < 4 ? class_lim[c + 1] : 0;   // class c holds lo < N <= class_lim[c]
+    int end_ = pos;
+    while (end_ < B && (bs.h_off[order[end_] + 1] - bs.h_off[order[end_]]) > lo) ++end_;
+    const int cnt_c = end_ - pos;
+    if (cnt_c == 0) continue;
+    const int nmax = bs.h_off[order[pos] + 1] - bs.h_off[order[pos]];
+    const size_t smem = (size_t)solve_layout(nmax, mode, p->lbfgs_m).total * 8;
+    if ((int)smem > e->max_smem_optin) {
+      tp_set_error("a %d-control-point trajectory needs %zu B of shared memory (> %d B per block)", nmax, smem, e->max_smem_optin);
+      return TP_ERR_CAPACITY;
     }
-    // loop body: success / failure / re-guide / weight doubling
-    int* slot = cnt + 2 + 2 * (r % 24);
-    CK(cudaMemsetAsync(slot, 0, 8, s));
+    cudaStream_t cs = e->class_stream[used];
+    CK(cudaStreamWaitEvent(cs, e->ev_fork, 0));
     {
-      ProfScope ps(e, 2, s, n_active);
-      k_plan_step<<<std::min(e->pools.workers, n_active), 32, 0, s>>>(bs.bv, bs.C, e->dmap, e->pools, slot + 1,
-                                                                      e->active[cur].as<int>(), n_cur,
-                                                                      e->active[cur ^ 1].as<int>(), slot);
+      ProfScope ps(e, 0, cs, cnt_c);
+      const int* ord = e->active[0].as<int>() + pos;
+      if (mode == 1) k_solve<1><<<cnt_c, TP_LB_THREADS, smem, cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, nmax, e->pool_flags.as<int>(), e->counters_ptr());
+      else if (mode == 2) k_solve<2><<<cnt_c, TP_LB_THREADS, smem, cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, nmax, e->pool_flags.as<int>(), e->counters_ptr());
+      else k_solve<0><<<cnt_c, TP_LB_THREADS, smem, cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, nmax, e->pool_flags.as<int>(), e->counters_ptr());
     }
-    e->launches += 3;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(e->h_counters, slot, 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    n_active = e->h_counters[0];
-    n_cur = slot;
-    cur ^= 1;
+    CK(cudaEventRecord(e->ev_join[used], cs));
+    e->launches += 1;
+    ++used;
+    pos = end_;
   }
-  // ---- steps 5-6: time re-parameterisation of the successful trajectories
-  {
-    ProfScope ps(e, 4, s);
-    k_reparam<<<B, TP_LB_THREADS, smem_rp, s>>>(bs.bv, bs.C);
-  }
+  for (int i = 0; i < used; ++i) CK(cudaStreamWaitEvent(s, e->ev_join[i], 0));
   if (e->results.ensure((size_t)B * sizeof(tp_vigo_result)) != TP_OK) return TP_ERR_CUDA;
   tp_vigo_result* dres = mem == TP_MEM_DEVICE ? results : e->results.as<tp_vigo_result>();
   k_collect_results<<<(B + 127) / 128, 128, 0, s>>>(bs.bv, dres);
-  e->launches += 2;
+  e->launches += 1;
   CK(cudaGetLastError());
   if (mem == TP_MEM_HOST) {
     CK(cudaMemcpyAsync(ctrl_out, bs.bv.ctrl, (size_t)bs.total * 24, cudaMemcpyDeviceToHost, s));
