@@ -1,0 +1,7 @@
+import os, sys, numpy as np
+sys.path.insert(0,'/root/repo')
+import trajectory_planner_b200 as tp, bench
+pmap = tp.OccMap.from_tpm(bench.MAP_TPM); eng = tp.Engine(0); eng.set_map(pmap); p = tp.default_params()
+off, ctrl = bench.make_workload(tp, pmap, eng.query_points, 4096, bench.SEED, p)
+out, res = eng.make_plan_batch(p, off, ctrl)
+print('ok', (res['status']==1).mean())

@@ -56,7 +56,7 @@ class Profile(C.Structure):
                 ("query_points", C.c_double)]
 
 
-PROF_KINDS = ["lbfgs", "collision_check", "plan_step", "plan_init", "reparam", "map_query"]
+PROF_KINDS = ["solve", "collision_check", "plan_step", "plan_init", "reparam", "map_query"]
 
 RESULT_DTYPE = np.dtype([
     ("status", "i4"), ("outer_rounds", "i4"), ("fail_count", "i4"), ("lbfgs_runs", "i4"), ("lbfgs_iters", "i4"),

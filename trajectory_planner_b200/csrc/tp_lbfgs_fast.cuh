@@ -73,6 +73,7 @@ struct VfCtx {
   const GuidePair* pairs;   // global list of this trajectory
   const int* head;          // global per-control-point list heads
   int n_pairs;
+  int serial_warp;     // which warp runs the serial coefficient phase (rotated per block: warp w lives on SM sub-partition w)
   bool pairs_in_sm;
   double w_dist, w_dyn;
   int n_dyn;
@@ -572,7 +573,7 @@ __device__ void lbfgs_run_fast(const VigoConst& C, VfCtx& V, tp_lbfgs_result& ou
       bsum += bound;
       __syncthreads();
       LT(tG)
-      if (tid < 32) vf_coeffs(V, sm + V.L.gram + (size_t)gbuf * VF_GRAM, end, bound, gg, tid);
+      if ((tid >> 5) == V.serial_warp) vf_coeffs(V, sm + V.L.gram + (size_t)gbuf * VF_GRAM, end, bound, gg, tid & 31);
       __syncthreads();
       LT(tC)
       const double cg = sc[0];

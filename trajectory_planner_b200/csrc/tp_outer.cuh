@@ -35,6 +35,8 @@ struct Worker {
   int* sc_len;         // max_seg
   uint32_t* round_ptr;
   int lane;
+  int flood_trigger;      // expansions after which astar_search checks reachability (adaptive per trajectory)
+  int goal_unreachable;   // set by astar_search when the flood fill proved the goal unreachable
 };
 
 struct AStarFrame {  // per-search constants (uniform across the warp)
@@ -194,7 +196,9 @@ struct Heap {
 // it.  The component is flooded with a lane-per-cell worklist over two bitmaps that temporarily
 // take over the heap's shared memory (the heap is parked in the tail of its HBM spill area).
 // Returns -1 when the goal is reachable (the search resumes), else the component size.
-#define TP_FLOOD_TRIGGER 1536
+#define TP_FLOOD_TRIGGER 4096       // expansions after which a search checks reachability
+#define TP_FLOOD_TRIGGER_AGAIN 192  // ... once this trajectory has already had an unreachable goal
+#define TP_FLOOD_CAND (32 * 26)
 __device__ int flood_component(const DevMap& map, const VigoConst& C, Worker& W, int heap_size, int si, int sj, int sk,
                                int ei, int ej, int ek, int k_lo) {
   AStarSmem& S = *W.sm;
@@ -202,80 +206,91 @@ __device__ int flood_component(const DevMap& map, const VigoConst& C, Worker& W,
   const int PX = C.pool[0], PY = C.pool[1], PZ = C.pool[2], KL = C.pool_kl;
   const int ncell = PX * PY * KL;
   const int nw = (ncell + 31) >> 5;
-  // shared-memory plan (the heap's 24 KB): V bitmap [nw] | head, tail | worklist ring Q[qcap]
+  // shared-memory plan (the heap's 24 KB): V bitmap [nw] | head, tail, ncand, pad | candidates | worklist ring Q[qcap]
   uint32_t* V = reinterpret_cast<uint32_t*>(S.hk);   // seen: visited-free or known-blocked
-  volatile uint32_t* ctr = V + nw;                    // [0] head, [1] tail (monotonic)
-  uint32_t* Q = V + nw + 2;
-  const int qcap = (int)((sizeof(S.hk) + sizeof(S.hn)) / 4) - nw - 2;
-  if (qcap < 32 * 26 + 64 || C.heap_cap < 3 * TP_HEAP_SMEM) return -1;
+  volatile uint32_t* ctr = V + nw;                    // [0] head, [1] tail (monotonic), [2] candidates of this round
+  uint32_t* cand = V + nw + 4;                        // packed (i << 16 | j << 8 | kk) neighbours to look up
+  uint32_t* Q = cand + TP_FLOOD_CAND;                 // packed cells waiting to be expanded
+  const int qcap = (int)((sizeof(S.hk) + sizeof(S.hn)) / 4) - nw - 4 - TP_FLOOD_CAND;
+  if (qcap < 2 * TP_FLOOD_CAND || C.heap_cap < 3 * TP_HEAP_SMEM) return -1;
   // park the heap
   const int keep = heap_size < TP_HEAP_SMEM ? heap_size : TP_HEAP_SMEM;
   double* pk = W.heap_k_gl + (C.heap_cap - TP_HEAP_SMEM);
   uint32_t* pn = W.heap_n_gl + (C.heap_cap - TP_HEAP_SMEM);
   for (int i = lane; i < keep; i += 32) { pk[i] = S.hk[i]; pn[i] = S.hn[i]; }
   __syncwarp();
-  for (int i = lane; i < nw + 2; i += 32) V[i] = 0u;
+  for (int i = lane; i < nw + 4; i += 32) V[i] = 0u;
   __syncwarp();
   const int klo_c = k_lo > 1 ? k_lo : 1;                                  // neighbour layers that can be entered
   const int khi_c = (k_lo + KL - 1) < (PZ - 2) ? (k_lo + KL - 1) : (PZ - 2);
-  // expand one cell: mark its unseen neighbours, enqueue the free ones.  The three vertical neighbours of
-  // a column are three consecutive bits of V and (almost always) one word of the z-fastest map.
-  auto expand = [&](int ci, int cj, int ck) {
-    for (int dx = -1; dx <= 1; ++dx) {
-      const int ni = ci + dx;
-      if (ni < 1 || ni >= PX - 1) continue;
-      for (int dy = -1; dy <= 1; ++dy) {
-        const int nj = cj + dy;
-        if (nj < 1 || nj >= PY - 1) continue;
-        const int ix = S.tx[ni], iy = S.ty[nj];
-        const size_t col = ((size_t)(ix < 0 ? 0 : ix) * map.dim[1] + (iy < 0 ? 0 : iy)) * map.wz;
-        int cached_w = -1;
-        uint32_t mw = 0u;
-        for (int dz = -1; dz <= 1; ++dz) {
-          const int nk = ck + dz;
-          if (nk < klo_c || nk > khi_c || !S.band[nk]) continue;
-          if (dx == 0 && dy == 0 && dz == 0) continue;
-          if (ni == si && nj == sj && nk == sk) continue;
-          const int b = (ni * PY + nj) * KL + (nk - k_lo);
-          const uint32_t bit = 1u << (b & 31);
-          if (V[b >> 5] & bit) continue;
-          bool blocked = true;
-          const int iz = S.tz[nk];
-          if (ix >= 0 && iy >= 0 && iz >= 0) {
-            if ((iz >> 5) != cached_w) {
-              cached_w = iz >> 5;
-              mw = __ldg(&map.inflated[col + cached_w]);
-            }
-            blocked = (mw >> (iz & 31)) & 1u;
-          }
-          const uint32_t old = atomicOr(&V[b >> 5], bit);
-          if (!(old & bit) && !blocked) {
-            const uint32_t pos = atomicAdd((uint32_t*)&ctr[1], 1u);
-            Q[pos % (uint32_t)qcap] = (uint32_t)b;
+  // One round = up to 32 cells.  Phase 1 (lane per cell): bit tests only, unseen enterable neighbours go to the
+  // shared candidate list.  Phase 2 (lane per candidate, balanced across the warp): one map gather + one atomicOr
+  // each; first-time free cells join the worklist.
+  auto round = [&](int ci, int cj, int ck, bool valid) {
+    if (valid) {
+      uint32_t mine[26];
+      int nm = 0;
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int ni = ci + dx;
+        if (ni < 1 || ni >= PX - 1) continue;
+        for (int dy = -1; dy <= 1; ++dy) {
+          const int nj = cj + dy;
+          if (nj < 1 || nj >= PY - 1) continue;
+          const int b0 = (ni * PY + nj) * KL - k_lo;
+          for (int dz = -1; dz <= 1; ++dz) {
+            const int nk = ck + dz;
+            if (nk < klo_c || nk > khi_c || !S.band[nk]) continue;
+            if (dx == 0 && dy == 0 && dz == 0) continue;
+            if (ni == si && nj == sj && nk == sk) continue;
+            const int b = b0 + nk;
+            if ((V[b >> 5] >> (b & 31)) & 1u) continue;
+            mine[nm++] = ((uint32_t)ni << 16) | ((uint32_t)nj << 8) | (uint32_t)(nk - k_lo);
           }
         }
       }
+      if (nm) {
+        const uint32_t base = atomicAdd((uint32_t*)&ctr[2], (uint32_t)nm);
+        for (int q = 0; q < nm; ++q) cand[base + q] = mine[q];
+      }
     }
+    __syncwarp();
+    const int nc = (int)ctr[2];
+    for (int t = lane; t < nc; t += 32) {
+      const uint32_t id = cand[t];
+      const int ni = (int)(id >> 16), nj = (int)((id >> 8) & 255u), kk = (int)(id & 255u);
+      const int b = (ni * PY + nj) * KL + kk;
+      const uint32_t bit = 1u << (b & 31);
+      bool blocked = true;
+      const int ix = S.tx[ni], iy = S.ty[nj], iz = S.tz[kk + k_lo];
+      if (ix >= 0 && iy >= 0 && iz >= 0) {
+        const uint32_t w = __ldg(&map.inflated[((size_t)ix * map.dim[1] + iy) * map.wz + (iz >> 5)]);
+        blocked = (w >> (iz & 31)) & 1u;
+      }
+      const uint32_t old = atomicOr(&V[b >> 5], bit);
+      if (!(old & bit) && !blocked) {
+        const uint32_t pos = atomicAdd((uint32_t*)&ctr[1], 1u);
+        Q[pos % (uint32_t)qcap] = id;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) ctr[2] = 0u;
+    __syncwarp();
   };
-  if (lane == 0) expand(si, sj, sk);
-  __syncwarp();
+  round(si, sj, sk, lane == 0);
   bool bail = false;
   for (;;) {
     const uint32_t h = ctr[0], t = ctr[1];
     __syncwarp();
     int n = (int)(t - h);
     if (n == 0) break;
-    if (n > qcap - 32 * 26) { bail = true; break; }   // the ring could overflow during this round
+    if (n > qcap - TP_FLOOD_CAND) { bail = true; break; }   // the ring could overflow during this round
     if (n > 32) n = 32;
     uint32_t cell = 0xFFFFFFFFu;
     if (lane < n) cell = Q[(h + (uint32_t)lane) % (uint32_t)qcap];
     if (lane == 0) ctr[0] = h + (uint32_t)n;
     __syncwarp();
-    if (cell != 0xFFFFFFFFu) {
-      const int kk = (int)(cell % (uint32_t)KL), r = (int)(cell / (uint32_t)KL);
-      expand(r / PY, r % PY, kk + k_lo);
-    }
-    __syncwarp();
+    const bool valid = cell != 0xFFFFFFFFu;
+    round((int)(cell >> 16), (int)((cell >> 8) & 255u), (int)(cell & 255u) + k_lo, valid);
   }
   const int count = (int)ctr[1] + 1;  // every free cell was enqueued exactly once, plus the start cell
   // is the goal in the component?
@@ -522,10 +537,18 @@ __device__ int astar_search(const DevMap& map, const VigoConst& C, Worker& W, co
       break;
     }
     if (C.p.astar_max_expansions > 0 && num_iter >= C.p.astar_max_expansions) break;
-    if (num_iter == TP_FLOOD_TRIGGER) {
+    if (num_iter == W.flood_trigger) {
       const int hs = __shfl_sync(0xffffffffu, H.size, 0);
+#ifdef TP_ASTAR_TIMING
+      const long long tf0 = clock64();
+#endif
       const int comp = flood_component(map, C, W, hs, si, sj, sk, ei, ej, ek, k_lo);
+#ifdef TP_ASTAR_TIMING
+      if (lane == 0) printf("[flood] result %d cycles %lld\n", comp, clock64() - tf0);
+      t0 = clock64();
+#endif
       if (comp >= 0) {  // goal unreachable: the search would pop the whole component and fail
+        W.goal_unreachable = 1;
         num_iter = (C.p.astar_max_expansions > 0 && comp > C.p.astar_max_expansions) ? C.p.astar_max_expansions : comp;
         break;
       }
@@ -533,7 +556,7 @@ __device__ int astar_search(const DevMap& map, const VigoConst& C, Worker& W, co
   }
   expansions = num_iter;
 #ifdef TP_ASTAR_TIMING
-  if (lane == 0 && num_iter > 200)
+  if (lane == 0)
     printf("[astar] exp %d heap %d cycles/exp: pop %.0f classify %.0f push %.0f\n", num_iter, H.size, (double)tA / num_iter,
            (double)tB / num_iter, (double)tC / num_iter);
 #endif
@@ -794,6 +817,7 @@ __device__ int path_search(const DevMap& map, const VigoConst& C, const BatchVie
     const D3 ps = ld3(ctrl, a), pe = ld3(ctrl, b2);
     int ex = 0;
     int len = astar_search(map, C, W, ps, pe, ex, err);
+    if (W.goal_unreachable) W.flood_trigger = TP_FLOOD_TRIGGER_AGAIN;   // this trajectory's next searches check early
     if (lane == 0) {
       st.astar_searches += 1;
       st.astar_expansions += ex;

@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(TP_LB_THREADS) k_cost(BatchView bv, VigoConst 
     VfCtx V;
     V.N = N; V.n = n; V.sm = sm; V.L = vf_layout(N);
     V.pairs = bv.pairs + (size_t)b * C.gcap; V.head = bv.cp_head + st.off; V.n_pairs = st.n_pairs; V.pairs_in_sm = false;
+    V.serial_warp = 0;
     V.w_dist = st.w_dist; V.w_dyn = st.w_dyn;
     V.n_dyn = bv.n_dyn; V.dyn_pos = bv.dyn_pos; V.dyn_vel = bv.dyn_vel; V.dyn_size = bv.dyn_size;
     for (int e = tid; e < 3 * N; e += TP_LB_THREADS) sm[V.L.cp + e] = bv.ctrl[3 * (size_t)st.off + e];
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(TP_LB_THREADS, 4) k_lbfgs(BatchView bv, VigoCo
     if (MODE == 2) {
       VfCtx V;
       V.N = N; V.n = n; V.sm = sm; V.L = vf_layout(N);
-      V.pairs = E.pairs; V.head = E.head; V.n_pairs = st.n_pairs; V.pairs_in_sm = false;
+      V.pairs = E.pairs; V.head = E.head; V.n_pairs = st.n_pairs; V.pairs_in_sm = false; V.serial_warp = 0;
       V.w_dist = E.w_dist; V.w_dyn = E.w_dyn;
       V.n_dyn = E.n_dyn; V.dyn_pos = E.dyn_pos; V.dyn_vel = E.dyn_vel; V.dyn_size = E.dyn_size;
       lbfgs_run_fast(C, V, r, xf, tid);
@@ -304,6 +305,8 @@ __device__ __forceinline__ Worker make_worker(const VigoConst& C, const AStarPoo
   W.sc_len = P.sc_len + (size_t)w * C.max_seg;
   W.round_ptr = P.rounds + w;
   W.lane = lane;
+  W.flood_trigger = TP_FLOOD_TRIGGER;
+  W.goal_unreachable = 0;
   return W;
 }
 
@@ -485,10 +488,12 @@ __host__ __device__ inline SolveLayout solve_layout(int N, int mode, int m) {
 template <int MODE>
 __global__ void __launch_bounds__(TP_LB_THREADS, 4) k_solve(BatchView bv, VigoConst C, DevMap map, AStarPools P,
                                                             const int* __restrict__ order, int class_max_n,
-                                                            int* slot_flags, double* counters) {
+                                                            int* slot_flags, double* counters, long long* timeline) {
   extern __shared__ double sm[];
   const int tid = threadIdx.x, lane = tid & 31;
   const int b = order[blockIdx.x];
+  long long t_start = 0;
+  if (timeline && tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start));
   const SolveLayout SL = solve_layout(class_max_n, MODE, C.p.lbfgs_m);
   TrajState& st = *reinterpret_cast<TrajState*>(sm + SL.st);
   double* cp = sm + SL.vf;
@@ -503,20 +508,27 @@ __global__ void __launch_bounds__(TP_LB_THREADS, 4) k_solve(BatchView bv, VigoCo
   const int N = st.N, n = 3 * (N - 2 * TP_DEGREE);
   double* gctrl = bv.ctrl + 3 * (size_t)st.off;
   for (int e = tid; e < 3 * N; e += TP_LB_THREADS) cp[e] = gctrl[e];
-  // ---- claim an A* node pool (one per resident block)
+  // ---- claim an A* node pool (one per resident block) and a serial-warp role.  Warp w of every block lives on
+  // SM sub-partition w, so the blocks sharing an SM take DIFFERENT warps for their serial phases (A*, guide
+  // points, the coefficient solve): a per-SM ticket rotates the role.
   if (tid == 0) {
     const int W_ = P.workers;
     int sidx = (int)(((unsigned)blockIdx.x * 2654435761u) % (unsigned)W_);
     while (atomicCAS(&slot_flags[sidx], 0, 1) != 0) sidx = sidx + 1 == W_ ? 0 : sidx + 1;
-    st.pad = sidx;
+    unsigned smid;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    const int ticket = atomicAdd(&slot_flags[W_ + (int)(smid & 255u)], 1);
+    st.pad = sidx | ((ticket & (TP_LB_WARPS - 1)) << 24);
   }
   __syncthreads();
-  const int s_slot = st.pad;
+  const int s_slot = st.pad & 0xFFFFFF;
+  const int sw = (st.pad >> 24) & (TP_LB_WARPS - 1);
+  const bool is_serial_warp = (tid >> 5) == sw;
   BatchView lbv = bv;                      // the outer-loop code reads control points through bv.ctrl + 3*off
   lbv.ctrl = cp - 3 * (size_t)st.off;
   Worker W = make_worker(C, P, s_slot, lane, &PS.as);
   // ---- makePlan steps 1-3
-  if (tid < 32) dev_plan_init(lbv, C, map, st, W, PS, b, lane);
+  if (is_serial_warp) dev_plan_init(lbv, C, map, st, W, PS, b, lane);
   __syncthreads();
   double fl = 0.0, its = 0.0, evs = 0.0, smp = 0.0;
   while (st.status == TS_ACTIVE) {
@@ -528,6 +540,7 @@ __global__ void __launch_bounds__(TP_LB_THREADS, 4) k_solve(BatchView bv, VigoCo
       VfCtx V;
       V.N = N; V.n = n; V.sm = cp; V.L = vf_layout(N);
       V.pairs = bv.pairs + (size_t)b * C.gcap; V.head = bv.cp_head + st.off; V.n_pairs = st.n_pairs; V.pairs_in_sm = false;
+      V.serial_warp = sw;
       V.w_dist = st.w_dist; V.w_dyn = st.w_dyn;
       V.n_dyn = bv.n_dyn; V.dyn_pos = bv.dyn_pos; V.dyn_vel = bv.dyn_vel; V.dyn_size = bv.dyn_size;
       lbfgs_run_fast(C, V, r, nullptr, tid);
@@ -563,7 +576,7 @@ __global__ void __launch_bounds__(TP_LB_THREADS, 4) k_solve(BatchView bv, VigoCo
     }
     __syncthreads();
     // ---- loop body: success / failure / re-guide / weight doubling
-    if (tid < 32) dev_plan_step(lbv, C, map, st, W, PS, b, lane);
+    if (is_serial_warp) dev_plan_step(lbv, C, map, st, W, PS, b, lane);
     __syncthreads();
   }
   // ---- linearFeasibilityReparam
@@ -591,6 +604,16 @@ __global__ void __launch_bounds__(TP_LB_THREADS, 4) k_solve(BatchView bv, VigoCo
     }
     __threadfence();
     atomicExch(&slot_flags[s_slot], 0);
+    if (timeline) {   // development aid (TP_TIMELINE): start / end time [ns], SM id, iterations of every block
+      long long t_end;
+      unsigned smid;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_end));
+      asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+      timeline[4 * (size_t)b] = t_start;
+      timeline[4 * (size_t)b + 1] = t_end;
+      timeline[4 * (size_t)b + 2] = (long long)smid;
+      timeline[4 * (size_t)b + 3] = (long long)st.lbfgs_iters | ((long long)st.astar_expansions << 32);
+    }
   }
 }
 
@@ -867,8 +890,8 @@ static int ensure_pools(tp_engine* e, const VigoConst& C) {
   if (e->pool_sc.ensure((size_t)workers * C.max_seg * TP_SC_CAP * 24) != TP_OK) return TP_ERR_CUDA;
   if (e->pool_sclen.ensure((size_t)workers * C.max_seg * 4) != TP_OK) return TP_ERR_CUDA;
   if (e->pool_rounds.ensure((size_t)workers * 4) != TP_OK) return TP_ERR_CUDA;
-  if (e->pool_flags.ensure((size_t)workers * 4) != TP_OK) return TP_ERR_CUDA;
-  CK(cudaMemsetAsync(e->pool_flags.p, 0, (size_t)workers * 4, e->stream));
+  if (e->pool_flags.ensure(((size_t)workers + 256) * 4) != TP_OK) return TP_ERR_CUDA;   // pool slots + per-SM tickets
+  CK(cudaMemsetAsync(e->pool_flags.p, 0, ((size_t)workers + 256) * 4, e->stream));
   CK(cudaMemsetAsync(e->pool_nodes.p, 0, (size_t)workers * (pool_nodes + 1) * sizeof(ANode), e->stream));
   CK(cudaMemsetAsync(e->pool_rounds.p, 0, (size_t)workers * 4, e->stream));
   CK(cudaStreamSynchronize(e->stream));
@@ -1494,6 +1517,12 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
   CK(cudaEventRecord(e->ev_stage, s));
   e->stage_busy = true;
   CK(cudaEventRecord(e->ev_fork, s));
+  long long* tl = nullptr;
+  const char* tl_path = getenv("TP_TIMELINE");
+  if (tl_path) {
+    if (e->scratch_a.ensure((size_t)B * 32) != TP_OK) return TP_ERR_CUDA;
+    tl = e->scratch_a.as<long long>();
+  }
   static const int class_lim[4] = {TP_MAX_CTRL, 104, 64, 40};   // upper N bound of each class, largest first
   int pos = 0, used = 0;
   for (int c = 0; c < 4 && pos < B; ++c) {
@@ -1513,9 +1542,9 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
     {
       ProfScope ps(e, 0, cs, cnt_c);
       const int* ord = e->active[0].as<int>() + pos;
-      if (mode == 1) k_solve<1><<<cnt_c, TP_LB_THREADS, smem, cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, nmax, e->pool_flags.as<int>(), e->counters_ptr());
-      else if (mode == 2) k_solve<2><<<cnt_c, TP_LB_THREADS, smem, cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, nmax, e->pool_flags.as<int>(), e->counters_ptr());
-      else k_solve<0><<<cnt_c, TP_LB_THREADS, smem, cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, nmax, e->pool_flags.as<int>(), e->counters_ptr());
+      if (mode == 1) k_solve<1><<<cnt_c, TP_LB_THREADS, smem, cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, nmax, e->pool_flags.as<int>(), e->counters_ptr(), tl);
+      else if (mode == 2) k_solve<2><<<cnt_c, TP_LB_THREADS, smem, cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, nmax, e->pool_flags.as<int>(), e->counters_ptr(), tl);
+      else k_solve<0><<<cnt_c, TP_LB_THREADS, smem, cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, nmax, e->pool_flags.as<int>(), e->counters_ptr(), tl);
     }
     CK(cudaGetLastError());
     CK(cudaEventRecord(e->ev_join[used], cs));
@@ -1524,6 +1553,15 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
     pos = end_;
   }
   for (int i = 0; i < used; ++i) CK(cudaStreamWaitEvent(s, e->ev_join[i], 0));
+  if (tl) {
+    std::vector<long long> h((size_t)B * 4);
+    CK(cudaMemcpyAsync(h.data(), tl, (size_t)B * 32, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (FILE* f = fopen(tl_path, "wb")) {
+      fwrite(h.data(), 8, h.size(), f);
+      fclose(f);
+    }
+  }
   if (e->results.ensure((size_t)B * sizeof(tp_vigo_result)) != TP_OK) return TP_ERR_CUDA;
   tp_vigo_result* dres = mem == TP_MEM_DEVICE ? results : e->results.as<tp_vigo_result>();
   k_collect_results<<<(B + 127) / 128, 128, 0, s>>>(bs.bv, dres);
