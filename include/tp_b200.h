@@ -167,8 +167,9 @@ void tp_vigo_default_params(tp_vigo_params* p);
 
 /* ------------------------------------------------------------------------------------ measurement
  * Per-kernel device timing with CUDA events on the launching stream (bench.py's roofline legs).
- * Kinds: 0 fused cost+L-BFGS (optimize), 1 trajectory collision check, 2 outer-loop step
- * (segments / A* / guide points), 3 initial segments+A*+guides, 4 re-parameterisation, 5 map queries. */
+ * Kinds: 0 the per-trajectory solve kernel of tp_vigo_make_plan_batch (one entry per size-class launch; the
+ * launches of one call overlap), 1 trajectory collision check, 2 (unused), 3 initial segments+A*+guides
+ * (tp_vigo_init_guides_batch), 4 re-parameterisation, 5 map queries. */
 #define TP_PROF_KINDS 8
 typedef struct tp_profile {
   double ms[TP_PROF_KINDS];         /* summed device time of the launches of each kind            */
@@ -255,6 +256,15 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
 int64_t tp_vigo_frontend_batch(const tp_map_t* m, const tp_vigo_params* p, int32_t B, const double* starts,
                                const double* goals, int32_t* offsets_out, double* ctrl_out, int64_t ctrl_cap,
                                uint8_t* valid);
+/* bsplineTraj::inputPathCheck (bsplineTraj.cpp:207-245): returns 1 when consecutive points are already
+ * <= 1.5 * ctrl_pt_dist apart, 0 otherwise; `adjusted` (may be NULL) receives the adjusted path. */
+int tp_vigo_input_path_check(const tp_map_t* m, const tp_vigo_params* p, int32_t K, const double* path, double* adjusted,
+                             int32_t cap, int32_t* n_adjusted);
+/* bsplineTraj::updatePath (bsplineTraj.cpp:290-323) for one path of K points (+ v0,v1,a0,a1 or NULL for rest):
+ * goal check, adjustPathLengthDirect, fillPath, parameterizeToBspline.  Returns the number of control points
+ * written to ctrl_out, 0 when the reference's updatePath returns false, < 0 on error. */
+int tp_vigo_update_path(const tp_map_t* m, const tp_vigo_params* p, int32_t K, const double* path, const double* start_end4,
+                        double* ctrl_out, int32_t cap);
 /* bspline::parameterizeToBspline (bspline.cpp:74-138): K points (+ v0,v1,a0,a1) -> K+2 control points */
 int tp_bspline_fit(double ts, int32_t K, const double* points, const double* start_end4, double* ctrl_out);
 /* bspline::at / getDerivative().at (bspline.cpp:32-72), host side (pose-at-time queries stay on the host) */

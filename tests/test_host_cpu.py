@@ -219,3 +219,34 @@ def test_reference_arm_of_bench_runs_on_cpu():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "solves/s" and line["value"] > 0
     assert line["cpu_baseline"]["cores"] >= 1 and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_cpp_shim_compiles_and_fails_loudly_without_gpu(tp, tmp_path):
+    """The reference-shaped C++ shim (include/trajectory_planner/bsplineTraj_b200.hpp) builds as C++14 against
+    the C ABI, and the headless node exits with the 'no engine' code when there is no GPU."""
+    exe = tmp_path / "node"
+    r = subprocess.run(["g++", "-std=c++14", "-O1", "-Wall", "-Werror", os.path.join(ROOT, "examples", "bspline_node_headless.cpp"),
+                        "-o", str(exe), "-L" + os.path.dirname(tp._capi.LIB_PATH), "-ltp_b200",
+                        "-Wl,-rpath," + os.path.dirname(tp._capi.LIB_PATH)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    import torch
+    if not torch.cuda.is_available():
+        r2 = subprocess.run([str(exe), os.path.join(ROOT, "data", "maps", "square_static.tpm")], capture_output=True, text=True, timeout=120)
+        assert r2.returncode == 3 and "no CPU fallback" in r2.stdout
+
+
+def test_update_path_host_entry(tp, sq_map, sq_omap):
+    """tp_vigo_update_path == the numpy restatement of bsplineTraj::updatePath on a resampled path."""
+    from oracle import frontend_np
+    p = tp.default_params()
+    from helpers import random_pairs
+    S, G = random_pairs(sq_omap, 1, np.random.default_rng(9), min_dist=6.0)
+    path = S[0] + np.linspace(0, 1, int(np.linalg.norm(G[0] - S[0]) / 0.2) + 1)[:, None] * (G[0] - S[0])
+    assert sq_omap.query(path[-1:])[0] == 0
+    import ctypes as C
+    out = np.zeros((len(path) + 1024, 3))
+    n = tp.load().tp_vigo_update_path(sq_map.h, C.byref(p), len(path), tp._capi.ptr(path), None, tp._capi.ptr(out), len(out))
+    assert n > 4
+    inp = frontend_np.adjust_path_length_direct(list(path), sq_omap, p.max_path_length)
+    want = frontend_np.parameterize_to_bspline(p.ctrl_pt_ts, np.array(inp), np.zeros((4, 3)))
+    assert want.shape[0] == n and np.max(np.abs(out[:n] - want)) <= 1e-8

@@ -399,17 +399,28 @@ class BsplineTraj:
             return False
         return self.updateControlPoints(ctrl)
 
+    def inputPathCheck(self, path):
+        """bsplineTraj::inputPathCheck (bsplineTraj.cpp:207-245) -> (satisfied, adjusted_path)."""
+        path = _f64(path).reshape(-1, 3)
+        adj = np.zeros((max(4 * len(path), 64) + 4096, 3))
+        n = C.c_int32(0)
+        rc = check(_capi.load().tp_vigo_input_path_check(self.engine.map.h, C.byref(self.params), len(path), ptr(path),
+                                                         ptr(adj), len(adj), C.byref(n)), "tp_vigo_input_path_check")
+        return bool(rc), adj[:n.value].copy()
+
     def updatePath(self, path, start_end_conditions=None):
-        """bsplineTraj::updatePath for an already resampled path (>= 4 points): goal check + B-spline fit.
-        (adjustPathLengthDirect/fillPath are applied by updatePathFromStartGoal's front end.)"""
+        """bsplineTraj::updatePath (bsplineTraj.cpp:290-323): goal check, adjustPathLengthDirect, fillPath,
+        parameterizeToBspline — the reference's host-side code path, kept on the host."""
         path = _f64(path).reshape(-1, 3)
         if self.engine.map is None:
             raise _capi.TpError("setMap first")
-        if self.engine.query_points(path[-1:])[0]:
+        se = None if start_end_conditions is None else _f64(start_end_conditions).reshape(4, 3)
+        out = np.zeros((len(path) + 1024, 3))
+        n = check(_capi.load().tp_vigo_update_path(self.engine.map.h, C.byref(self.params), len(path), ptr(path), ptr(se),
+                                                   ptr(out), len(out)), "tp_vigo_update_path")
+        if n <= 0:
             return False
-        if len(path) < 4:
-            return False
-        return self.updateControlPoints(bspline_fit(self.params.ctrl_pt_ts, path, start_end_conditions))
+        return self.updateControlPoints(out[:n])
 
     def updateDynamicObstacles(self, pos, vel, size):
         self.dyn = (pos, vel, size)

@@ -354,4 +354,45 @@ int64_t tp_vigo_frontend_batch(const tp_map_t* m, const tp_vigo_params* p, int32
   return total;
 }
 
+// bsplineTraj::inputPathCheck (bsplineTraj.cpp:207-245) for one path
+int tp_vigo_input_path_check(const tp_map_t* m, const tp_vigo_params* p, int32_t K, const double* path, double* adjusted,
+                             int32_t cap, int32_t* n_adjusted) {
+  if (!m || !p || K < 0 || (K > 0 && !path) || !n_adjusted) return TP_ERR_INVALID_ARG;
+  std::vector<P3> in((size_t)K), adj;
+  for (int i = 0; i < K; ++i) in[i] = {path[3 * i], path[3 * i + 1], path[3 * i + 2]};
+  const bool sat = input_path_check(m, in, p->ctrl_pt_dist, p->max_path_length, adj);
+  *n_adjusted = (int32_t)adj.size();
+  if (adjusted) {
+    if ((int)adj.size() > cap) {
+      tp_set_error("tp_vigo_input_path_check: capacity %d < %zu points", cap, adj.size());
+      return TP_ERR_CAPACITY;
+    }
+    for (size_t i = 0; i < adj.size(); ++i) { adjusted[3 * i] = adj[i].x; adjusted[3 * i + 1] = adj[i].y; adjusted[3 * i + 2] = adj[i].z; }
+  }
+  return sat ? 1 : 0;
+}
+
+// bsplineTraj::updatePath (bsplineTraj.cpp:290-323) for one path: goal check, adjustPathLengthDirect, fillPath,
+// parameterizeToBspline.  Returns the number of control points written, 0 when the reference returns false.
+int tp_vigo_update_path(const tp_map_t* m, const tp_vigo_params* p, int32_t K, const double* path, const double* start_end4,
+                        double* ctrl_out, int32_t cap) {
+  if (!m || !p || K <= 0 || !path || !ctrl_out) return TP_ERR_INVALID_ARG;
+  std::vector<P3> in((size_t)K), inp;
+  for (int i = 0; i < K; ++i) in[i] = {path[3 * i], path[3 * i + 1], path[3 * i + 2]};
+  const P3 goal = in.back();
+  if (m->is_inflated_occupied(goal.x, goal.y, goal.z)) return 0;   // :291-295
+  adjust_path_length_direct(m, in, p->max_path_length, inp);
+  if (inp.size() < 4 && !fill_path(in, inp)) return 0;
+  const double zeros[12] = {0};
+  std::vector<double> ctrl;
+  fit_bspline(p->ctrl_pt_ts, inp, start_end4 ? start_end4 : zeros, ctrl);
+  const int n = (int)ctrl.size() / 3;
+  if (n > cap) {
+    tp_set_error("tp_vigo_update_path: capacity %d < %d control points", cap, n);
+    return TP_ERR_CAPACITY;
+  }
+  std::memcpy(ctrl_out, ctrl.data(), sizeof(double) * 3 * n);
+  return n;
+}
+
 }  // extern "C"
