@@ -458,3 +458,77 @@ def test_astar_exhaustive_failure_and_long_detour(tp, orc):
     assert paths[1] is not None and ex[1] > 4096  # reachable long detour across the trigger
     assert big >= 3 and paths[2] is None and paths[3] is not None
     e.close()
+
+
+def test_collision_sweep_box_map_bit_exact(tp, orc):
+    """BASELINE configs[4] in small: 1 M samples against the box.bt raster, decisions bit-exact vs the oracle
+    (uniform points over the map's bounding box plus a margin outside it, and trajectory-coherent samples)."""
+    from helpers import oracle_map_from
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    m = tp.OccMap.from_tpm(os.path.join(root, "data", "maps", "box.tpm"))
+    om = oracle_map_from(orc, m)
+    e = tp.Engine(0)
+    e.set_map(m)
+    info = m.info()
+    lo = np.array(info["origin"]) - 0.5
+    hi = np.array(info["origin"]) + np.array(info["dims"]) * info["res"] + 0.5
+    rng = np.random.default_rng(3)
+    q = rng.uniform(lo, hi, (1 << 20, 3))
+    p0 = rng.uniform(lo, hi, (256, 1, 3))
+    d = rng.normal(size=(256, 1, 3)); d /= np.linalg.norm(d, axis=2, keepdims=True)
+    coh = (p0 + d * (0.025 * np.arange(512))[None, :, None]).reshape(-1, 3)
+    for pts in (q, coh):
+        got = e.query_points(pts)
+        assert np.array_equal(got, om.query(pts))
+        assert 0.0 < got.mean() < 1.0
+    e.close()
+
+
+@pytest.mark.parametrize("name", ["maze", "tunnel"])
+def test_make_plan_on_octomap_rasters_strict_bit_faithful(tp, orc, name):
+    """BASELINE configs[2] in small: ViGO solves on maze.bt / tunnel.bt rasterised to the occMap contract (native
+    0.1 m resolution, inflation (4,4,2)); start/goal over free inflated cells of the z in [0.7,1.3] slab, 2-20 m
+    apart.  strict_order: whole-solve control flow and control points identical to the oracle."""
+    from helpers import oracle_map_from
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    m = tp.OccMap.from_tpm(os.path.join(root, "data", "maps", name + ".tpm"))
+    om = oracle_map_from(orc, m)
+    info = m.info()
+    inf = m.grid("inflated")
+    kz = int(np.floor((1.0 - info["origin"][2]) / info["res"]))
+    free = np.argwhere(inf[:, :, kz] == 0)
+    rng = np.random.default_rng(17)
+    S, G = [], []
+    while len(S) < 48:
+        a, b = free[rng.integers(len(free))], free[rng.integers(len(free))]
+        pa = np.array(info["origin"]) + (np.array([a[0], a[1], kz]) + 0.5) * info["res"]
+        pb = np.array(info["origin"]) + (np.array([b[0], b[1], kz]) + 0.5) * info["res"]
+        pa[2] = pb[2] = 1.0
+        if 2.0 <= np.linalg.norm(pa - pb) <= 20.0:
+            S.append(pa); G.append(pb)
+    p = tp.default_params()
+    p.strict_order = 1
+    off, ctrl, valid = tp.frontend_batch(m, p, np.array(S), np.array(G))
+    keep = [b for b in range(len(S)) if valid[b] and off[b + 1] - off[b] >= 7][:32]
+    assert len(keep) >= 16
+    o2 = np.concatenate([[0], np.cumsum([off[b + 1] - off[b] for b in keep])]).astype(np.int32)
+    c2 = np.concatenate([ctrl[off[b]:off[b + 1]] for b in keep], 0)
+    e = tp.Engine(0)
+    e.set_map(m)
+    out, res = e.make_plan_batch(p, o2, c2)
+    po = om.lib.default_params()
+    po.soft_atan2 = 1
+    _, out_o, st_o = orc.make_plan_batch(om, po, o2, c2, nthreads=4)
+    r = _plan_compare(o2, out, res, out_o, st_o)
+    print(name, r)
+    assert r["agree"] == len(keep) and r["same_flow"] == len(keep) and r["exact"] == len(keep)
+    # default mode: successful trajectories are collision free under the oracle's check
+    p.strict_order = 0
+    out2, res2 = e.make_plan_batch(p, o2, c2)
+    for b in range(len(keep)):
+        if res2["status"][b] == 1:
+            pl = orc.Planner(om)
+            pl.set_ctrl(out2[o2[b]:o2[b + 1]])
+            assert not pl.has_collision(), b
+    assert abs((res2["status"] == 1).mean() - st_o["success"].mean()) <= 0.15
+    e.close()
