@@ -270,6 +270,47 @@ int tp_bspline_fit(double ts, int32_t K, const double* points, const double* sta
 /* bspline::at / getDerivative().at (bspline.cpp:32-72), host side (pose-at-time queries stay on the host) */
 int tp_bspline_eval(int32_t N, const double* ctrl, double ts, int32_t deriv, int32_t nt, const double* t, double* out);
 
+/* ------------------------------------------------------------------------------------ min-snap / polyTraj (secondary path)
+ * polyTrajSolver's QP (polyTrajSolver.cpp:241-904; degree 7, differential degree 4) solved exactly through its KKT
+ * system, and polyTrajOctomap's collision-check-and-insert-waypoint loop (polyTrajOctomap.cpp:259-321, 547-656) on the
+ * engine's map with this contract: a point is "collision" when it lies outside the metric bounding box of the known
+ * cells, in an unknown cell, or in an occupied cell (raw occupancy, not inflated); a sample collides when any point
+ * of its collision box does (polyTrajOctomap.cpp:547-569, float coordinates as octomap::point3d).
+ * Paths are ragged: path b owns waypoints wp_offsets[b] .. wp_offsets[b+1]-1 (K_b = n_b - 1 segments).
+ * coef layout: problem b, axis a, segment s, power d at 24*(wp_offsets[b] - b) + a*8*K_b + 8*s + d (real time,
+ * de-normalised as polyTrajSolver.cpp:874-878); times = the time knots (desiredTime_). */
+typedef struct tp_poly_params {
+  double desired_vel;      /* desired_velocity                         1.0 */
+  double delT;             /* sample_delta_time                        0.1 */
+  double box[3];           /* collision_box                [0.4,0.4,0.2] */
+  double map_res;          /* map_resolution (box stride)              0.2 */
+  int32_t cont;            /* continuity_degree (2..4)                   4 */
+  int32_t max_iter;        /* maximum_iteration_num                    100 */
+  int32_t max_waypoints;   /* cap on a path's waypoints while inserting (<= 64) */
+  int32_t reserved;
+} tp_poly_params;
+void tp_poly_default_params(tp_poly_params* p);
+/* polyTrajSolver::solve (polyTrajSolver.cpp:849-904). bc (may be NULL = rest): per problem v0, v1, a0, a1 (12 doubles).
+ * status[b]: 0 ok, -1 singular KKT, -2 too many segments, -3 fewer than 2 waypoints.  Host memory. */
+int tp_minsnap_solve_batch(tp_engine_t* e, const tp_poly_params* p, int32_t B, const int32_t* wp_offsets, const double* waypoints,
+                           const double* bc, double* coef, double* times, int32_t* status);
+/* getTrajectory + checkCollisionTraj (polyTrajSolver.cpp:1125-1137, polyTrajOctomap.cpp:634-656): valid[B],
+ * seg_hit[sum K] (segment i of path b at wp_offsets[b]-b+i), n_samples[B]; optional positions / per-sample flags
+ * (samples[B*samp_cap*3], sample_hit[B*samp_cap]; pass NULL, NULL, 0 to skip). */
+int tp_poly_check_batch(tp_engine_t* e, const tp_poly_params* p, int32_t B, const int32_t* wp_offsets, const double* waypoints,
+                        const double* coef, const double* times, uint8_t* valid, uint8_t* seg_hit, int32_t* n_samples,
+                        double* samples, uint8_t* sample_hit, int32_t samp_cap);
+/* polyTrajOctomap::checkCollision (polyTrajOctomap.cpp:547-569) on n caller-supplied positions */
+int tp_poly_box_collision(tp_engine_t* e, const tp_poly_params* p, int64_t n, const double* xyz, uint8_t* hit);
+/* polyTrajOctomap::makePlanAddingWaypoint (polyTrajOctomap.cpp:259-321) for B paths.  The reference never refreshes the
+ * solver's path after insertWaypoint (:287-289 commented out) and so re-solves the original path until maxIter; this
+ * entry point implements the evident intent (re-solve the path WITH the inserted waypoints).  Outputs: the final
+ * waypoint lists (wp_offsets_out[B+1], waypoints_out with room for wp_cap points), their coefficients / knots in
+ * the layouts above (sized for wp_cap), valid[B], iters[B]. */
+int tp_polytraj_make_plan_batch(tp_engine_t* e, const tp_poly_params* p, int32_t B, const int32_t* wp_offsets, const double* waypoints,
+                                int32_t* wp_offsets_out, double* waypoints_out, int64_t wp_cap, double* coef_out, double* times_out,
+                                uint8_t* valid_out, int32_t* iters_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,6 +43,11 @@ class EngineCfg(C.Structure):
     ]
 
 
+class PolyParams(C.Structure):
+    _fields_ = [("desired_vel", C.c_double), ("delT", C.c_double), ("box", C.c_double * 3), ("map_res", C.c_double),
+                ("cont", C.c_int32), ("max_iter", C.c_int32), ("max_waypoints", C.c_int32), ("reserved", C.c_int32)]
+
+
 class MapInfo(C.Structure):
     _fields_ = [
         ("res", C.c_double), ("origin", C.c_double * 3), ("dims", C.c_int32 * 3), ("inflate", C.c_int32 * 3),
@@ -56,7 +61,7 @@ class Profile(C.Structure):
                 ("query_points", C.c_double)]
 
 
-PROF_KINDS = ["solve", "collision_check", "plan_step", "plan_init", "reparam", "map_query"]
+PROF_KINDS = ["solve", "collision_check", "plan_step", "plan_init", "reparam", "map_query", "minsnap_solve", "poly_check"]
 
 RESULT_DTYPE = np.dtype([
     ("status", "i4"), ("outer_rounds", "i4"), ("fail_count", "i4"), ("lbfgs_runs", "i4"), ("lbfgs_iters", "i4"),
@@ -74,7 +79,8 @@ SYMBOLS = [
     "tp_vigo_optimize_batch", "tp_vigo_has_collision_batch", "tp_vigo_find_collision_seg_batch", "tp_astar_batch",
     "tp_vigo_init_guides_batch", "tp_vigo_make_plan_batch", "tp_vigo_frontend_batch", "tp_vigo_input_path_check", "tp_vigo_update_path", "tp_bspline_fit",
     "tp_bspline_eval", "tp_engine_profile_enable", "tp_engine_profile_get", "tp_microbench_fp64",
-    "tp_microbench_gather",
+    "tp_microbench_gather", "tp_poly_default_params", "tp_minsnap_solve_batch", "tp_poly_check_batch",
+    "tp_poly_box_collision", "tp_polytraj_make_plan_batch",
 ]
 
 
@@ -142,6 +148,12 @@ def load():
     L.tp_vigo_update_path.argtypes = [vp, PP, C.c_int32, vp, vp, vp, C.c_int32]
     L.tp_bspline_fit.argtypes = [C.c_double, C.c_int32, vp, vp, vp]
     L.tp_bspline_eval.argtypes = [C.c_int32, vp, C.c_double, C.c_int32, C.c_int32, vp, vp]
+    QP = C.POINTER(PolyParams)
+    L.tp_poly_default_params.argtypes = [QP]
+    L.tp_minsnap_solve_batch.argtypes = [vp, QP, C.c_int32, vp, vp, vp, vp, vp, vp]
+    L.tp_poly_check_batch.argtypes = [vp, QP, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int32]
+    L.tp_poly_box_collision.argtypes = [vp, QP, C.c_int64, vp, vp]
+    L.tp_polytraj_make_plan_batch.argtypes = [vp, QP, C.c_int32, vp, vp, vp, vp, C.c_int64, vp, vp, vp, vp]
     L.tp_engine_profile_enable.argtypes = [vp, C.c_int]
     L.tp_engine_profile_get.argtypes = [vp, C.POINTER(Profile)]
     L.tp_microbench_fp64.argtypes = [vp, _dp]

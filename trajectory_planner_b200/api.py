@@ -354,6 +354,90 @@ class Engine:
               "tp_vigo_make_plan_batch")
 
 
+def default_poly_params():
+    p = _capi.PolyParams()
+    _capi.load().tp_poly_default_params(C.byref(p))
+    return p
+
+
+def _poly_split(wp_off, coef, times):
+    """flat coef/times -> per-path (coef[3, 8K], times[K+1])."""
+    out = []
+    for b in range(len(wp_off) - 1):
+        K = wp_off[b + 1] - wp_off[b] - 1
+        base = 24 * (wp_off[b] - b)
+        out.append((coef[base:base + 24 * K].reshape(3, 8 * K) if K > 0 else np.zeros((3, 0)), times[wp_off[b]:wp_off[b + 1]]))
+    return out
+
+
+class PolyTraj:
+    """Batched min-snap path of trajPlanner::polyTrajOctomap / polyTrajSolver on one engine (secondary path)."""
+
+    def __init__(self, engine, params=None):
+        self.engine = engine
+        self.params = params if params is not None else default_poly_params()
+
+    @staticmethod
+    def _flat(paths):
+        off = np.concatenate([[0], np.cumsum([len(p) for p in paths])]).astype(np.int32)
+        wp = np.concatenate([_f64(p).reshape(-1, 3) for p in paths], 0) if len(paths) else np.zeros((0, 3))
+        return off, np.ascontiguousarray(wp)
+
+    def solve_batch(self, paths, bc=None):
+        """polyTrajSolver::solve for a list of waypoint arrays -> list of (coef[3, 8K], times[K+1]), status[B]."""
+        off, wp = self._flat(paths)
+        B = len(paths)
+        coef = np.zeros(24 * max(int(off[-1]) - B, 1))
+        times = np.zeros(max(int(off[-1]), 1))
+        status = np.zeros(B, np.int32)
+        bcf = None if bc is None else _f64(bc).reshape(B, 12)
+        check(self.engine.L.tp_minsnap_solve_batch(self.engine.h, C.byref(self.params), B, ptr(off), ptr(wp), ptr(bcf), ptr(coef),
+                                                   ptr(times), ptr(status)), "tp_minsnap_solve_batch")
+        return _poly_split(off, coef, times), status
+
+    def check_batch(self, paths, sols, want_samples=False, samp_cap=2048):
+        off, wp = self._flat(paths)
+        B = len(paths)
+        coef = np.concatenate([s[0].ravel() for s in sols]) if B else np.zeros(0)
+        times = np.concatenate([s[1] for s in sols]) if B else np.zeros(0)
+        valid = np.zeros(B, np.uint8)
+        seg = np.zeros(max(int(off[-1]) - B, 1), np.uint8)
+        ns = np.zeros(B, np.int32)
+        samples = np.zeros((B, samp_cap, 3)) if want_samples else None
+        shit = np.zeros((B, samp_cap), np.uint8) if want_samples else None
+        check(self.engine.L.tp_poly_check_batch(self.engine.h, C.byref(self.params), B, ptr(off), ptr(wp), ptr(_f64(coef)), ptr(_f64(times)),
+                                                ptr(valid), ptr(seg), ptr(ns), ptr(samples), ptr(shit), samp_cap if want_samples else 0),
+              "tp_poly_check_batch")
+        segs = [np.nonzero(seg[off[b] - b: off[b + 1] - b - 1])[0] for b in range(B)]
+        if want_samples:
+            return valid, segs, ns, [samples[b, :ns[b]] for b in range(B)], [shit[b, :ns[b]] for b in range(B)]
+        return valid, segs, ns
+
+    def box_collision(self, xyz):
+        xyz = _f64(xyz).reshape(-1, 3)
+        out = np.zeros(len(xyz), np.uint8)
+        check(self.engine.L.tp_poly_box_collision(self.engine.h, C.byref(self.params), len(xyz), ptr(xyz), ptr(out)), "tp_poly_box_collision")
+        return out
+
+    def make_plan_batch(self, paths):
+        """polyTrajOctomap::makePlanAddingWaypoint for a list of waypoint arrays ->
+        list of dict(valid, iters, path, coef, times)."""
+        off, wp = self._flat(paths)
+        B = len(paths)
+        cap = B * 64
+        off_o = np.zeros(B + 1, np.int32)
+        wp_o = np.zeros((cap, 3))
+        coef = np.zeros(24 * cap)
+        times = np.zeros(cap)
+        valid = np.zeros(B, np.uint8)
+        iters = np.zeros(B, np.int32)
+        check(self.engine.L.tp_polytraj_make_plan_batch(self.engine.h, C.byref(self.params), B, ptr(off), ptr(wp), ptr(off_o), ptr(wp_o),
+                                                        cap, ptr(coef), ptr(times), ptr(valid), ptr(iters)), "tp_polytraj_make_plan_batch")
+        sols = _poly_split(off_o, coef, times)
+        return [dict(valid=bool(valid[b]), iters=int(iters[b]), path=wp_o[off_o[b]:off_o[b + 1]].copy(), coef=sols[b][0], times=sols[b][1])
+                for b in range(B)]
+
+
 class BsplineTraj:
     """Method-for-method stand-in for trajPlanner::bsplineTraj (bsplineTraj.h:87-181) for one
     trajectory: the planner state lives on the host, every heavy step runs on the GPU engine."""

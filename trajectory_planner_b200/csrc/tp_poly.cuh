@@ -1,0 +1,328 @@
+// Secondary path: batched min-snap polynomial solve + trajectory sampling + box collision check + the
+// "insert a midpoint waypoint into every colliding segment and re-solve" loop of
+// polyTrajOctomap::makePlanAddingWaypoint (polyTrajOctomap.cpp:259-321).  Included at the end of tp_vigo.cu
+// (same translation unit: shares tp_engine).
+//
+//  k_minsnap_solve : the QP of polyTrajSolver (P: polyTrajSolver.cpp:241-271, equality rows :314-584, bounds
+//                    :587-813, time allocation :125-138, de-normalisation :870-879) solved EXACTLY through its
+//                    KKT system [P A^T; A 0][x; lambda] = [0; b] (the reference hands it to OSQP, eps 1e-3) by an
+//                    in-place LU with partial pivoting, one thread block per problem, the three axes share the
+//                    factorisation.  The matrix (<= 14K x 14K, K <= 63 segments) lives in HBM scratch owned by the
+//                    resident block; rows whose multiplier is exactly zero are skipped (the KKT is sparse).
+//  k_poly_check    : polyTrajSolver::getTrajectory (:1125-1137, accumulated t += delT, position = sum c_d pow(t,d))
+//                    + polyTrajOctomap::checkCollisionTraj / checkCollision / checkCollisionPoint
+//                    (polyTrajOctomap.cpp:634-656, 547-590): per sample a box of points, each "collision" when
+//                    outside the known bounding box, unknown, or occupied; colliding samples mark their segment.
+#pragma once
+
+#define PL_THREADS 128
+#define PL_DEG 7
+#define PL_NC (PL_DEG + 1)
+#define PL_MAX_SEG 63          // segments per path the solver accepts (n = 14 K <= 882)
+
+struct PolyMap {   // the 3-state grid of the polyTraj collision contract
+  const uint32_t* __restrict__ occ;
+  const uint32_t* __restrict__ known;
+  double res;
+  double mn[3];
+  int dim[3];
+  int wz;
+  double bbmin[3], bbmax[3];   // metric bounding box of the known cells (octomap getMetricMin/Max stand-in)
+};
+
+// polyTrajOctomap::checkCollisionPoint with ignoreUnknown = false
+__device__ __forceinline__ bool pm_collision_point(const PolyMap& m, double x, double y, double z) {
+  if (x < m.bbmin[0] || x > m.bbmax[0] || y < m.bbmin[1] || y > m.bbmax[1] || z < m.bbmin[2] || z > m.bbmax[2]) return true;
+  const double fx = floor((x - m.mn[0]) / m.res), fy = floor((y - m.mn[1]) / m.res), fz = floor((z - m.mn[2]) / m.res);
+  if (!(fx >= 0.0 && fx < (double)m.dim[0] && fy >= 0.0 && fy < (double)m.dim[1] && fz >= 0.0 && fz < (double)m.dim[2])) return true;
+  const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+  const size_t w = ((size_t)ix * m.dim[1] + iy) * m.wz + (iz >> 5);
+  if (!((__ldg(&m.known[w]) >> (iz & 31)) & 1u)) return true;
+  return (__ldg(&m.occ[w]) >> (iz & 31)) & 1u;
+}
+// polyTrajOctomap::checkCollision: p is converted to float (pose2Octomap), the box corners are doubles computed
+// from the float coordinates, every box point goes back through float (octomap::point3d)
+__device__ __forceinline__ bool pm_collision_box(const PolyMap& m, double px, double py, double pz, const double box[3],
+                                                 double map_res) {
+  const double fx = (double)(float)px, fy = (double)(float)py, fz = (double)(float)pz;
+  const double xmin = fx - box[0] / 2, xmax = fx + box[0] / 2;
+  const double ymin = fy - box[1] / 2, ymax = fy + box[1] / 2;
+  const double zmin = fz - box[2] / 2, zmax = fz + box[2] / 2;
+  const int xNum = (int)((xmax - xmin) / map_res), yNum = (int)((ymax - ymin) / map_res), zNum = (int)((zmax - zmin) / map_res);
+  for (int a = 0; a <= xNum; ++a)
+    for (int b = 0; b <= yNum; ++b)
+      for (int c = 0; c <= zNum; ++c) {
+        const double qx = (double)(float)(xmin + a * map_res), qy = (double)(float)(ymin + b * map_res),
+                     qz = (double)(float)(zmin + c * map_res);
+        if (pm_collision_point(m, qx, qy, qz)) return true;
+      }
+  return false;
+}
+
+// ------------------------------------------------------------------------------------------- solve
+struct PolySolveArgs {
+  int B;
+  const int* wp_off;      // [B+1] waypoint offsets
+  const double* wp;       // [3 * total waypoints]
+  const double* bc;       // [B * 12] v0, v1, a0, a1 per problem (may be null -> zeros)
+  double desired_vel;
+  int cont;               // continuity degree 2..4
+  double* coef;           // out: problem b, axis a, segment s, power d at 24*(wp_off[b]-b) + a*8*K + 8*s + d
+  double* times;          // out: [total waypoints] time knots
+  int* status;            // out: 0 ok, -1 singular, -2 too many segments
+  double* scratch;        // [grid * (nmax*nmax + 3*nmax)]
+  int nmax;
+  int* queue;
+};
+
+__global__ void __launch_bounds__(PL_THREADS) k_minsnap_solve(PolySolveArgs A) {
+  __shared__ int s_b, s_piv, s_bad;
+  __shared__ double s_red[PL_THREADS / 32];
+  __shared__ int s_redi[PL_THREADS / 32];
+  __shared__ double s_dt[PL_MAX_SEG + 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* M = A.scratch + (size_t)blockIdx.x * ((size_t)A.nmax * A.nmax + 3 * (size_t)A.nmax);
+  double* R = M + (size_t)A.nmax * A.nmax;   // rhs, [n][3]
+  for (;;) {
+    if (tid == 0) s_b = atomicAdd(A.queue, 1);
+    __syncthreads();
+    const int b = s_b;
+    if (b >= A.B) break;
+    const int w0 = A.wp_off[b], nwp = A.wp_off[b + 1] - w0, K = nwp - 1;
+    const size_t coff = (size_t)3 * PL_NC * (w0 - b);
+    if (K < 1 || K > PL_MAX_SEG) {
+      if (tid == 0) A.status[b] = K < 1 ? -3 : -2;
+      __syncthreads();
+      continue;
+    }
+    const int nvar = PL_NC * K;
+    const int ncon = (2 + 2 * (K - 1)) + 2 * (2 + (K - 1)) + (K - 1) * (A.cont - 2);
+    const int n = nvar + ncon;
+    const double* wp = A.wp + 3 * (size_t)w0;
+    // ---- time allocation (avgTimeAllocation): knots accumulate distance / desiredVel
+    if (tid == 0) {
+      double tt = 0.0;
+      A.times[w0] = 0.0;
+      for (int i = 1; i < nwp; ++i) {
+        const double dx = wp[3 * i] - wp[3 * i - 3], dy = wp[3 * i + 1] - wp[3 * i - 2], dz = wp[3 * i + 2] - wp[3 * i - 1];
+        const double dur = sqrt(dx * dx + dy * dy + dz * dz) / A.desired_vel;
+        s_dt[i - 1] = dur;
+        tt += dur;
+        A.times[w0 + i] = tt;
+      }
+      s_bad = 0;
+    }
+    for (size_t e = tid; e < (size_t)n * n; e += PL_THREADS) M[e] = 0.0;
+    for (int e = tid; e < 3 * n; e += PL_THREADS) R[e] = 0.0;
+    __syncthreads();
+    // ---- P: snap Gram matrix on normalised time (constructP)
+    for (int e = tid; e < K * 16; e += PL_THREADS) {
+      const int s = e / 16, i = 4 + (e % 16) / 4, j = 4 + (e % 4);
+      double f = 1.0;
+      for (int d = 0; d < 4; ++d) f *= (double)((i - d) * (j - d));
+      f /= (double)(i + j - 7);
+      M[(size_t)(s * PL_NC + i) * n + (s * PL_NC + j)] = f;
+    }
+    // ---- A (and A^T) + b: rows in the reference's order (constructA / constructBound)
+    if (tid == 0) {
+      const double* bc = A.bc ? A.bc + 12 * (size_t)b : nullptr;
+      int r = nvar;
+      auto put = [&](int row, int seg, double t1, int order, double scale, double sign) {
+        // derivative row of segment `seg` at normalised time 0 (t1 = 0) or 1: c_d * t^(d-order)
+        for (int d = order; d < PL_NC; ++d) {
+          double c = 1.0;
+          for (int k = 0; k < order; ++k) c *= (double)(d - k);
+          if (t1 == 0.0 && d != order) continue;
+          const double v = sign * c * scale;
+          const int col = seg * PL_NC + d;
+          M[(size_t)row * n + col] += v;
+          M[(size_t)col * n + row] += v;
+        }
+      };
+      auto rhs = [&](int row, double x, double y, double z) { R[3 * row] = x; R[3 * row + 1] = y; R[3 * row + 2] = z; };
+      put(r, 0, 0.0, 0, 1.0, 1.0); rhs(r, wp[0], wp[1], wp[2]); ++r;
+      put(r, K - 1, 1.0, 0, 1.0, 1.0); rhs(r, wp[3 * K], wp[3 * K + 1], wp[3 * K + 2]); ++r;
+      for (int i = 0; i < K - 1; ++i) { put(r, i, 1.0, 0, 1.0, 1.0); rhs(r, wp[3 * i + 3], wp[3 * i + 4], wp[3 * i + 5]); ++r; }
+      for (int i = 0; i < K - 1; ++i) { put(r, i, 1.0, 0, 1.0, 1.0); put(r, i + 1, 0.0, 0, 1.0, -1.0); ++r; }
+      for (int order = 1; order <= 2; ++order) {
+        put(r, 0, 0.0, order, 1.0, 1.0);
+        if (bc) rhs(r, bc[(order == 1 ? 0 : 6)], bc[(order == 1 ? 1 : 7)], bc[(order == 1 ? 2 : 8)]);
+        ++r;
+        put(r, K - 1, 1.0, order, 1.0, 1.0);
+        if (bc) rhs(r, bc[(order == 1 ? 3 : 9)], bc[(order == 1 ? 4 : 10)], bc[(order == 1 ? 5 : 11)]);
+        ++r;
+        for (int i = 0; i < K - 1; ++i) {
+          double sl = 1.0, sr = 1.0;
+          for (int k = 0; k < order; ++k) { sl *= s_dt[i + 1]; sr *= s_dt[i]; }
+          put(r, i, 1.0, order, sl, 1.0);
+          put(r, i + 1, 0.0, order, sr, -1.0);
+          ++r;
+        }
+      }
+      for (int order = 3; order <= A.cont; ++order)
+        for (int i = 0; i < K - 1; ++i) {
+          double sl = 1.0, sr = 1.0;
+          for (int k = 0; k < order; ++k) { sl *= s_dt[i + 1]; sr *= s_dt[i]; }
+          put(r, i, 1.0, order, sl, 1.0);
+          put(r, i + 1, 0.0, order, sr, -1.0);
+          ++r;
+        }
+    }
+    __syncthreads();
+    // ---- LU with partial pivoting, right-looking; rows with a zero multiplier are skipped
+    for (int k = 0; k < n; ++k) {
+      double best = -1.0;
+      int bi = k;
+      for (int i = k + tid; i < n; i += PL_THREADS) {
+        const double v = fabs(M[(size_t)i * n + k]);
+        if (v > best) { best = v; bi = i; }
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+      }
+      if (lane == 0) { s_red[warp] = best; s_redi[warp] = bi; }
+      __syncthreads();
+      if (tid == 0) {
+        double bb = s_red[0];
+        int ii = s_redi[0];
+        for (int w = 1; w < PL_THREADS / 32; ++w)
+          if (s_red[w] > bb || (s_red[w] == bb && s_redi[w] < ii)) { bb = s_red[w]; ii = s_redi[w]; }
+        s_piv = ii;
+        if (!(bb > 1e-300)) s_bad = 1;
+      }
+      __syncthreads();
+      if (s_bad) break;
+      const int p = s_piv;
+      if (p != k) {
+        for (int j = k + tid; j < n; j += PL_THREADS) {
+          const double a = M[(size_t)k * n + j];
+          M[(size_t)k * n + j] = M[(size_t)p * n + j];
+          M[(size_t)p * n + j] = a;
+        }
+        if (tid < 3) { const double a = R[3 * k + tid]; R[3 * k + tid] = R[3 * p + tid]; R[3 * p + tid] = a; }
+        __syncthreads();
+      }
+      const double inv = 1.0 / M[(size_t)k * n + k];
+      for (int i = k + 1 + warp; i < n; i += PL_THREADS / 32) {
+        const double mik = M[(size_t)i * n + k];
+        if (mik == 0.0) continue;   // uniform per warp
+        const double l = mik * inv;
+        for (int j = k + 1 + lane; j < n; j += 32) M[(size_t)i * n + j] -= l * M[(size_t)k * n + j];
+        if (lane < 3) R[3 * i + lane] -= l * R[3 * k + lane];
+        if (lane == 0) M[(size_t)i * n + k] = 0.0;
+      }
+      __syncthreads();
+    }
+    if (s_bad) {
+      if (tid == 0) A.status[b] = -1;
+      __syncthreads();
+      continue;
+    }
+    // ---- back substitution, one warp per axis
+    if (warp < 3) {
+      for (int i = n - 1; i >= 0; --i) {
+        double acc = 0.0;
+        for (int j = i + 1 + lane; j < n; j += 32) acc += M[(size_t)i * n + j] * R[3 * j + warp];
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) R[3 * i + warp] = (R[3 * i + warp] - acc) / M[(size_t)i * n + i];
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // ---- de-normalise: c_d /= dt^d (solveX..Z, :874-878)
+    for (int e = tid; e < 3 * nvar; e += PL_THREADS) {
+      const int a = e / nvar, q = e - a * nvar, s = q / PL_NC, d = q - s * PL_NC;
+      A.coef[coff + (size_t)a * nvar + q] = R[3 * q + a] / pow(s_dt[s], (double)d);
+    }
+    if (tid == 0) A.status[b] = 0;
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------- sample + check
+struct PolyCheckArgs {
+  int B;
+  const int* wp_off;
+  const double* wp;
+  const double* coef;
+  const double* times;
+  const double* t_acc;     // accumulated sample times: t_acc[0] = 0, t_acc[s+1] = t_acc[s] + delT
+  int n_t_acc;
+  double box[3];
+  double map_res;
+  uint8_t* valid;          // [B] 1 = no colliding sample
+  uint8_t* seg_hit;        // [total segments] at wp_off[b] - b + i
+  int* n_samples;          // [B] trajectory entries (polynomial samples + the appended last waypoint)
+  double* samples;         // optional [B * samp_cap * 3] positions (parity entry), else null
+  uint8_t* sample_hit;     // optional [B * samp_cap]
+  int samp_cap;
+};
+
+__device__ __forceinline__ void poly_eval(const double* coef, const double* knots, int K, double t, double out[3]) {
+  // polyTrajSolver::getPose: first segment with knot[i] <= t <= knot[i+1]; position = sum_d c_d * pow(t - knot[i], d)
+  out[0] = out[1] = out[2] = 0.0;
+  for (int i = 0; i < K; ++i) {
+    if (t >= knots[i] && t <= knots[i + 1]) {
+      const double tt = t - knots[i];
+      for (int a = 0; a < 3; ++a) {
+        const double* c = coef + (size_t)a * PL_NC * K + PL_NC * i;
+        double x = 0.0;
+        for (int d = 0; d < PL_NC; ++d) x += c[d] * pow(tt, (double)d);
+        out[a] = x;
+      }
+      return;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(PL_THREADS) k_poly_check(PolyCheckArgs A, PolyMap map) {
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int w0 = A.wp_off[b], nwp = A.wp_off[b + 1] - w0, K = nwp - 1;
+  if (K < 1) {
+    if (tid == 0) { A.valid[b] = 1; A.n_samples[b] = 0; }
+    return;
+  }
+  const double* knots = A.times + w0;
+  const double* coef = A.coef + (size_t)3 * PL_NC * (w0 - b);
+  uint8_t* seg_hit = A.seg_hit + (w0 - b);
+  const double T = knots[K];
+  for (int i = tid; i < K; i += PL_THREADS) seg_hit[i] = 0;
+  __syncthreads();
+  // number of polynomial samples: t_acc[s] < T
+  int lo = 0, hi = A.n_t_acc;   // first s with t_acc[s] >= T
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (A.t_acc[mid] < T) lo = mid + 1; else hi = mid;
+  }
+  const int npoly = lo, ntraj = npoly + 1;
+  int any = 0;
+  for (int s = tid; s < ntraj; s += PL_THREADS) {
+    double p[3];
+    if (s < npoly) poly_eval(coef, knots, K, A.t_acc[s], p);
+    else { p[0] = A.wp[3 * (size_t)(w0 + K)]; p[1] = A.wp[3 * (size_t)(w0 + K) + 1]; p[2] = A.wp[3 * (size_t)(w0 + K) + 2]; }
+    const bool hit = pm_collision_box(map, p[0], p[1], p[2], A.box, A.map_res);
+    if (A.samples && s < A.samp_cap) {
+      double* o = A.samples + ((size_t)b * A.samp_cap + s) * 3;
+      o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+      A.sample_hit[(size_t)b * A.samp_cap + s] = hit ? 1 : 0;
+    }
+    if (hit) {
+      any = 1;
+      const double t = s < A.n_t_acc ? A.t_acc[s] : 1e300;   // checkCollisionTraj's own accumulated t (:639,654)
+      for (int i = 0; i < K; ++i)
+        if (t >= knots[i] && t <= knots[i + 1]) { seg_hit[i] = 1; break; }
+    }
+  }
+  any = __syncthreads_or(any);
+  if (tid == 0) { A.valid[b] = any ? 0 : 1; A.n_samples[b] = ntraj; }
+}
+
+// box collision check on caller-supplied positions (parity entry: decisions are bit-exact functions of the position)
+__global__ void k_poly_box_points(PolyMap map, long n, const double* __restrict__ xyz, double bx, double by, double bz,
+                                  double map_res, uint8_t* __restrict__ out) {
+  const double box[3] = {bx, by, bz};
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    out[i] = pm_collision_box(map, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], box, map_res) ? 1 : 0;
+}

@@ -680,6 +680,8 @@ __global__ void k_collect_results(BatchView bv, tp_vigo_result* out) {
   out[b] = r;
 }
 
+#include "tp_poly.cuh"
+
 // =========================================================================== engine
 struct DevBuf {
   void* p = nullptr;
@@ -716,7 +718,11 @@ struct tp_engine {
   // map replica
   bool has_map = false;
   DevMap dmap;
-  DevBuf map_infl, map_known;
+  DevBuf map_infl, map_known, map_occ;
+  double known_bbmin[3] = {0, 0, 0}, known_bbmax[3] = {0, 0, 0};   // metric bounding box of the known cells
+  DevBuf poly_scratch, poly_tacc;
+  int poly_tacc_n = 0;
+  double poly_tacc_dt = -1;
   double map_res = 0;
   // tables (depend on params + map res)
   DevBuf t_check, t_reparam, a_line;
@@ -1152,7 +1158,7 @@ void tp_engine_destroy(tp_engine_t* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
-  DevBuf* bufs[] = {&e->map_infl, &e->map_known, &e->t_check, &e->t_reparam, &e->a_line, &e->pool_nodes, &e->pool_heaps, &e->pool_heapn,
+  DevBuf* bufs[] = {&e->map_occ, &e->poly_scratch, &e->poly_tacc, &e->map_infl, &e->map_known, &e->t_check, &e->t_reparam, &e->a_line, &e->pool_nodes, &e->pool_heaps, &e->pool_heapn,
                     &e->pool_paths, &e->pool_sc, &e->pool_sclen, &e->pool_rounds, &e->pool_flags, &e->off, &e->ctrl, &e->st, &e->pairs,
                     &e->cp_head, &e->cp_tail, &e->active[0], &e->active[1], &e->counters, &e->results, &e->dyn,
                     &e->scratch_a, &e->scratch_b, &e->scratch_c};
@@ -1177,6 +1183,25 @@ int tp_engine_set_map(tp_engine_t* e, const tp_map_t* m) {
   if (e->map_infl.ensure(wi.size() * 4) != TP_OK || e->map_known.ensure(wk.size() * 4) != TP_OK) return TP_ERR_CUDA;
   CK(cudaMemcpy(e->map_infl.p, wi.data(), wi.size() * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(e->map_known.p, wk.data(), wk.size() * 4, cudaMemcpyHostToDevice));
+  {
+    std::vector<uint32_t> wo;
+    m->pack(0, wo);
+    if (e->map_occ.ensure(wo.size() * 4) != TP_OK) return TP_ERR_CUDA;
+    CK(cudaMemcpy(e->map_occ.p, wo.data(), wo.size() * 4, cudaMemcpyHostToDevice));
+    // bounding box of the known cells (the polyTraj collision contract's getMetricMin/Max)
+    int lo[3] = {m->dims[0], m->dims[1], m->dims[2]}, hi[3] = {-1, -1, -1};
+    for (int ix = 0; ix < m->dims[0]; ++ix)
+      for (int iy = 0; iy < m->dims[1]; ++iy)
+        for (int iz = 0; iz < m->dims[2]; ++iz)
+          if (m->known[m->addr(ix, iy, iz)]) {
+            const int v[3] = {ix, iy, iz};
+            for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], v[a]); hi[a] = std::max(hi[a], v[a]); }
+          }
+    for (int a = 0; a < 3; ++a) {
+      e->known_bbmin[a] = m->origin[a] + (hi[a] >= 0 ? lo[a] : 0) * m->res;
+      e->known_bbmax[a] = m->origin[a] + (hi[a] >= 0 ? hi[a] + 1 : 0) * m->res;
+    }
+  }
   e->dmap.inflated = e->map_infl.as<uint32_t>();
   e->dmap.known = e->map_known.as<uint32_t>();
   e->dmap.res = m->res;
@@ -1691,6 +1716,245 @@ int tp_microbench_gather(tp_engine_t* e, int64_t bytes, double* gbs) {
   cudaEventDestroy(a);
   cudaEventDestroy(b);
   *gbs = best;
+  return TP_OK;
+}
+
+
+// ------------------------------------------------------------------------------------ min-snap / polyTraj (secondary path)
+static PolyMap make_polymap(const tp_engine* e) {
+  PolyMap pm;
+  pm.occ = (const uint32_t*)e->map_occ.p;
+  pm.known = (const uint32_t*)e->map_known.p;
+  pm.res = e->dmap.res;
+  for (int a = 0; a < 3; ++a) { pm.mn[a] = e->dmap.mn[a]; pm.dim[a] = e->dmap.dim[a]; pm.bbmin[a] = e->known_bbmin[a]; pm.bbmax[a] = e->known_bbmax[a]; }
+  pm.wz = e->dmap.wz;
+  return pm;
+}
+void tp_poly_default_params(tp_poly_params* p) {
+  // cfg/planner_interactive.yaml + polyTrajOctomap.cpp:14-108 (mode = true: the re-insert loop)
+  memset(p, 0, sizeof(*p));
+  p->desired_vel = 1.0; p->delT = 0.1;
+  p->box[0] = 0.4; p->box[1] = 0.4; p->box[2] = 0.2;
+  p->map_res = 0.2; p->cont = 4; p->max_iter = 100; p->max_waypoints = 64;
+}
+static int poly_check_params(const tp_engine* e, const tp_poly_params* p, bool need_map) {
+  if (!e || !p) return TP_ERR_INVALID_ARG;
+  if (need_map && !e->has_map) { tp_set_error("engine has no map"); return TP_ERR_NO_MAP; }
+  if (!(p->desired_vel > 0) || !(p->delT > 0) || !(p->map_res > 0) || p->cont < 2 || p->cont > 4) {
+    tp_set_error("invalid polyTraj parameters");
+    return TP_ERR_INVALID_ARG;
+  }
+  return TP_OK;
+}
+// device-side solve on device-resident waypoints; outputs device pointers
+static int poly_solve_device(tp_engine* e, const tp_poly_params* p, int B, int max_k, const int* d_off, const double* d_wp,
+                             const double* d_bc, double* d_coef, double* d_times, int* d_status, cudaStream_t s) {
+  if (max_k > PL_MAX_SEG) { tp_set_error("a path has %d segments (max %d)", max_k, PL_MAX_SEG); return TP_ERR_CAPACITY; }
+  const int nmax = 14 * std::max(max_k, 1);
+  const int grid = std::min(B, e->sm_count * 8);
+  if (e->poly_scratch.ensure((size_t)grid * ((size_t)nmax * nmax + 3 * (size_t)nmax) * 8) != TP_OK || e->counters.ensure(64 * 4) != TP_OK)
+    return TP_ERR_CUDA;
+  CK(cudaMemsetAsync(e->counters.p, 0, 64 * 4, s));
+  PolySolveArgs A;
+  A.B = B; A.wp_off = d_off; A.wp = d_wp; A.bc = d_bc; A.desired_vel = p->desired_vel; A.cont = p->cont;
+  A.coef = d_coef; A.times = d_times; A.status = d_status; A.scratch = e->poly_scratch.as<double>(); A.nmax = nmax;
+  A.queue = e->counters.as<int>();
+  {
+    ProfScope ps(e, 6, s, B);
+    k_minsnap_solve<<<grid, PL_THREADS, 0, s>>>(A);
+  }
+  e->launches += 1;
+  CK(cudaGetLastError());
+  return TP_OK;
+}
+static int poly_ensure_tacc(tp_engine* e, double delT, cudaStream_t s) {
+  if (e->poly_tacc_dt == delT && e->poly_tacc_n > 0) return TP_OK;
+  std::vector<double> t;
+  double x = 0.0;
+  for (int i = 0; i < 65536; ++i) { t.push_back(x); x += delT; }
+  if (e->poly_tacc.ensure(t.size() * 8) != TP_OK) return TP_ERR_CUDA;
+  CK(cudaMemcpyAsync(e->poly_tacc.p, t.data(), t.size() * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(s));
+  e->poly_tacc_n = (int)t.size();
+  e->poly_tacc_dt = delT;
+  return TP_OK;
+}
+
+int tp_minsnap_solve_batch(tp_engine_t* e, const tp_poly_params* p, int32_t B, const int32_t* wp_offsets, const double* waypoints,
+                           const double* bc, double* coef, double* times, int32_t* status) {
+  int rc = poly_check_params(e, p, false);
+  if (rc != TP_OK) return rc;
+  if (B <= 0 || !wp_offsets || !waypoints || !coef || !times || !status) return TP_ERR_INVALID_ARG;
+  CK(cudaSetDevice(e->device));
+  cudaStream_t s = e->stream;
+  const int total = wp_offsets[B];
+  int max_k = 0;
+  for (int b = 0; b < B; ++b) max_k = std::max(max_k, wp_offsets[b + 1] - wp_offsets[b] - 1);
+  const size_t ncoef = (size_t)24 * std::max(total - B, 1);
+  if (e->off.ensure((size_t)(B + 1) * 4) != TP_OK || e->ctrl.ensure((size_t)std::max(total, 1) * 24) != TP_OK ||
+      e->scratch_a.ensure(ncoef * 8) != TP_OK || e->scratch_b.ensure((size_t)std::max(total, 1) * 8) != TP_OK ||
+      e->scratch_c.ensure((size_t)B * 4 + (bc ? (size_t)B * 96 : 0) + 64) != TP_OK)
+    return TP_ERR_CUDA;
+  CK(cudaMemcpyAsync(e->off.p, wp_offsets, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(e->ctrl.p, waypoints, (size_t)total * 24, cudaMemcpyHostToDevice, s));
+  int* d_status = e->scratch_c.as<int>();
+  double* d_bc = nullptr;
+  if (bc) {
+    d_bc = reinterpret_cast<double*>(e->scratch_c.as<char>() + (((size_t)B * 4 + 63) & ~(size_t)63));
+    CK(cudaMemcpyAsync(d_bc, bc, (size_t)B * 96, cudaMemcpyHostToDevice, s));
+  }
+  rc = poly_solve_device(e, p, B, max_k, e->off.as<int>(), e->ctrl.as<double>(), d_bc, e->scratch_a.as<double>(), e->scratch_b.as<double>(), d_status, s);
+  if (rc != TP_OK) return rc;
+  CK(cudaMemcpyAsync(coef, e->scratch_a.p, (size_t)24 * (total - B) * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(times, e->scratch_b.p, (size_t)total * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(status, d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return TP_OK;
+}
+
+int tp_poly_check_batch(tp_engine_t* e, const tp_poly_params* p, int32_t B, const int32_t* wp_offsets, const double* waypoints,
+                        const double* coef, const double* times, uint8_t* valid, uint8_t* seg_hit, int32_t* n_samples,
+                        double* samples, uint8_t* sample_hit, int32_t samp_cap) {
+  int rc = poly_check_params(e, p, true);
+  if (rc != TP_OK) return rc;
+  if (B <= 0 || !wp_offsets || !waypoints || !coef || !times || !valid || !seg_hit || !n_samples) return TP_ERR_INVALID_ARG;
+  CK(cudaSetDevice(e->device));
+  cudaStream_t s = e->stream;
+  rc = poly_ensure_tacc(e, p->delT, s);
+  if (rc != TP_OK) return rc;
+  const int total = wp_offsets[B], nseg = total - B;
+  const size_t ncoef = (size_t)24 * std::max(nseg, 1);
+  const size_t samp_bytes = samples ? (size_t)B * samp_cap * 25 : 0;
+  if (e->off.ensure((size_t)(B + 1) * 4) != TP_OK || e->ctrl.ensure((size_t)std::max(total, 1) * 24) != TP_OK ||
+      e->scratch_a.ensure(ncoef * 8) != TP_OK || e->scratch_b.ensure((size_t)std::max(total, 1) * 8) != TP_OK ||
+      e->scratch_c.ensure((size_t)B * 8 + (size_t)std::max(nseg, 1) + 64) != TP_OK || (samples && e->results.ensure(samp_bytes + 64) != TP_OK))
+    return TP_ERR_CUDA;
+  CK(cudaMemcpyAsync(e->off.p, wp_offsets, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(e->ctrl.p, waypoints, (size_t)total * 24, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(e->scratch_a.p, coef, (size_t)24 * nseg * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(e->scratch_b.p, times, (size_t)total * 8, cudaMemcpyHostToDevice, s));
+  PolyCheckArgs A;
+  A.B = B; A.wp_off = e->off.as<int>(); A.wp = e->ctrl.as<double>(); A.coef = e->scratch_a.as<double>(); A.times = e->scratch_b.as<double>();
+  A.t_acc = e->poly_tacc.as<double>(); A.n_t_acc = e->poly_tacc_n;
+  for (int a = 0; a < 3; ++a) A.box[a] = p->box[a];
+  A.map_res = p->map_res;
+  A.n_samples = e->scratch_c.as<int>();
+  A.valid = reinterpret_cast<uint8_t*>(A.n_samples + B);
+  A.seg_hit = A.valid + B;
+  A.samples = samples ? e->results.as<double>() : nullptr;
+  A.sample_hit = samples ? reinterpret_cast<uint8_t*>(e->results.as<double>() + (size_t)B * samp_cap * 3) : nullptr;
+  A.samp_cap = samp_cap;
+  if (samples) CK(cudaMemsetAsync(e->results.p, 0, samp_bytes, s));
+  {
+    ProfScope ps(e, 7, s, B);
+    k_poly_check<<<B, PL_THREADS, 0, s>>>(A, make_polymap(e));
+  }
+  e->launches += 1;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(valid, A.valid, (size_t)B, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(seg_hit, A.seg_hit, (size_t)nseg, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(n_samples, A.n_samples, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+  if (samples) {
+    CK(cudaMemcpyAsync(samples, A.samples, (size_t)B * samp_cap * 24, cudaMemcpyDeviceToHost, s));
+    if (sample_hit) CK(cudaMemcpyAsync(sample_hit, A.sample_hit, (size_t)B * samp_cap, cudaMemcpyDeviceToHost, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  return TP_OK;
+}
+
+int tp_poly_box_collision(tp_engine_t* e, const tp_poly_params* p, int64_t n, const double* xyz, uint8_t* hit) {
+  int rc = poly_check_params(e, p, true);
+  if (rc != TP_OK) return rc;
+  if (n < 0 || (n > 0 && (!xyz || !hit))) return TP_ERR_INVALID_ARG;
+  if (n == 0) return TP_OK;
+  CK(cudaSetDevice(e->device));
+  cudaStream_t s = e->stream;
+  if (e->scratch_a.ensure((size_t)n * 24) != TP_OK || e->scratch_c.ensure((size_t)n) != TP_OK) return TP_ERR_CUDA;
+  CK(cudaMemcpyAsync(e->scratch_a.p, xyz, (size_t)n * 24, cudaMemcpyHostToDevice, s));
+  const long blocks = std::min<long>((n + 255) / 256, (long)e->sm_count * 8);
+  k_poly_box_points<<<(int)blocks, 256, 0, s>>>(make_polymap(e), (long)n, e->scratch_a.as<double>(), p->box[0], p->box[1], p->box[2],
+                                                 p->map_res, e->scratch_c.as<uint8_t>());
+  e->launches += 1;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(hit, e->scratch_c.p, (size_t)n, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return TP_OK;
+}
+
+// polyTrajOctomap::makePlanAddingWaypoint (polyTrajOctomap.cpp:259-321) for B paths: solve -> sample -> box collision check ->
+// insert a midpoint into every colliding segment (highest index first, :178-186) -> re-solve, until collision free,
+// max_iter iterations (the reference's countIter > maxIter_ exit) or the waypoint cap.  The waypoint lists grow on the
+// host between device passes; only the still-invalid paths are re-submitted.
+int tp_polytraj_make_plan_batch(tp_engine_t* e, const tp_poly_params* p, int32_t B, const int32_t* wp_offsets, const double* waypoints,
+                                int32_t* wp_offsets_out, double* waypoints_out, int64_t wp_cap, double* coef_out, double* times_out,
+                                uint8_t* valid_out, int32_t* iters_out) {
+  int rc = poly_check_params(e, p, true);
+  if (rc != TP_OK) return rc;
+  if (B <= 0 || !wp_offsets || !waypoints || !wp_offsets_out || !waypoints_out || !coef_out || !times_out || !valid_out || !iters_out)
+    return TP_ERR_INVALID_ARG;
+  const int cap_wp = std::min(p->max_waypoints > 1 ? p->max_waypoints : 64, PL_MAX_SEG + 1);
+  std::vector<std::vector<double>> path((size_t)B), coef((size_t)B), tms((size_t)B);
+  std::vector<int> active;
+  for (int b = 0; b < B; ++b) {
+    path[b].assign(waypoints + 3 * (size_t)wp_offsets[b], waypoints + 3 * (size_t)wp_offsets[b + 1]);
+    valid_out[b] = 0;
+    iters_out[b] = 0;
+    if (wp_offsets[b + 1] - wp_offsets[b] < 2) { valid_out[b] = 1; continue; }   // single-point path (:262-266)
+    if (wp_offsets[b + 1] - wp_offsets[b] > cap_wp) { tp_set_error("path %d has more than %d waypoints", b, cap_wp); return TP_ERR_CAPACITY; }
+    active.push_back(b);
+  }
+  std::vector<int> off;
+  std::vector<double> wp, c, t;
+  std::vector<int> st;
+  std::vector<uint8_t> val, seg;
+  std::vector<int> ns;
+  while (!active.empty()) {
+    const int nb = (int)active.size();
+    off.assign(1, 0);
+    wp.clear();
+    for (int b : active) {
+      wp.insert(wp.end(), path[b].begin(), path[b].end());
+      off.push_back((int)(wp.size() / 3));
+    }
+    const int total = off[nb], nseg = total - nb;
+    c.resize((size_t)24 * nseg); t.resize((size_t)total); st.resize(nb); val.resize(nb); seg.resize(nseg); ns.resize(nb);
+    rc = tp_minsnap_solve_batch(e, p, nb, off.data(), wp.data(), nullptr, c.data(), t.data(), st.data());
+    if (rc != TP_OK) return rc;
+    rc = tp_poly_check_batch(e, p, nb, off.data(), wp.data(), c.data(), t.data(), val.data(), seg.data(), ns.data(), nullptr, nullptr, 0);
+    if (rc != TP_OK) return rc;
+    std::vector<int> next;
+    for (int q = 0; q < nb; ++q) {
+      const int b = active[q];
+      const int K = off[q + 1] - off[q] - 1;
+      coef[b].assign(c.begin() + (size_t)24 * (off[q] - q), c.begin() + (size_t)24 * (off[q] - q) + (size_t)24 * K);
+      tms[b].assign(t.begin() + off[q], t.begin() + off[q + 1]);
+      iters_out[b] += 1;
+      if (st[q] == 0 && val[q]) { valid_out[b] = 1; continue; }
+      if (iters_out[b] > p->max_iter) continue;   // ++countIter; if (countIter > maxIter_) break;  (:302-305)
+      int add = 0;
+      for (int i = 0; i < K; ++i) add += seg[off[q] - q + i];
+      if ((int)path[b].size() / 3 + add > cap_wp) continue;
+      for (int i = K - 1; i >= 0; --i)
+        if (seg[off[q] - q + i]) {
+          double mid[3];
+          for (int a = 0; a < 3; ++a) mid[a] = (path[b][3 * i + a] + path[b][3 * (i + 1) + a]) / 2;
+          path[b].insert(path[b].begin() + 3 * (i + 1), mid, mid + 3);
+        }
+      next.push_back(b);
+    }
+    active.swap(next);
+  }
+  int64_t tot = 0;
+  wp_offsets_out[0] = 0;
+  for (int b = 0; b < B; ++b) {
+    const int64_t n = (int64_t)path[b].size() / 3;
+    if (tot + n > wp_cap) { tp_set_error("tp_polytraj_make_plan_batch: wp_cap too small"); return TP_ERR_CAPACITY; }
+    memcpy(waypoints_out + 3 * tot, path[b].data(), path[b].size() * 8);
+    if (!tms[b].empty()) memcpy(times_out + tot, tms[b].data(), tms[b].size() * 8);
+    if (!coef[b].empty()) memcpy(coef_out + 24 * (tot - b), coef[b].data(), coef[b].size() * 8);
+    tot += n;
+    wp_offsets_out[b + 1] = (int32_t)tot;
+  }
   return TP_OK;
 }
 
