@@ -199,7 +199,7 @@ struct Heap {
 #define TP_FLOOD_TRIGGER 4096       // expansions after which a search checks reachability
 #define TP_FLOOD_TRIGGER_AGAIN 192  // ... once this trajectory has already had an unreachable goal
 #define TP_FLOOD_CAND (32 * 26)
-__device__ int flood_component(const DevMap& map, const VigoConst& C, Worker& W, int heap_size, int si, int sj, int sk,
+__device__ __noinline__ int flood_component(const DevMap& map, const VigoConst& C, Worker& W, int heap_size, int si, int sj, int sk,
                                int ei, int ej, int ek, int k_lo) {
   AStarSmem& S = *W.sm;
   const int lane = W.lane;
@@ -327,7 +327,7 @@ __device__ int flood_component(const DevMap& map, const VigoConst& C, Worker& W,
 // round of global loads (current node, <= 26 neighbour nodes as LDG.128, <= 26 map words, all in
 // flight together); the open-set heap, the per-axis map-index tables and the serial pass's staging
 // live in shared memory; no FP64 division or integer division is on the per-expansion path.
-__device__ int astar_search(const DevMap& map, const VigoConst& C, Worker& W, const D3& start_in, const D3& end_in,
+__device__ __noinline__ int astar_search(const DevMap& map, const VigoConst& C, Worker& W, const D3& start_in, const D3& end_in,
                             int& expansions, int& err) {
   const int lane = W.lane;
   AStarSmem& S = *W.sm;
@@ -621,7 +621,7 @@ __device__ __forceinline__ void st3(double* p, int i, const D3& v) {
 }
 
 // bsplineTraj::shortcutPath (bsplineTraj.h:206-240): path (len points) -> sc; returns its length
-__device__ int shortcut_path(const DevMap& map, const VigoConst& C, const BatchView& bv, const double* path, int len,
+__device__ __noinline__ int shortcut_path(const DevMap& map, const VigoConst& C, const BatchView& bv, const double* path, int len,
                              double* sc, int lane, int& err) {
   int n = 0;
   auto push = [&](const D3& p) {
@@ -661,7 +661,7 @@ __device__ int shortcut_path(const DevMap& map, const VigoConst& C, const BatchV
 __device__ __forceinline__ double angle_between(const D3& a, const D3& b) { return tp_atan2(norm3(cross3(a, b)), dot3(a, b)); }
 
 // bsplineTraj::findGuidePointSemiCircle (bsplineTraj.h:251-304), serial (lane 0)
-__device__ bool find_guide_point(int cpIdx, int segFirst, int segSecond, const double* path, int plen, D3& guide) {
+__device__ __noinline__ bool find_guide_point(int cpIdx, int segFirst, int segSecond, const double* path, int plen, D3& guide) {
   const double PI_const = 3.1415926;  // utils.h:19 (sic)
   const double minAngle = PI_const * 0.0 / 4.0, maxAngle = PI_const * 4.0 / 4.0;
   const int numCp = segSecond - segFirst - 1;
@@ -708,7 +708,7 @@ __device__ bool find_guide_point(int cpIdx, int segFirst, int segSecond, const d
 }
 
 // append one (guide point, direction) pair to control point c of trajectory `st` (lane 0)
-__device__ void append_pair(const DevMap& map, const VigoConst& C, const BatchView& bv, int b, TrajState& st, int c,
+__device__ __noinline__ void append_pair(const DevMap& map, const VigoConst& C, const BatchView& bv, int b, TrajState& st, int c,
                             const D3& gp, const D3& gv) {
   if (st.n_pairs >= C.gcap) {
     st.err |= ERR_PAIR_OVERFLOW;
@@ -728,7 +728,7 @@ __device__ void append_pair(const DevMap& map, const VigoConst& C, const BatchVi
 
 // bsplineTraj::assignGuidePointsSemiCircle (bsplineTraj.cpp:517-571) over the shortcut paths kept
 // in W.sc; serial, lane 0.  npaths may exceed nseg after the merge quirk of pathSearch.
-__device__ void assign_guides(const DevMap& map, const VigoConst& C, const BatchView& bv, int b, TrajState& st,
+__device__ __noinline__ void assign_guides(const DevMap& map, const VigoConst& C, const BatchView& bv, int b, TrajState& st,
                               const Worker& W, const int (*segs)[2], int nseg, int npaths) {
   const double* ctrl = bv.ctrl + 3 * (size_t)st.off;
   D3 guide = d3(0, 0, 0);  // the reference leaves it uninitialised when the search fails (H4)
@@ -754,7 +754,7 @@ __device__ void assign_guides(const DevMap& map, const VigoConst& C, const Batch
 
 // bsplineTraj::findCollisionSeg (bsplineTraj.cpp:403-445).  Lanes evaluate the per-point and
 // per-line map queries (pure), lane 0 replays the serial scan.  hit/line: shared scratch bytes.
-__device__ int find_collision_seg(const DevMap& map, const VigoConst& C, const BatchView& bv, const TrajState& st,
+__device__ __noinline__ int find_collision_seg(const DevMap& map, const VigoConst& C, const BatchView& bv, const TrajState& st,
                                   uint8_t* hit, uint8_t* line, int (*out)[2], int lane, int& err) {
   const double* ctrl = bv.ctrl + 3 * (size_t)st.off;
   const int N = st.N;
@@ -805,7 +805,7 @@ __device__ int find_collision_seg(const DevMap& map, const VigoConst& C, const B
 // bsplineTraj::pathSearch (bsplineTraj.cpp:447-514) + the shortcut of each found path (kept in
 // W.sc[path index]).  segs/nseg are updated in place by the merge quirk (:496-511: after a merge
 // only the merged segments survive).  Returns the number of paths, or -1 when the search fails.
-__device__ int path_search(const DevMap& map, const VigoConst& C, const BatchView& bv, TrajState& st, Worker& W,
+__device__ __noinline__ int path_search(const DevMap& map, const VigoConst& C, const BatchView& bv, TrajState& st, Worker& W,
                            int (*segs)[2], int& nseg, int& err) {
   const double* ctrl = bv.ctrl + 3 * (size_t)st.off;
   const int lane = W.lane;
@@ -880,7 +880,7 @@ __device__ __forceinline__ int find_seg_index(const int (*segs)[2], int n, int i
   return -1;
 }
 // bsplineTraj::isControlPointRequireNewGuide (bsplineTraj.h:417-429)
-__device__ bool cp_requires_new_guide(const VigoConst& C, const BatchView& bv, int b, const TrajState& st, int c) {
+__device__ __noinline__ bool cp_requires_new_guide(const VigoConst& C, const BatchView& bv, int b, const TrajState& st, int c) {
   const D3 cp = ld3(bv.ctrl + 3 * (size_t)st.off, c);
   for (int gi = bv.cp_head[st.off + c]; gi >= 0;) {
     const GuidePair& pr = bv.pairs[(size_t)b * C.gcap + gi];

@@ -312,7 +312,7 @@ __device__ __forceinline__ Worker make_worker(const VigoConst& C, const AStarPoo
 
 // makePlan steps 1-3 (bsplineTraj.cpp:341-352) for trajectory b; `bv.ctrl + 3*st.off` are its control points
 // (global or shared).  Leaves st.status == TS_ACTIVE when the solve goes on.
-__device__ void dev_plan_init(const BatchView& bv, const VigoConst& C, const DevMap& map, TrajState& st, Worker& W,
+__device__ __noinline__ void dev_plan_init(const BatchView& bv, const VigoConst& C, const DevMap& map, TrajState& st, Worker& W,
                               PlanSmem& S, int b, int lane) {
   int err = 0;
   if (st.N < 2 * TP_DEGREE + 1 || st.N > TP_MAX_CTRL) {
@@ -334,7 +334,7 @@ __device__ void dev_plan_init(const BatchView& bv, const VigoConst& C, const Dev
 
 // body of optimizeTrajectory's loop after the collision check (bsplineTraj.cpp:628-679).  Sets st.status to a
 // final value or leaves TS_ACTIVE (another optimize() follows).
-__device__ void dev_plan_step(const BatchView& bv, const VigoConst& C, const DevMap& map, TrajState& st, Worker& W,
+__device__ __noinline__ void dev_plan_step(const BatchView& bv, const VigoConst& C, const DevMap& map, TrajState& st, Worker& W,
                               PlanSmem& S, int b, int lane) {
   int err = 0;
   const int hasCol = st.has_col & 1, hasDyn = (st.has_col >> 1) & 1;
@@ -659,6 +659,18 @@ __global__ void __launch_bounds__(32) k_find_seg(BatchView bv, VigoConst C, DevM
   }
 }
 
+// difficulty proxy for the issue order: number of optimised control points inside inflated obstacles
+__global__ void k_count_colliding(BatchView bv, DevMap map, int* out) {
+  const int b = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= bv.B) return;
+  const int o = bv.off[b], N = bv.off[b + 1] - o;
+  int c = 0;
+  for (int i = TP_DEGREE + lane; i <= N - TP_DEGREE - 1; i += 32)
+    c += dm_inflated(map, bv.ctrl[3 * (size_t)(o + i)], bv.ctrl[3 * (size_t)(o + i) + 1], bv.ctrl[3 * (size_t)(o + i) + 2]) ? 1 : 0;
+  for (int q = 16; q > 0; q >>= 1) c += __shfl_xor_sync(0xffffffffu, c, q);
+  if (lane == 0) out[b] = c;
+}
+
 __global__ void k_collect_results(BatchView bv, tp_vigo_result* out) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= bv.B) return;
@@ -731,8 +743,8 @@ struct tp_engine {
   // A* pools
   AStarPools pools;
   DevBuf pool_nodes, pool_heaps, pool_heapn, pool_paths, pool_sc, pool_sclen, pool_rounds, pool_flags;
-  cudaStream_t class_stream[4] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev_fork = nullptr, ev_stage = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t class_stream[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_stage = nullptr, ev_join[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool stage_busy = false;
   bool solve_attr_set = false;
   int pools_key[8] = {0};
@@ -1165,7 +1177,7 @@ void tp_engine_destroy(tp_engine_t* e) {
   for (DevBuf* b : bufs) b->release();
   if (e->h_counters) cudaFreeHost(e->h_counters);
   if (e->h_stage) cudaFreeHost(e->h_stage);
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 8; ++i) {
     if (e->class_stream[i]) cudaStreamDestroy(e->class_stream[i]);
     if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
   }
@@ -1519,7 +1531,7 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
     CK(cudaFuncSetAttribute(k_solve<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CK(cudaFuncSetAttribute(k_solve<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CK(cudaFuncSetAttribute(k_solve<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 8; ++i) {
       CK(cudaStreamCreateWithFlags(&e->class_stream[i], cudaStreamNonBlocking));
       CK(cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming));
     }
@@ -1527,12 +1539,28 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
     CK(cudaEventCreateWithFlags(&e->ev_stage, cudaEventDisableTiming));
     e->solve_attr_set = true;
   }
-  // ---- issue order: longest trajectory first; size classes so that shared memory per block (hence
-  // resident blocks per SM) follows the trajectory length.  One launch per non-empty class, on
-  // sibling streams so that a class's tail overlaps the next class's start.
-  std::vector<int> order((size_t)B);
+  // ---- issue order.  Size classes (by control-point count) so that shared memory per block — hence resident
+  // blocks per SM — follows the trajectory length; one launch per non-empty class, on sibling streams so that a
+  // class's tail overlaps the next class's start.  Inside a class the likely-hardest trajectories go first: the
+  // number of control points that start inside inflated obstacles predicts the work (re-guide rounds, A* detours)
+  // better than the length does, and a hard trajectory issued late is the batch's tail.
+  std::vector<int> order((size_t)B), ncol((size_t)B);
+  {
+    k_count_colliding<<<(B + 3) / 4, 128, 0, s>>>(bs.bv, e->dmap, e->active[1].as<int>());
+    e->launches += 1;
+    CK(cudaMemcpyAsync(ncol.data(), e->active[1].p, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  static const int class_lim[4] = {TP_MAX_CTRL, 104, 64, 40};   // upper N bound of each class, largest first
+  auto class_of = [&](int b) {
+    const int n = bs.h_off[b + 1] - bs.h_off[b];
+    return n > class_lim[1] ? 0 : (n > class_lim[2] ? 1 : (n > class_lim[3] ? 2 : 3));
+  };
   for (int b = 0; b < B; ++b) order[b] = b;
   std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+    const int cx = class_of(x), cy = class_of(y);
+    if (cx != cy) return cx < cy;
+    if (ncol[x] != ncol[y]) return ncol[x] > ncol[y];
     return (bs.h_off[x + 1] - bs.h_off[x]) > (bs.h_off[y + 1] - bs.h_off[y]);
   });
   if (e->stage_busy) CK(cudaEventSynchronize(e->ev_stage));   // the previous call's copy out of the staging buffer
@@ -1548,15 +1576,34 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
     if (e->scratch_a.ensure((size_t)B * 32) != TP_OK) return TP_ERR_CUDA;
     tl = e->scratch_a.as<long long>();
   }
-  static const int class_lim[4] = {TP_MAX_CTRL, 104, 64, 40};   // upper N bound of each class, largest first
-  int pos = 0, used = 0;
-  for (int c = 0; c < 4 && pos < B; ++c) {
-    const int lo = c + 1 < 4 ? class_lim[c + 1] : 0;   // class c holds lo < N <= class_lim[c]
-    int end_ = pos;
-    while (end_ < B && (bs.h_off[order[end_] + 1] - bs.h_off[order[end_]]) > lo) ++end_;
-    const int cnt_c = end_ - pos;
-    if (cnt_c == 0) continue;
-    const int nmax = bs.h_off[order[pos] + 1] - bs.h_off[order[pos]];
+  // class ranges in `order`, each split into a head (the likely-hardest 1/8, issued before anything else so that the
+  // long solves of the big small-trajectory class do not start late) and a rest
+  struct Launch { int pos, cnt, nmax; };
+  Launch heads[4], rests[4];
+  int nheads = 0, nrests = 0;
+  {
+    int pos = 0;
+    for (int c = 0; c < 4 && pos < B; ++c) {
+      int end_ = pos, nmax = 0;
+      while (end_ < B && class_of(order[end_]) == c) {
+        nmax = std::max(nmax, bs.h_off[order[end_] + 1] - bs.h_off[order[end_]]);
+        ++end_;
+      }
+      const int cnt_c = end_ - pos;
+      if (cnt_c == 0) continue;
+      const int head = cnt_c >= 64 ? cnt_c / 8 : 0;
+      if (head) heads[nheads++] = {pos, head, nmax};
+      rests[nrests++] = {pos + head, cnt_c - head, nmax};
+      pos = end_;
+    }
+  }
+  Launch seq[8];
+  int nseq = 0;
+  for (int i = nheads - 1; i >= 0; --i) seq[nseq++] = heads[i];   // smallest class first: it is the most numerous
+  for (int i = 0; i < nrests; ++i) seq[nseq++] = rests[i];
+  int used = 0;
+  for (int q = 0; q < nseq; ++q) {
+    const int pos = seq[q].pos, cnt_c = seq[q].cnt, nmax = seq[q].nmax;
     const size_t smem = (size_t)solve_layout(nmax, mode, p->lbfgs_m).total * 8;
     if ((int)smem > e->max_smem_optin) {
       tp_set_error("a %d-control-point trajectory needs %zu B of shared memory (> %d B per block)", nmax, smem, e->max_smem_optin);
@@ -1575,7 +1622,6 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
     CK(cudaEventRecord(e->ev_join[used], cs));
     e->launches += 1;
     ++used;
-    pos = end_;
   }
   for (int i = 0; i < used; ++i) CK(cudaStreamWaitEvent(s, e->ev_join[i], 0));
   if (tl) {
