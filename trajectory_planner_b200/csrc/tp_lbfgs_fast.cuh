@@ -339,85 +339,82 @@ __device__ __forceinline__ void vf_gram_update(const VfCtx& V, int slot, int gbu
 __device__ __forceinline__ void vf_gram_shift(const VfCtx& V, int gbuf_new, int tid) {
   const double* O = V.sm + V.L.gram + (size_t)(gbuf_new ^ 1) * VF_GRAM;
   double* G = V.sm + V.L.gram + (size_t)gbuf_new * VF_GRAM;
-  for (int t = tid; t < 2 * (VF_M - 1) * (VF_M - 1); t += TP_LB_THREADS) {
-    const int which = t >= (VF_M - 1) * (VF_M - 1);
-    const int u = which ? t - (VF_M - 1) * (VF_M - 1) : t;
-    const int i = u / (VF_M - 1), a = u - i * (VF_M - 1);
-    const int base = which ? VF_G_YY : VF_G_SY;
-    G[base + (i + 1) * VF_GS + (a + 1)] = O[base + i * VF_GS + a];
+  // both blocks are contiguous [16][17] arrays: cell c = i*17 + a moves to c + 18; walk the 2 x 272-cell range
+  for (int c = tid; c < 2 * VF_M * VF_GS; c += TP_LB_THREADS) {
+    const int cc = c >= VF_M * VF_GS ? c - VF_M * VF_GS : c;
+    const int i = cc / VF_GS, a = cc - i * VF_GS;
+    if (i < VF_M - 1 && a < VF_M - 1) G[c + VF_GS + 1] = O[c];
   }
   if (tid < VF_M - 1) G[VF_G_INV + tid + 1] = O[VF_G_INV + tid];
 }
 
 // Two-loop recursion in coefficient space (lbfgs.hpp:1293-1316) on the age-ordered Gram buffer `G`
-// (age i = the i-th newest pair; entries of pairs not stored yet are zero).  Warp 0; the two
-// triangular recurrences run redundantly in every lane on registers (dependent chain: one multiply
-// + one FMA per step, no shuffles), the dense y_i.(gamma q) product is lane-parallel.
+// (age i = the i-th newest pair; entries of pairs not stored yet are zero).  One warp, lane i <-> pair of age i.
+// Both triangular recurrences are ROLLED loops (the SM's instruction cache, not its pipes, is what the
+// fused kernel runs out of — profiles/r01c): per step the finished value is broadcast through shared
+// memory and every lane applies one FMA to its own running sum.
 // `newest` = slot of the newest pair, gg = g.g.  Writes ca[slot], cb[slot] (coefficients of
 // s_slot, y_slot), sc[0] = coefficient of g, sc[1] = g.d (the line search's dginit).
-__device__ __forceinline__ void vf_coeffs(const VfCtx& V, double* G, int newest, int bound, double gg, int lane) {
+__device__ __noinline__ void vf_coeffs(const VfCtx& V, double* G, int newest, int bound, double gg, int lane) {
   const double* SY = G + VF_G_SY;
   const double* YY = G + VF_G_YY;
-  const double* Sg = G + VF_G_SG;
-  const double* Yg = G + VF_G_YG;
-  double* tb = G + VF_G_TB;
+  double* tb = G + VF_G_TB;          // broadcast scratch (16 doubles)
   double* ca = V.sm + V.L.ca;
   double* cb = V.sm + V.L.cb;
   double* sc = V.sm + V.L.sc;
   const unsigned FULL = 0xffffffffu;
+  const int i = lane & (VF_M - 1);
   // 1/ys and 1/yy of the newest pair (two lanes divide concurrently)
   const double dd = lane == 0 ? SY[0] : YY[0];
   const double rc = 1.0 / dd;
   const double inv0 = __shfl_sync(FULL, rc, 0);
   const double gamma = SY[0] * __shfl_sync(FULL, rc, 1);   // ys/yy (lbfgs.hpp:1305)
   if (lane == 0) G[VF_G_INV] = inv0;
-  double inv[VF_M], al[VF_M], r[VF_M];
-  inv[0] = inv0;
-#pragma unroll
-  for (int a = 1; a < VF_M; ++a) inv[a] = G[VF_G_INV + a];
-#pragma unroll
-  for (int i = 0; i < VF_M; ++i) r[i] = -Sg[i];
+  const double inv_i = i == 0 ? inv0 : G[VF_G_INV + i];     // 0 for pairs not stored yet
+  const double sg_i = G[VF_G_SG + i], yg_i = G[VF_G_YG + i];
   // ---- first loop, newest -> oldest: alpha_a = (s_a.q)/ys_a; q -= alpha_a y_a  (q starts at -g); r_i = s_i.q
-#pragma unroll
-  for (int a = 0; a < VF_M; ++a) {
-    al[a] = r[a] * inv[a];
-#pragma unroll
-    for (int i = a + 1; i < VF_M; ++i) r[i] = fma(-al[a], SY[i * VF_GS + a], r[i]);
+  double r = -sg_i;
+  double al = 0.0;
+  for (int a = 0; a < bound; ++a) {
+    if (lane == a) { al = r * inv_i; tb[0] = al; }
+    __syncwarp();
+    const double ala = tb[0];
+    if (i > a) r = fma(-ala, SY[i * VF_GS + a], r);
+    __syncwarp();
   }
-  // ---- t_i = y_i.(gamma q) = -gamma (y_i.g + sum_a alpha_a y_i.y_a), lane i < 16
-  {
-    const int i = lane & (VF_M - 1);
-    double t0 = Yg[i], t1 = 0.0;
-#pragma unroll
-    for (int a = 0; a < VF_M; a += 2) {
-      t0 = fma(al[a], YY[i * VF_GS + a], t0);
-      t1 = fma(al[a + 1], YY[i * VF_GS + a + 1], t1);
-    }
-    if (lane < VF_M) tb[i] = -gamma * (t0 + t1);
-  }
+  // ---- acc_i = y_i.(gamma q) = -gamma (y_i.g + sum_a alpha_a y_i.y_a)
+  if (lane < VF_M) tb[i] = al;
   __syncwarp();
-  double acc[VF_M];
-#pragma unroll
-  for (int i = 0; i < VF_M; ++i) acc[i] = tb[i];
-  // ---- second loop, oldest -> newest: beta_j = (y_j.d)/ys_j; d += (alpha_j - beta_j) s_j; acc_i = y_i.d
-  double part0 = 0.0, part1 = 0.0;
-#pragma unroll
-  for (int j = VF_M - 1; j >= 0; --j) {
-    const double aa = fma(-acc[j], inv[j], al[j]);
-#pragma unroll
-    for (int i = 0; i < j; ++i) acc[i] = fma(aa, SY[j * VF_GS + i], acc[i]);
-    const double bb = -gamma * al[j];
-    part0 = fma(aa, Sg[j], part0);
-    part1 = fma(bb, Yg[j], part1);
-    if (lane == 0 && j < bound) {
-      const int sj = (newest - j) & (VF_M - 1);
-      ca[sj] = aa;
-      cb[sj] = bb;
-    }
+  double t0 = yg_i, t1 = 0.0;
+  for (int a = 0; a < bound; a += 2) {
+    t0 = fma(tb[a], YY[i * VF_GS + a], t0);
+    t1 = fma(tb[a + 1], YY[i * VF_GS + a + 1], t1);   // tb / YY of a pair not stored yet are zero
   }
+  double acc = -gamma * (t0 + t1);
+  __syncwarp();
+  // ---- second loop, oldest -> newest: beta_j = (y_j.d)/ys_j; d += (alpha_j - beta_j) s_j; acc_i = y_i.d
+  double aa = 0.0;
+  for (int j = bound - 1; j >= 0; --j) {
+    if (lane == j) { aa = fma(-acc, inv_i, al); tb[0] = aa; }
+    __syncwarp();
+    const double aj = tb[0];
+    if (i < j) acc = fma(aj, SY[j * VF_GS + i], acc);
+    __syncwarp();
+  }
+  const bool mine = lane < VF_M && i < bound;
+  const double bb = -gamma * al;
+  if (mine) {
+    const int si = (newest - i) & (VF_M - 1);
+    ca[si] = aa;
+    cb[si] = bb;
+  }
+  // g.d = sum aa_i s_i.g + sum b_i y_i.g - gamma g.g
+  double part = mine ? fma(aa, sg_i, bb * yg_i) : 0.0;
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
   if (lane == 0) {
     sc[0] = -gamma;
-    sc[1] = (part0 + part1) - gamma * gg;   // g.d = sum aa_i s_i.g + sum b_i y_i.g - gamma g.g
+    sc[1] = part - gamma * gg;
   }
 }
 
@@ -580,9 +577,14 @@ __device__ void lbfgs_run_fast(const VigoConst& C, VfCtx& V, tp_lbfgs_result& ou
       dginit_next = sc[1];
       VF_OWNED(i) {
         double a0 = cg * g[i], a1 = 0.0;
+        const double* sp = S + i;
+        const double* yp = Y + i;
+#pragma unroll 4
         for (int j = 0; j < bound; ++j) {
-          a0 += ca[j] * S[(size_t)j * ns + i];
-          a1 += cb[j] * Y[(size_t)j * ns + i];
+          a0 = fma(ca[j], sp[0], a0);
+          a1 = fma(cb[j], yp[0], a1);
+          sp += ns;
+          yp += ns;
         }
         d[i] = a0 + a1;
       }
