@@ -54,6 +54,7 @@ __global__ void k_init_states(BatchView bv, VigoConst C) {
   st.err = 0;
   st.lbfgs_runs = st.lbfgs_iters = st.lbfgs_evals = st.last_ret = 0;
   st.astar_searches = st.astar_expansions = 0;
+  st.astar_unreach = 0;
   st.vclock = 0;
   st.w_dist = C.p.w_distance;
   st.w_dyn = C.p.w_dyn;
@@ -486,12 +487,10 @@ __host__ __device__ inline SolveLayout solve_layout(int N, int mode, int m) {
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(TP_LB_THREADS, 4) k_solve(BatchView bv, VigoConst C, DevMap map, AStarPools P,
-                                                            const int* __restrict__ order, int class_max_n,
-                                                            int* slot_flags, double* counters, long long* timeline) {
-  extern __shared__ double sm[];
+__device__ __forceinline__ void solve_one(const BatchView& bv, const VigoConst& C, const DevMap& map, const AStarPools& P,
+                                          int b, int class_max_n, int s_slot, int sw, double* counters,
+                                          long long* timeline, int resume, int rounds_this_pass, double* sm) {
   const int tid = threadIdx.x, lane = tid & 31;
-  const int b = order[blockIdx.x];
   long long t_start = 0;
   if (timeline && tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start));
   const SolveLayout SL = solve_layout(class_max_n, MODE, C.p.lbfgs_m);
@@ -508,30 +507,23 @@ __global__ void __launch_bounds__(TP_LB_THREADS, 4) k_solve(BatchView bv, VigoCo
   const int N = st.N, n = 3 * (N - 2 * TP_DEGREE);
   double* gctrl = bv.ctrl + 3 * (size_t)st.off;
   for (int e = tid; e < 3 * N; e += TP_LB_THREADS) cp[e] = gctrl[e];
-  // ---- claim an A* node pool (one per resident block) and a serial-warp role.  Warp w of every block lives on
-  // SM sub-partition w, so the blocks sharing an SM take DIFFERENT warps for their serial phases (A*, guide
-  // points, the coefficient solve): a per-SM ticket rotates the role.
-  if (tid == 0) {
-    const int W_ = P.workers;
-    int sidx = (int)(((unsigned)blockIdx.x * 2654435761u) % (unsigned)W_);
-    while (atomicCAS(&slot_flags[sidx], 0, 1) != 0) sidx = sidx + 1 == W_ ? 0 : sidx + 1;
-    unsigned smid;
-    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
-    const int ticket = atomicAdd(&slot_flags[W_ + (int)(smid & 255u)], 1);
-    st.pad = sidx | ((ticket & (TP_LB_WARPS - 1)) << 24);
-  }
   __syncthreads();
-  const int s_slot = st.pad & 0xFFFFFF;
-  const int sw = (st.pad >> 24) & (TP_LB_WARPS - 1);
   const bool is_serial_warp = (tid >> 5) == sw;
   BatchView lbv = bv;                      // the outer-loop code reads control points through bv.ctrl + 3*off
   lbv.ctrl = cp - 3 * (size_t)st.off;
   Worker W = make_worker(C, P, s_slot, lane, &PS.as);
-  // ---- makePlan steps 1-3
-  if (is_serial_warp) dev_plan_init(lbv, C, map, st, W, PS, b, lane);
+  // ---- makePlan steps 1-3 (first pass only; a resumed trajectory continues its optimise / check / re-guide loop:
+  // every optimize() starts from a fresh L-BFGS state, so splitting a solve at a round boundary changes nothing)
+  if (!resume) {
+    if (is_serial_warp) dev_plan_init(lbv, C, map, st, W, PS, b, lane);
+  } else if (st.astar_unreach) {
+    W.flood_trigger = TP_FLOOD_TRIGGER_AGAIN;
+  }
   __syncthreads();
   double fl = 0.0, its = 0.0, evs = 0.0, smp = 0.0;
-  while (st.status == TS_ACTIVE) {
+  int rounds_done = 0;
+  while (st.status == TS_ACTIVE && rounds_done < rounds_this_pass) {
+    ++rounds_done;
     // ---- optimize()
     tp_lbfgs_result r;
     if (n <= 0) {
@@ -576,7 +568,10 @@ __global__ void __launch_bounds__(TP_LB_THREADS, 4) k_solve(BatchView bv, VigoCo
     }
     __syncthreads();
     // ---- loop body: success / failure / re-guide / weight doubling
-    if (is_serial_warp) dev_plan_step(lbv, C, map, st, W, PS, b, lane);
+    if (is_serial_warp) {
+      dev_plan_step(lbv, C, map, st, W, PS, b, lane);
+      if (lane == 0 && W.goal_unreachable) st.astar_unreach = 1;
+    }
     __syncthreads();
   }
   // ---- linearFeasibilityReparam
@@ -602,18 +597,67 @@ __global__ void __launch_bounds__(TP_LB_THREADS, 4) k_solve(BatchView bv, VigoCo
       atomicAdd(&counters[2], evs);
       atomicAdd(&counters[3], smp);
     }
-    __threadfence();
-    atomicExch(&slot_flags[s_slot], 0);
     if (timeline) {   // development aid (TP_TIMELINE): start / end time [ns], SM id, iterations of every block
       long long t_end;
       unsigned smid;
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_end));
       asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
-      timeline[4 * (size_t)b] = t_start;
+      if (!resume) timeline[4 * (size_t)b] = t_start;
       timeline[4 * (size_t)b + 1] = t_end;
       timeline[4 * (size_t)b + 2] = (long long)smid;
       timeline[4 * (size_t)b + 3] = (long long)st.lbfgs_iters | ((long long)st.astar_expansions << 32);
     }
+  }
+  __syncthreads();
+}
+
+// Persistent workers: one launch per size class; a worker of class c owns shared memory for that class's longest
+// trajectory and serves its own class first, then STEALS from the classes of shorter trajectories (they fit), so
+// every worker stays busy until the whole batch is drained.  Each class's list is ordered hardest-first.
+// cls_begin[5]: ranges of `order` per class (largest trajectories = class 0); cls_next[4]: atomic cursors.
+template <int MODE>
+__global__ void __launch_bounds__(TP_LB_THREADS, 4) k_solve(BatchView bv, VigoConst C, DevMap map, AStarPools P,
+                                                            const int* __restrict__ order, const int* __restrict__ cls_begin,
+                                                            int* cls_next, int my_class, int class_max_n,
+                                                            int* slot_flags, double* counters, long long* timeline,
+                                                            int resume, int rounds_this_pass) {
+  extern __shared__ double sm[];
+  const int tid = threadIdx.x;
+  const SolveLayout SL = solve_layout(class_max_n, MODE, C.p.lbfgs_m);
+  int* pick = reinterpret_cast<int*>(sm + SL.total);   // 2 ints past the layout (the launch reserves them)
+  // ---- claim an A* node pool (one per resident worker) and a serial-warp role.  Warp w of every block lives on SM
+  // sub-partition w, so the workers sharing an SM take DIFFERENT warps for their serial phases (A*, guide points, the
+  // coefficient recurrences): a per-SM ticket rotates the role.
+  if (tid == 0) {
+    const int W_ = P.workers;
+    int sidx = (int)(((unsigned)(blockIdx.x + 977 * my_class) * 2654435761u) % (unsigned)W_);
+    while (atomicCAS(&slot_flags[sidx], 0, 1) != 0) sidx = sidx + 1 == W_ ? 0 : sidx + 1;
+    unsigned smid;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    const int ticket = atomicAdd(&slot_flags[W_ + (int)(smid & 255u)], 1);
+    pick[1] = sidx | ((ticket & (TP_LB_WARPS - 1)) << 24);
+  }
+  __syncthreads();
+  const int s_slot = pick[1] & 0xFFFFFF;
+  const int sw = (pick[1] >> 24) & (TP_LB_WARPS - 1);
+  for (;;) {
+    if (tid == 0) {
+      int b = -1;
+      for (int c = my_class; c < 4 && b < 0; ++c) {
+        if (cls_begin[c + 1] == cls_begin[c]) continue;
+        const int i = cls_begin[c] + atomicAdd(&cls_next[c], 1);
+        if (i < cls_begin[c + 1]) b = order[i];
+      }
+      pick[0] = b;
+    }
+    __syncthreads();
+    const int b = pick[0];
+    if (b < 0) break;
+    solve_one<MODE>(bv, C, map, P, b, class_max_n, s_slot, sw, counters, timeline, resume, rounds_this_pass, sm);
+  }
+  if (tid == 0) {
+    __threadfence();
+    atomicExch(&slot_flags[s_slot], 0);
   }
 }
 
@@ -669,6 +713,14 @@ __global__ void k_count_colliding(BatchView bv, DevMap map, int* out) {
     c += dm_inflated(map, bv.ctrl[3 * (size_t)(o + i)], bv.ctrl[3 * (size_t)(o + i) + 1], bv.ctrl[3 * (size_t)(o + i) + 2]) ? 1 : 0;
   for (int q = 16; q > 0; q >>= 1) c += __shfl_xor_sync(0xffffffffu, c, q);
   if (lane == 0) out[b] = c;
+}
+
+// difficulty key after the first round (see tp_vigo_make_plan_batch): -1 when the trajectory is finished
+__global__ void k_difficulty(BatchView bv, int* out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= bv.B) return;
+  const TrajState& st = bv.st[b];
+  out[b] = st.status == TS_ACTIVE ? st.lbfgs_iters + (3 * st.astar_expansions) / 10 + 5 * st.n_pairs : -1;
 }
 
 __global__ void k_collect_results(BatchView bv, tp_vigo_result* out) {
@@ -1541,89 +1593,150 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
   }
   // ---- issue order.  Size classes (by control-point count) so that shared memory per block — hence resident
   // blocks per SM — follows the trajectory length; one launch per non-empty class, on sibling streams so that a
-  // class's tail overlaps the next class's start.  Inside a class the likely-hardest trajectories go first: the
-  // number of control points that start inside inflated obstacles predicts the work (re-guide rounds, A* detours)
-  // better than the length does, and a hard trajectory issued late is the batch's tail.
-  std::vector<int> order((size_t)B), ncol((size_t)B);
-  {
-    k_count_colliding<<<(B + 3) / 4, 128, 0, s>>>(bs.bv, e->dmap, e->active[1].as<int>());
-    e->launches += 1;
-    CK(cudaMemcpyAsync(ncol.data(), e->active[1].p, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-  }
+  // class's tail overlaps the next class's start.  A hard trajectory issued late is the batch's tail, and how hard
+  // a trajectory is shows after its first round: the solve therefore runs in TWO PASSES of the same kernel.
+  //   pass 1: every trajectory through makePlan steps 1-3 and the first optimise / check / re-guide round, ordered
+  //           inside a class by the number of control points that start inside inflated obstacles;
+  //   pass 2: the trajectories still colliding (~60 %), ordered by first-round work (L-BFGS iterations, A*
+  //           expansions, guide pairs: correlation 0.86 with the remaining time), hardest first.
+  // Every optimize() starts from a fresh L-BFGS state, so cutting a solve at a round boundary changes no result.
   static const int class_lim[4] = {TP_MAX_CTRL, 104, 64, 40};   // upper N bound of each class, largest first
   auto class_of = [&](int b) {
     const int n = bs.h_off[b + 1] - bs.h_off[b];
     return n > class_lim[1] ? 0 : (n > class_lim[2] ? 1 : (n > class_lim[3] ? 2 : 3));
   };
-  for (int b = 0; b < B; ++b) order[b] = b;
-  std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
-    const int cx = class_of(x), cy = class_of(y);
-    if (cx != cy) return cx < cy;
-    if (ncol[x] != ncol[y]) return ncol[x] > ncol[y];
-    return (bs.h_off[x + 1] - bs.h_off[x]) > (bs.h_off[y + 1] - bs.h_off[y]);
-  });
-  if (e->stage_busy) CK(cudaEventSynchronize(e->ev_stage));   // the previous call's copy out of the staging buffer
-  if (ensure_stage(e, (size_t)B * 4) != TP_OK) return TP_ERR_CUDA;
-  memcpy(e->h_stage, order.data(), (size_t)B * 4);
-  CK(cudaMemcpyAsync(e->active[0].p, e->h_stage, (size_t)B * 4, cudaMemcpyHostToDevice, s));
-  CK(cudaEventRecord(e->ev_stage, s));
-  e->stage_busy = true;
-  CK(cudaEventRecord(e->ev_fork, s));
   long long* tl = nullptr;
   const char* tl_path = getenv("TP_TIMELINE");
   if (tl_path) {
     if (e->scratch_a.ensure((size_t)B * 32) != TP_OK) return TP_ERR_CUDA;
     tl = e->scratch_a.as<long long>();
   }
-  // class ranges in `order`, each split into a head (the likely-hardest 1/8, issued before anything else so that the
-  // long solves of the big small-trajectory class do not start late) and a rest
-  struct Launch { int pos, cnt, nmax; };
-  Launch heads[4], rests[4];
-  int nheads = 0, nrests = 0;
-  {
-    int pos = 0;
-    for (int c = 0; c < 4 && pos < B; ++c) {
-      int end_ = pos, nmax = 0;
-      while (end_ < B && class_of(order[end_]) == c) {
-        nmax = std::max(nmax, bs.h_off[order[end_] + 1] - bs.h_off[order[end_]]);
-        ++end_;
+  std::vector<int> key((size_t)B), ids;
+  // one pass: sort `ids` by (class, key desc, N desc), upload, launch per class (hardest eighth of each class first)
+  auto run_pass = [&](int resume, int rounds) -> int {
+    std::stable_sort(ids.begin(), ids.end(), [&](int x, int y) {
+      const int cx = class_of(x), cy = class_of(y);
+      if (cx != cy) return cx < cy;
+      if (key[x] != key[y]) return key[x] > key[y];
+      return (bs.h_off[x + 1] - bs.h_off[x]) > (bs.h_off[y + 1] - bs.h_off[y]);
+    });
+    const int M = (int)ids.size();
+    if (M == 0) return TP_OK;
+    // class ranges + work estimates
+    int cb[5] = {0, 0, 0, 0, 0}, nmax[4] = {0, 0, 0, 0};
+    double work[4] = {0, 0, 0, 0};
+    for (int i = 0; i < M; ++i) {
+      const int c = class_of(ids[i]), n = bs.h_off[ids[i] + 1] - bs.h_off[ids[i]];
+      cb[c + 1] += 1;
+      nmax[c] = std::max(nmax[c], n);
+      work[c] += (double)n * (1.0 + 0.05 * std::max(key[ids[i]], 0));
+    }
+    for (int c = 0; c < 4; ++c) cb[c + 1] += cb[c];
+    size_t smem[4] = {0, 0, 0, 0};
+    for (int c = 0; c < 4; ++c)
+      if (nmax[c] > 0) {
+        smem[c] = (size_t)solve_layout(nmax[c], mode, p->lbfgs_m).total * 8 + 16;
+        if ((int)smem[c] > e->max_smem_optin) {
+          tp_set_error("a %d-control-point trajectory needs %zu B of shared memory (> %d B per block)", nmax[c], smem[c], e->max_smem_optin);
+          return TP_ERR_CAPACITY;
+        }
       }
-      const int cnt_c = end_ - pos;
-      if (cnt_c == 0) continue;
-      const int head = cnt_c >= 64 ? cnt_c / 8 : 0;
-      if (head) heads[nheads++] = {pos, head, nmax};
-      rests[nrests++] = {pos + head, cnt_c - head, nmax};
-      pos = end_;
+    // worker mix per SM: a[c] persistent workers of class c (a worker serves its class and every class of shorter
+    // trajectories); at most 4 workers (registers), shared memory permitting; minimise the estimated makespan
+    // T = max_c (work of classes 0..c) / (workers of classes 0..c)
+    int best[4] = {0, 0, 0, 0};
+    double bestT = 1e300;
+    int bestN = 0;
+    const size_t smem_sm = 227 * 1024;
+    int a[4];
+    for (a[0] = 0; a[0] <= 4; ++a[0])
+      for (a[1] = 0; a[0] + a[1] <= 4; ++a[1])
+        for (a[2] = 0; a[0] + a[1] + a[2] <= 4; ++a[2])
+          for (a[3] = 0; a[0] + a[1] + a[2] + a[3] <= 4; ++a[3]) {
+            size_t used_sm = 0;
+            bool ok = true;
+            for (int c = 0; c < 4; ++c) {
+              if (a[c] > 0 && nmax[c] == 0) ok = false;
+              used_sm += (size_t)a[c] * (smem[c] + 1024);
+            }
+            if (!ok || used_sm > smem_sm) continue;
+            double T = 0, wsum = 0;
+            int nsum = 0;
+            for (int c = 0; c < 4; ++c) {
+              wsum += work[c];
+              nsum += a[c];
+              if (work[c] > 0) {
+                if (nsum == 0) { ok = false; break; }
+                T = std::max(T, wsum / nsum);
+              }
+            }
+            if (!ok || nsum == 0) continue;
+            if (T < bestT * 0.999 || (T < bestT * 1.001 && nsum > bestN)) {
+              bestT = T;
+              bestN = nsum;
+              for (int c = 0; c < 4; ++c) best[c] = a[c];
+            }
+          }
+    if (bestN == 0) { tp_set_error("no feasible worker mix"); return TP_ERR_CAPACITY; }
+    if (e->stage_busy) CK(cudaEventSynchronize(e->ev_stage));   // the previous copy out of the staging buffer
+    if (ensure_stage(e, (size_t)M * 4 + 64) != TP_OK) return TP_ERR_CUDA;
+    memcpy(e->h_stage, ids.data(), (size_t)M * 4);
+    int* h_cb = reinterpret_cast<int*>(static_cast<char*>(e->h_stage) + (size_t)M * 4);
+    for (int c = 0; c < 5; ++c) h_cb[c] = cb[c];
+    for (int c = 0; c < 4; ++c) h_cb[5 + c] = 0;
+    int* d_cb = e->counters.as<int>() + 16;   // [16..20] class ranges, [21..24] cursors
+    CK(cudaMemcpyAsync(e->active[0].p, e->h_stage, (size_t)M * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_cb, h_cb, 9 * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(e->ev_stage, s));
+    e->stage_busy = true;
+    CK(cudaEventRecord(e->ev_fork, s));
+    int used = 0;
+    for (int c = 0; c < 4; ++c) {
+      if (best[c] == 0) continue;
+      // no more workers than trajectories this class (and the ones it can steal) can feed
+      const int feed = cb[4] - cb[c];
+      const int grid = std::min(best[c] * e->sm_count, std::max(feed, 1));
+      cudaStream_t cs = e->class_stream[used];
+      CK(cudaStreamWaitEvent(cs, e->ev_fork, 0));
+      {
+        ProfScope ps(e, 0, cs, grid);
+        const int* ord = e->active[0].as<int>();
+        if (mode == 1) k_solve<1><<<grid, TP_LB_THREADS, smem[c], cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, d_cb, d_cb + 5, c, nmax[c], e->pool_flags.as<int>(), e->counters_ptr(), tl, resume, rounds);
+        else if (mode == 2) k_solve<2><<<grid, TP_LB_THREADS, smem[c], cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, d_cb, d_cb + 5, c, nmax[c], e->pool_flags.as<int>(), e->counters_ptr(), tl, resume, rounds);
+        else k_solve<0><<<grid, TP_LB_THREADS, smem[c], cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, d_cb, d_cb + 5, c, nmax[c], e->pool_flags.as<int>(), e->counters_ptr(), tl, resume, rounds);
+      }
+      CK(cudaGetLastError());
+      CK(cudaEventRecord(e->ev_join[used], cs));
+      e->launches += 1;
+      ++used;
     }
-  }
-  Launch seq[8];
-  int nseq = 0;
-  for (int i = nheads - 1; i >= 0; --i) seq[nseq++] = heads[i];   // smallest class first: it is the most numerous
-  for (int i = 0; i < nrests; ++i) seq[nseq++] = rests[i];
-  int used = 0;
-  for (int q = 0; q < nseq; ++q) {
-    const int pos = seq[q].pos, cnt_c = seq[q].cnt, nmax = seq[q].nmax;
-    const size_t smem = (size_t)solve_layout(nmax, mode, p->lbfgs_m).total * 8;
-    if ((int)smem > e->max_smem_optin) {
-      tp_set_error("a %d-control-point trajectory needs %zu B of shared memory (> %d B per block)", nmax, smem, e->max_smem_optin);
-      return TP_ERR_CAPACITY;
-    }
-    cudaStream_t cs = e->class_stream[used];
-    CK(cudaStreamWaitEvent(cs, e->ev_fork, 0));
-    {
-      ProfScope ps(e, 0, cs, cnt_c);
-      const int* ord = e->active[0].as<int>() + pos;
-      if (mode == 1) k_solve<1><<<cnt_c, TP_LB_THREADS, smem, cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, nmax, e->pool_flags.as<int>(), e->counters_ptr(), tl);
-      else if (mode == 2) k_solve<2><<<cnt_c, TP_LB_THREADS, smem, cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, nmax, e->pool_flags.as<int>(), e->counters_ptr(), tl);
-      else k_solve<0><<<cnt_c, TP_LB_THREADS, smem, cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, nmax, e->pool_flags.as<int>(), e->counters_ptr(), tl);
-    }
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(e->ev_join[used], cs));
+    for (int i = 0; i < used; ++i) CK(cudaStreamWaitEvent(s, e->ev_join[i], 0));
+    if (getenv("TP_PROF_DUMP")) fprintf(stderr, "[tp-mix] workers/SM by class: %d %d %d %d (smem %zu %zu %zu %zu B), class sizes %d %d %d %d\n",
+                                        best[0], best[1], best[2], best[3], smem[0], smem[1], smem[2], smem[3], cb[1] - cb[0], cb[2] - cb[1],
+                                        cb[3] - cb[2], cb[4] - cb[3]);
+    return TP_OK;
+  };
+  const bool two_pass = getenv("TP_TWO_PASS") != nullptr && B >= 256;
+  // pass 1 (or the only pass for small batches)
+  k_count_colliding<<<(B + 3) / 4, 128, 0, s>>>(bs.bv, e->dmap, e->active[1].as<int>());
+  e->launches += 1;
+  CK(cudaMemcpyAsync(key.data(), e->active[1].p, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  ids.resize((size_t)B);
+  for (int b = 0; b < B; ++b) ids[b] = b;
+  rc = run_pass(0, two_pass ? 1 : 0x7fffffff);
+  if (rc != TP_OK) return rc;
+  if (two_pass) {
+    k_difficulty<<<(B + 127) / 128, 128, 0, s>>>(bs.bv, e->active[1].as<int>());
     e->launches += 1;
-    ++used;
+    CK(cudaMemcpyAsync(key.data(), e->active[1].p, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    ids.clear();
+    for (int b = 0; b < B; ++b)
+      if (key[b] >= 0) ids.push_back(b);
+    rc = run_pass(1, 0x7fffffff);
+    if (rc != TP_OK) return rc;
   }
-  for (int i = 0; i < used; ++i) CK(cudaStreamWaitEvent(s, e->ev_join[i], 0));
   if (tl) {
     std::vector<long long> h((size_t)B * 4);
     CK(cudaMemcpyAsync(h.data(), tl, (size_t)B * 32, cudaMemcpyDeviceToHost, s));

@@ -35,6 +35,8 @@ struct TrajState {
   int lbfgs_runs, lbfgs_iters, lbfgs_evals, last_ret;
   int astar_searches, astar_expansions;
   int pad;
+  int astar_unreach;        // a search of this trajectory proved its goal unreachable (later searches check early)
+  int pad2;
   long long vclock;         // virtual clock (tp_vigo_params::vclock_budget)
   double w_dist, w_dyn;     // weightDistance_, weightDynamicObstacle_ (mutated by the outer loop)
   double final_cost, linear_factor;
