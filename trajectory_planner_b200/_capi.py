@@ -8,7 +8,7 @@ import subprocess
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libtp_b200.so")
+LIB_PATH = os.environ.get("TP_B200_LIB") or os.path.join(PKG_DIR, "libtp_b200.so")   # TP_B200_LIB: development builds (timing probes)
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 
 _dp = C.POINTER(C.c_double)

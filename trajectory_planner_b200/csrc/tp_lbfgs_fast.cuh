@@ -36,19 +36,35 @@
 #define VF_G_TB (VF_G_INV + VF_M)
 #define VF_GRAM (VF_G_TB + VF_M)
 
+// History in TENSOR MEMORY (tm layout): the 2 x 16 history values of a vector element are only ever combined with
+// other values of the SAME element (Gram products, direction), so every thread keeps the history of the elements it
+// owns in its own TMEM lane: element q of thread t = columns [64 q, 64 q + 64) of lane t (16 s then 16 y doubles, by
+// slot).  VF_TM_Q elements per thread fit the block's VF_TM_COLS columns (4 blocks x 128 = the SM's 512 columns);
+// the elements beyond 128 * VF_TM_Q keep their history columns in shared memory ("overflow").
+#define VF_TM_COLS 128
+#define VF_TM_Q 2
+#define VF_TM_ELEMS (VF_TM_Q * TP_LB_THREADS)
+
 struct VfLayout {  // offsets in doubles from the start of dynamic shared memory
-  int ns;          // padded history row stride, ns % 16 == 4 (conflict-free MMA fragment loads)
-  int cp, g, xp, gp, d, S, Y, gram, ca, cb, sc, red, pair, pstart, total;
+  int ns;          // smem layout: padded history row stride, ns % 16 == 4 (conflict-free MMA fragment loads);
+                   // tm layout: row stride of the overflow history (elements e >= VF_TM_ELEMS), 0 if none
+  int cp, g, xp, gp, d, S, Y, gram, ca, cb, sc, red, gred, pair, pstart, total;
 };
-__host__ __device__ inline VfLayout vf_layout(int N) {
+__host__ __device__ inline VfLayout vf_layout(int N, bool tm = false) {
   VfLayout L;
   const int n = 3 * (N - 2 * TP_DEGREE);
   const int nn = n > 0 ? n : 0;
   int ns = (nn + 15) / 16 * 16 + 4;
+  int gs = ns;
+  if (tm) {
+    const int novf = nn + 3 * TP_DEGREE - VF_TM_ELEMS;
+    ns = novf > 0 ? novf + (novf & 1) : 0;
+    gs = nn + (nn & 1);
+  }
   L.ns = ns;
   int o = 0;
   L.cp = o; o += 3 * N + (N & 1);
-  L.g = o; o += ns;
+  L.g = o; o += gs;
   L.xp = o; o += nn + (nn & 1);
   L.gp = o; o += nn + (nn & 1);
   L.d = o; o += nn + (nn & 1);
@@ -59,12 +75,13 @@ __host__ __device__ inline VfLayout vf_layout(int N) {
   L.cb = o; o += VF_M;
   L.sc = o; o += 8;
   L.red = o; o += 2 * TP_LB_WARPS * 4;
+  L.gred = o; o += tm ? TP_LB_WARPS * (2 * VF_M + 2) : 0;   // per-warp partial Gram sums (tm layout)
   L.pair = o; o += VF_PAIRS_SM * 7;
   L.pstart = o; o += (N + 2 + 1) / 2;   // (N + 1) ints
   L.total = o;
   return L;
 }
-__host__ __device__ inline size_t vf_smem_bytes(int N) { return (size_t)vf_layout(N).total * 8; }
+__host__ __device__ inline size_t vf_smem_bytes(int N, bool tm = false) { return (size_t)vf_layout(N, tm).total * 8; }
 
 struct VfCtx {
   int N, n;
@@ -74,6 +91,7 @@ struct VfCtx {
   const int* head;          // global per-control-point list heads
   int n_pairs;
   int serial_warp;     // which warp runs the serial coefficient phase (rotated per block: warp w lives on SM sub-partition w)
+  uint32_t tbase;      // tm layout: TMEM address of this block's columns (lane 0)
   bool pairs_in_sm;
   double w_dist, w_dyn;
   int n_dyn;
@@ -372,15 +390,16 @@ __device__ __noinline__ void vf_coeffs(const VfCtx& V, double* G, int newest, in
   if (lane == 0) G[VF_G_INV] = inv0;
   const double inv_i = i == 0 ? inv0 : G[VF_G_INV + i];     // 0 for pairs not stored yet
   const double sg_i = G[VF_G_SG + i], yg_i = G[VF_G_YG + i];
-  // ---- first loop, newest -> oldest: alpha_a = (s_a.q)/ys_a; q -= alpha_a y_a  (q starts at -g); r_i = s_i.q
-  double r = -sg_i;
+  // Both recurrences run on ROW-SCALED quantities (r_i / ys_i, (y_i.d) / ys_i) so that the value a step broadcasts is
+  // a lane's running value itself: per step one register shuffle + one FMA on the dependent chain.
+  // ---- first loop, newest -> oldest: alpha_a = (s_a.q)/ys_a; q -= alpha_a y_a  (q starts at -g)
+  double rr = -sg_i * inv_i;
   double al = 0.0;
   for (int a = 0; a < bound; ++a) {
-    if (lane == a) { al = r * inv_i; tb[0] = al; }
-    __syncwarp();
-    const double ala = tb[0];
-    if (i > a) r = fma(-ala, SY[i * VF_GS + a], r);
-    __syncwarp();
+    const double ala = __shfl_sync(FULL, rr, a);
+    const double l = SY[i * VF_GS + a] * inv_i;
+    if (i == a) al = ala;
+    if (i > a) rr = fma(-ala, l, rr);
   }
   // ---- acc_i = y_i.(gamma q) = -gamma (y_i.g + sum_a alpha_a y_i.y_a)
   if (lane < VF_M) tb[i] = al;
@@ -390,17 +409,15 @@ __device__ __noinline__ void vf_coeffs(const VfCtx& V, double* G, int newest, in
     t0 = fma(tb[a], YY[i * VF_GS + a], t0);
     t1 = fma(tb[a + 1], YY[i * VF_GS + a + 1], t1);   // tb / YY of a pair not stored yet are zero
   }
-  double acc = -gamma * (t0 + t1);
-  __syncwarp();
-  // ---- second loop, oldest -> newest: beta_j = (y_j.d)/ys_j; d += (alpha_j - beta_j) s_j; acc_i = y_i.d
-  double aa = 0.0;
+  // ---- second loop, oldest -> newest: beta_j = (y_j.d)/ys_j; d += (alpha_j - beta_j) s_j; accp_i = (y_i.d)/ys_i
+  double accp = (-gamma * (t0 + t1)) * inv_i;
   for (int j = bound - 1; j >= 0; --j) {
-    if (lane == j) { aa = fma(-acc, inv_i, al); tb[0] = aa; }
-    __syncwarp();
-    const double aj = tb[0];
-    if (i < j) acc = fma(aj, SY[j * VF_GS + i], acc);
-    __syncwarp();
+    const double bj = __shfl_sync(FULL, accp, j);   // final for pair j: later steps only touch i < j
+    const double l = SY[j * VF_GS + i] * inv_i;
+    const double u = fma(tb[j], l, accp);            // off the dependent chain
+    if (i < j) accp = fma(-bj, l, u);
   }
+  const double aa = al - accp;
   const bool mine = lane < VF_M && i < bound;
   const double bb = -gamma * al;
   if (mine) {
@@ -418,9 +435,245 @@ __device__ __noinline__ void vf_coeffs(const VfCtx& V, double* G, int newest, in
   }
 }
 
+// ---------------------------------------------------------------------------- history in tensor memory
+// tcgen05.ld / st with the 32x32b shape: thread t of warp w reads / writes consecutive 32-bit columns of TMEM lane
+// 32 (w % 4) + t — a lane-private scratchpad next to the register file (measured: tools/microbench/tmem_rt.cu).
+__device__ __forceinline__ void tm_st1(uint32_t taddr, double v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(__double2loint(v)), "r"(__double2hiint(v)) : "memory");
+}
+__device__ __forceinline__ void tm_st8(uint32_t taddr, const double (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+               "r"(__double2loint(v[0])), "r"(__double2hiint(v[0])), "r"(__double2loint(v[1])), "r"(__double2hiint(v[1])),
+               "r"(__double2loint(v[2])), "r"(__double2hiint(v[2])), "r"(__double2loint(v[3])), "r"(__double2hiint(v[3])),
+               "r"(__double2loint(v[4])), "r"(__double2hiint(v[4])), "r"(__double2loint(v[5])), "r"(__double2hiint(v[5])),
+               "r"(__double2loint(v[6])), "r"(__double2hiint(v[6])), "r"(__double2loint(v[7])), "r"(__double2hiint(v[7]))
+               : "memory");
+}
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// 16 columns = 8 doubles; the wait takes the destination registers as in/out operands so that no use can be
+// scheduled above it
+__device__ __forceinline__ void tm_ld8(uint32_t taddr, double (&v)[8]) {
+  uint32_t r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])::"memory");
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = __hiloint2double((int)r[2 * k + 1], (int)r[2 * k]);
+}
+// two 16-column loads in flight, one wait
+__device__ __forceinline__ void tm_ld8x2(uint32_t ta, uint32_t tb, double (&va)[8], double (&vb)[8]) {
+  uint32_t r[16], q[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(ta));
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
+                 "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
+               : "r"(tb));
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(q[0]),
+                 "+r"(q[1]), "+r"(q[2]), "+r"(q[3]), "+r"(q[4]), "+r"(q[5]), "+r"(q[6]), "+r"(q[7]), "+r"(q[8]), "+r"(q[9]),
+                 "+r"(q[10]), "+r"(q[11]), "+r"(q[12]), "+r"(q[13]), "+r"(q[14]), "+r"(q[15])::"memory");
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    va[k] = __hiloint2double((int)r[2 * k + 1], (int)r[2 * k]);
+    vb[k] = __hiloint2double((int)q[2 * k + 1], (int)q[2 * k]);
+  }
+}
+// allocate this block's VF_TM_COLS columns (warp 0), publish the address through `slot` (shared); returns the
+// address with the calling warp's lane quarter.  Blocks until columns are free: every holder finishes on its own.
+__device__ __forceinline__ uint32_t tm_block_alloc(uint32_t* slot, int tid) {
+  if ((tid >> 5) == 0) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(slot);
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sa), "r"(VF_TM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  return *slot + ((uint32_t)(((tid >> 5) & 3) * 32) << 16);
+}
+__device__ __forceinline__ void tm_block_free(const uint32_t* slot, int tid) {
+  __syncthreads();
+  if ((tid >> 5) == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*slot), "r"(VF_TM_COLS) : "memory");
+}
+
+// number of owned-element rounds of a block: element e = tid + 128 q of the control-point array (e - 9 = index in x)
+__device__ __forceinline__ int vf_rounds(int n) { return (n + 3 * TP_DEGREE + TP_LB_THREADS - 1) / TP_LB_THREADS; }
+
+// 2 x 8 history values of owned element q: slots 8 ha .. 8 ha + 7 of S (ya = 0) or Y (ya = 1), and the same for b
+__device__ __forceinline__ void vf_hist_ld8x2(const VfCtx& V, int q, int ya, int ha, int yb, int hb, int tid, double (&va)[8],
+                                              double (&vb)[8]) {
+  if (q < VF_TM_Q) {
+    tm_ld8x2(V.tbase + (uint32_t)(64 * q + 32 * ya + 16 * ha), V.tbase + (uint32_t)(64 * q + 32 * yb + 16 * hb), va, vb);
+  } else {
+    const int o = tid + TP_LB_THREADS * (q - VF_TM_Q);
+    const bool ok = o < V.L.ns;
+    const double* ra = V.sm + (ya ? V.L.Y : V.L.S) + (size_t)(8 * ha) * V.L.ns + o;
+    const double* rb = V.sm + (yb ? V.L.Y : V.L.S) + (size_t)(8 * hb) * V.L.ns + o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      va[k] = ok ? ra[(size_t)k * V.L.ns] : 0.0;
+      vb[k] = ok ? rb[(size_t)k * V.L.ns] : 0.0;
+    }
+  }
+}
+__device__ __forceinline__ void vf_hist_st(const VfCtx& V, int q, int slot, int tid, double s, double y) {
+  if (q < VF_TM_Q) {
+    tm_st1(V.tbase + (uint32_t)(64 * q + 2 * slot), s);
+    tm_st1(V.tbase + (uint32_t)(64 * q + 32 + 2 * slot), y);
+    tm_wait_st();
+  } else {
+    const int o = tid + TP_LB_THREADS * (q - VF_TM_Q);
+    if (o < V.L.ns) {
+      V.sm[V.L.S + (size_t)slot * V.L.ns + o] = s;
+      V.sm[V.L.Y + (size_t)slot * V.L.ns + o] = y;
+    }
+  }
+}
+__device__ __forceinline__ void vf_hist_zero(const VfCtx& V, int tid) {
+  const double z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int c = 0; c < VF_TM_COLS; c += 16) tm_st8(V.tbase + c, z);
+  tm_wait_st();
+  for (int e = tid; e < 2 * VF_M * V.L.ns; e += TP_LB_THREADS) V.sm[V.L.S + e] = 0.0;
+}
+
+// Gram update, tm layout, part 1 (all threads): store the new pair (s, y) = (x - xp, g - gp) in slot `slot`, then the
+// per-warp partial sums of   s_j.g, y_j.g  (j = 0..15, the new pair included)  and  s_new.y_new, y_new.y_new.
+// Only 2 x 16 + 2 fresh dot products per iteration: the other Gram entries of the new pair follow from
+// y_new = g - g_prev by linearity (vf_gram_finish_tm).
+// The 32 sums over the warp's lanes are one recursive-halving reduce-scatter (31 double shuffles, 5 dependent steps,
+// fixed order => deterministic): lanes 0-15 end with s_lane.g, lanes 16-31 with y_(lane-16).g.
+__device__ __noinline__ void vf_gram_partial_tm(const VfCtx& V, int slot, int tid) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = tid & 31, warp = tid >> 5, n = V.n, Q = vf_rounds(n);
+  const double* cp = V.sm + V.L.cp;
+  const double* g = V.sm + V.L.g;
+  const double* xp = V.sm + V.L.xp;
+  const double* gp = V.sm + V.L.gp;
+  double* gred = V.sm + V.L.gred + warp * (2 * VF_M + 2);
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
+  double e0 = 0.0, e1 = 0.0;
+  double acc[16];   // after the xor-16 exchange: lanes 0-15 hold the S-type sums, lanes 16-31 the Y-type sums
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+  for (int q = 0; q < Q; ++q) {
+    const int e = tid + TP_LB_THREADS * q, i = e - 3 * TP_DEGREE;
+    const bool ok = i >= 0 && i < n;
+    const double gi = ok ? g[i] : 0.0;
+    const double s = ok ? cp[e] - xp[i] : 0.0;
+    const double y = ok ? gi - gp[i] : 0.0;
+    vf_hist_st(V, q, slot, tid, s, y);
+    e0 = fma(s, y, e0);
+    e1 = fma(y, y, e1);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      double vs[8], vy[8];
+      vf_hist_ld8x2(V, q, 0, h, 1, h, tid, vs, vy);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const double ps = vs[k] * gi, py = vy[k] * gi;
+        const double send = b4 ? ps : py, keep = b4 ? py : ps;
+        acc[8 * h + k] += keep + __shfl_xor_sync(FULL, send, 16);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const double send = b3 ? acc[k] : acc[k + 8], keep = b3 ? acc[k + 8] : acc[k];
+    acc[k] = keep + __shfl_xor_sync(FULL, send, 8);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double send = b2 ? acc[k] : acc[k + 4], keep = b2 ? acc[k + 4] : acc[k];
+    acc[k] = keep + __shfl_xor_sync(FULL, send, 4);
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const double send = b1 ? acc[k] : acc[k + 2], keep = b1 ? acc[k + 2] : acc[k];
+    acc[k] = keep + __shfl_xor_sync(FULL, send, 2);
+  }
+  {
+    const double send = b0 ? acc[0] : acc[1], keep = b0 ? acc[1] : acc[0];
+    acc[0] = keep + __shfl_xor_sync(FULL, send, 1);
+  }
+  e0 = warp_sum(e0);
+  e1 = warp_sum(e1);
+  gred[lane] = acc[0];
+  if (lane == 0) {
+    gred[2 * VF_M] = e0;
+    gred[2 * VF_M + 1] = e1;
+  }
+}
+
+// Gram update, tm layout, part 2 (the serial warp, after a barrier): combine the warps' partial sums in a fixed
+// order and fill the newest pair's row / column of the age-ordered blocks `G` (O = the previous iteration's buffer):
+//   Sg[a] = s_a.g, Yg[a] = y_a.g                                  fresh
+//   SY[a][0] = s_a.y_new = s_a.g - s_a.g_prev = Sg[a] - O.Sg[a-1]   (a >= 1: pair a was pair a-1 one iteration ago)
+//   YY[a][0] = YY[0][a] = y_a.y_new = Yg[a] - O.Yg[a-1]
+//   SY[0][0] = s_new.y_new, YY[0][0] = y_new.y_new                fresh
+__device__ __forceinline__ void vf_gram_finish_tm(const VfCtx& V, double* G, const double* O, int slot, int lane) {
+  const double* gred = V.sm + V.L.gred;
+  const int str = 2 * VF_M + 2;
+  const double tot = ((gred[lane] + gred[str + lane]) + gred[2 * str + lane]) + gred[3 * str + lane];
+  const int j = lane & (VF_M - 1);
+  const int age = (slot - j) & (VF_M - 1);
+  if (lane < VF_M) {
+    G[VF_G_SG + age] = tot;
+    if (age != 0) G[VF_G_SY + age * VF_GS] = tot - O[VF_G_SG + age - 1];
+    else G[VF_G_SY] = ((gred[2 * VF_M] + gred[str + 2 * VF_M]) + gred[2 * str + 2 * VF_M]) + gred[3 * str + 2 * VF_M];
+  } else {
+    G[VF_G_YG + age] = tot;
+    if (age != 0) {
+      const double v = tot - O[VF_G_YG + age - 1];
+      G[VF_G_YY + age] = v;
+      G[VF_G_YY + age * VF_GS] = v;
+    } else {
+      G[VF_G_YY] = ((gred[2 * VF_M + 1] + gred[str + 2 * VF_M + 1]) + gred[2 * str + 2 * VF_M + 1]) + gred[3 * str + 2 * VF_M + 1];
+    }
+  }
+  __syncwarp();
+}
+
+// d = cg g + sum_j ca[j] s_j + cb[j] y_j over all 16 slots (coefficients of slots not stored yet are zero)
+__device__ __noinline__ void vf_direction_tm(const VfCtx& V, double cg, int tid) {
+  const int n = V.n, Q = vf_rounds(n);
+  const double* g = V.sm + V.L.g;
+  const double* ca = V.sm + V.L.ca;
+  const double* cb = V.sm + V.L.cb;
+  double* d = V.sm + V.L.d;
+  for (int q = 0; q < Q; ++q) {
+    const int i = tid + TP_LB_THREADS * q - 3 * TP_DEGREE;
+    const bool ok = i >= 0 && i < n;
+    double a0 = ok ? cg * g[i] : 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    double va[8], vb[8];
+    vf_hist_ld8x2(V, q, 0, 0, 0, 1, tid, va, vb);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      a0 = fma(ca[k], va[k], a0);
+      a1 = fma(ca[8 + k], vb[k], a1);
+    }
+    vf_hist_ld8x2(V, q, 1, 0, 1, 1, tid, va, vb);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      a2 = fma(cb[k], va[k], a2);
+      a3 = fma(cb[8 + k], vb[k], a3);
+    }
+    if (ok) d[i] = (a0 + a1) + (a2 + a3);
+  }
+}
+
 // One optimize() (bsplineTraj.cpp:687-718), throughput form.  V.sm + L.cp holds the control points on
 // entry; on return it holds the LAST EVALUATED point (bsplineTraj.cpp:803) and xfinal (global, may be
 // null) the solver's own x.
+template <bool TM>
 __device__ void lbfgs_run_fast(const VigoConst& C, VfCtx& V, tp_lbfgs_result& out, double* xfinal, int tid) {
   const int n = V.n, N = V.N, ns = V.L.ns;
   double* sm = V.sm;
@@ -440,10 +693,15 @@ __device__ void lbfgs_run_fast(const VigoConst& C, VfCtx& V, tp_lbfgs_result& ou
   R.flip = 0;
   const double min_step = 1e-20, max_step = 1e20, ftol = 1e-4, gtol = 0.9, xtol = 1e-16;  // lbfgs.hpp:942-954
   const int max_ls = C.p.lbfgs_max_linesearch;
+  const double geps2 = C.p.lbfgs_g_eps * C.p.lbfgs_g_eps;
   // zero the history rows, the Gram blocks and the padding of g (garbage would poison the MMA tiles)
-  for (int e = tid; e < 2 * VF_M * ns; e += TP_LB_THREADS) S[e] = 0.0;   // S and Y are contiguous
+  if (TM) {
+    vf_hist_zero(V, tid);
+  } else {
+    for (int e = tid; e < 2 * VF_M * ns; e += TP_LB_THREADS) S[e] = 0.0;   // S and Y are contiguous
+    for (int e = n + tid; e < ns; e += TP_LB_THREADS) g[e] = 0.0;
+  }
   for (int e = tid; e < 2 * VF_GRAM + 2 * VF_M + 8; e += TP_LB_THREADS) (sm + V.L.gram)[e] = 0.0;   // gram, ca, cb, sc
-  for (int e = n + tid; e < ns; e += TP_LB_THREADS) g[e] = 0.0;
   vf_stage_pairs(V, tid);
   __syncthreads();
   int evals = 0, k = 0, ret, bsum = 0;
@@ -552,41 +810,55 @@ __device__ void lbfgs_run_fast(const VigoConst& C, VfCtx& V, tp_lbfgs_result& ou
         ret = ls;
         break;
       }
-      xnorm = sqrt(xx);
-      gnorm = sqrt(gg);
-      if (xnorm < 1.0) xnorm = 1.0;
-      if (gnorm / xnorm <= C.p.lbfgs_g_eps) { ret = 0; break; }
+      // ||g|| / max(1, ||x||) <= g_epsilon (lbfgs.hpp:1218-1225) without the two square roots and the division
+      if (gg <= geps2 * (xx < 1.0 ? 1.0 : xx)) { ret = 0; break; }
       if (C.p.lbfgs_max_iter != 0 && C.p.lbfgs_max_iter < k + 1) { ret = LB_MAXITER; break; }
       // ---------------- new pair into slot `end`, Gram update, coefficients, direction
-      double* s = S + (size_t)end * ns;
-      double* y = Y + (size_t)end * ns;
-      LT0
-      VF_OWNED(i) { s[i] = x[i] - xp[i]; y[i] = g[i] - gp[i]; }
-      gbuf ^= 1;
-      vf_gram_shift(V, gbuf, tid);
-      __syncthreads();
-      vf_gram_update(V, end, gbuf, tid);
       const int bound = (VF_M <= k) ? VF_M : k;
       bsum += bound;
-      __syncthreads();
-      LT(tG)
-      if ((tid >> 5) == V.serial_warp) vf_coeffs(V, sm + V.L.gram + (size_t)gbuf * VF_GRAM, end, bound, gg, tid & 31);
-      __syncthreads();
-      LT(tC)
-      const double cg = sc[0];
-      dginit_next = sc[1];
-      VF_OWNED(i) {
-        double a0 = cg * g[i], a1 = 0.0;
-        const double* sp = S + i;
-        const double* yp = Y + i;
-#pragma unroll 4
-        for (int j = 0; j < bound; ++j) {
-          a0 = fma(ca[j], sp[0], a0);
-          a1 = fma(cb[j], yp[0], a1);
-          sp += ns;
-          yp += ns;
+      LT0
+      gbuf ^= 1;
+      if (TM) {
+        vf_gram_shift(V, gbuf, tid);
+        vf_gram_partial_tm(V, end, tid);
+        __syncthreads();
+        LT(tG)
+        if ((tid >> 5) == V.serial_warp) {
+          double* G = sm + V.L.gram + (size_t)gbuf * VF_GRAM;
+          vf_gram_finish_tm(V, G, sm + V.L.gram + (size_t)(gbuf ^ 1) * VF_GRAM, end, tid & 31);
+          vf_coeffs(V, G, end, bound, gg, tid & 31);
         }
-        d[i] = a0 + a1;
+        __syncthreads();
+        LT(tC)
+        dginit_next = sc[1];
+        vf_direction_tm(V, sc[0], tid);
+      } else {
+        double* s = S + (size_t)end * ns;
+        double* y = Y + (size_t)end * ns;
+        VF_OWNED(i) { s[i] = x[i] - xp[i]; y[i] = g[i] - gp[i]; }
+        vf_gram_shift(V, gbuf, tid);
+        __syncthreads();
+        vf_gram_update(V, end, gbuf, tid);
+        __syncthreads();
+        LT(tG)
+        if ((tid >> 5) == V.serial_warp) vf_coeffs(V, sm + V.L.gram + (size_t)gbuf * VF_GRAM, end, bound, gg, tid & 31);
+        __syncthreads();
+        LT(tC)
+        const double cg = sc[0];
+        dginit_next = sc[1];
+        VF_OWNED(i) {
+          double a0 = cg * g[i], a1 = 0.0;
+          const double* sp = S + i;
+          const double* yp = Y + i;
+#pragma unroll 4
+          for (int j = 0; j < bound; ++j) {
+            a0 = fma(ca[j], sp[0], a0);
+            a1 = fma(cb[j], yp[0], a1);
+            sp += ns;
+            yp += ns;
+          }
+          d[i] = a0 + a1;
+        }
       }
       LT(tD)
       ++k;
@@ -596,7 +868,7 @@ __device__ void lbfgs_run_fast(const VigoConst& C, VfCtx& V, tp_lbfgs_result& ou
   }
   if (xfinal) VF_OWNED(i) xfinal[i] = x[i];
 #ifdef TP_LBFGS_TIMING
-  if (tid == 0 && k > 50)
+  if (tid == 0 && k > 50 && TP_LBFGS_TIMING > 1)
     printf("[lbfgs] N %d k %d evals %d cycles/iter: total %.0f eval %.0f gram %.0f coeffs %.0f dform %.0f | per eval: partial %.0f blocksum %.0f\n", N, k, evals,
            (double)(clock64() - tT0) / k, (double)tE / k, (double)tG / k, (double)tC / k, (double)tD / k,
            (double)g_tp_t_partial / evals, (double)g_tp_t_sum / evals);

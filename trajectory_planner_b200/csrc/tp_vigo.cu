@@ -133,6 +133,10 @@ __global__ void __launch_bounds__(TP_LB_THREADS, 4) k_lbfgs(BatchView bv, VigoCo
   const int b = active[blockIdx.x], tid = threadIdx.x;
   TrajState& st = bv.st[b];
   const int N = st.N, n = 3 * (N - 2 * TP_DEGREE);
+  // tensor-memory address slot: one word past this trajectory's layout (the launch reserves 16 B beyond the largest)
+  uint32_t* tm_slot = reinterpret_cast<uint32_t*>(sm + vf_layout(N < 2 * TP_DEGREE ? 2 * TP_DEGREE : N, true).total);
+  uint32_t tbase = 0;
+  if (MODE == 3) tbase = tm_block_alloc(tm_slot, tid);
   tp_lbfgs_result r;
   if (n <= 0) {
     r.ret = LB_INVALID_N; r.iters = 0; r.evals = 0; r.reserved = 0; r.fx = 0;
@@ -147,13 +151,14 @@ __global__ void __launch_bounds__(TP_LB_THREADS, 4) k_lbfgs(BatchView bv, VigoCo
     E.w_dist = st.w_dist; E.w_dyn = st.w_dyn;
     E.n_dyn = bv.n_dyn; E.dyn_pos = bv.dyn_pos; E.dyn_vel = bv.dyn_vel; E.dyn_size = bv.dyn_size;
     double* xf = xfinal_out ? xfinal_out + 3 * ((size_t)st.off - (size_t)2 * TP_DEGREE * b) : nullptr;
-    if (MODE == 2) {
+    if (MODE >= 2) {
       VfCtx V;
-      V.N = N; V.n = n; V.sm = sm; V.L = vf_layout(N);
+      V.N = N; V.n = n; V.sm = sm; V.L = vf_layout(N, MODE == 3);
       V.pairs = E.pairs; V.head = E.head; V.n_pairs = st.n_pairs; V.pairs_in_sm = false; V.serial_warp = 0;
       V.w_dist = E.w_dist; V.w_dyn = E.w_dyn;
       V.n_dyn = E.n_dyn; V.dyn_pos = E.dyn_pos; V.dyn_vel = E.dyn_vel; V.dyn_size = E.dyn_size;
-      lbfgs_run_fast(C, V, r, xf, tid);
+      V.tbase = tbase;
+      lbfgs_run_fast<MODE == 3>(C, V, r, xf, tid);
     } else {
       lbfgs_run<MODE == 1>(C, E, cp + 3 * N, r, xf, tid);
     }
@@ -176,6 +181,7 @@ __global__ void __launch_bounds__(TP_LB_THREADS, 4) k_lbfgs(BatchView bv, VigoCo
       atomicAdd(&counters[2], (double)r.evals);
     }
   }
+  if (MODE == 3) tm_block_free(tm_slot, tid);
 }
 
 // ---- hasCollisionTrajectory (+ hasDynamicCollisionTrajectory), block-wide on control points in shared memory
@@ -475,7 +481,7 @@ __host__ __device__ inline SolveLayout solve_layout(int N, int mode, int m) {
   L.st = o; o += (int)((sizeof(TrajState) + 7) / 8);
   L.vf = o;
   const int cp_d = 3 * N + (N & 1);
-  const int solver = mode == 2 ? vf_layout(N).total : (int)lbfgs_smem_doubles(N, m) + (N & 1);
+  const int solver = mode >= 2 ? vf_layout(N, mode == 3).total : (int)lbfgs_smem_doubles(N, m) + (N & 1);
   L.plan = L.vf + cp_d;
   const int plan_end = L.plan + (int)((sizeof(PlanSmem) + 7) / 8);
   const int rp_end = L.plan + 3 * (N - 1) + 3 * (N - 2) + 2 * TP_LB_WARPS + 4;
@@ -488,7 +494,7 @@ __host__ __device__ inline SolveLayout solve_layout(int N, int mode, int m) {
 
 template <int MODE>
 __device__ __forceinline__ void solve_one(const BatchView& bv, const VigoConst& C, const DevMap& map, const AStarPools& P,
-                                          int b, int class_max_n, int s_slot, int sw, double* counters,
+                                          int b, int class_max_n, int s_slot, int sw, uint32_t tbase, double* counters,
                                           long long* timeline, int resume, int rounds_this_pass, double* sm) {
   const int tid = threadIdx.x, lane = tid & 31;
   long long t_start = 0;
@@ -522,20 +528,29 @@ __device__ __forceinline__ void solve_one(const BatchView& bv, const VigoConst& 
   __syncthreads();
   double fl = 0.0, its = 0.0, evs = 0.0, smp = 0.0;
   int rounds_done = 0;
+#ifdef TP_LBFGS_TIMING
+  long long ph[4] = {0, 0, 0, 0}, pt0 = clock64(), pt1;
+  const long long pstart = pt0;
+#define PH(i) { pt1 = clock64(); ph[i] += pt1 - pt0; pt0 = pt1; }
+#else
+#define PH(i)
+#endif
+  PH(0)
   while (st.status == TS_ACTIVE && rounds_done < rounds_this_pass) {
     ++rounds_done;
     // ---- optimize()
     tp_lbfgs_result r;
     if (n <= 0) {
       r.ret = LB_INVALID_N; r.iters = 0; r.evals = 0; r.reserved = 0; r.fx = 0;
-    } else if (MODE == 2) {
+    } else if (MODE >= 2) {
       VfCtx V;
-      V.N = N; V.n = n; V.sm = cp; V.L = vf_layout(N);
+      V.N = N; V.n = n; V.sm = cp; V.L = vf_layout(N, MODE == 3);
+      V.tbase = tbase;
       V.pairs = bv.pairs + (size_t)b * C.gcap; V.head = bv.cp_head + st.off; V.n_pairs = st.n_pairs; V.pairs_in_sm = false;
       V.serial_warp = sw;
       V.w_dist = st.w_dist; V.w_dyn = st.w_dyn;
       V.n_dyn = bv.n_dyn; V.dyn_pos = bv.dyn_pos; V.dyn_vel = bv.dyn_vel; V.dyn_size = bv.dyn_size;
-      lbfgs_run_fast(C, V, r, nullptr, tid);
+      lbfgs_run_fast<MODE == 3>(C, V, r, nullptr, tid);
     } else {
       EvalCtx E;
       E.N = N; E.n = n; E.cp = cp;
@@ -559,6 +574,7 @@ __device__ __forceinline__ void solve_one(const BatchView& bv, const VigoConst& 
         evs += r.evals;
       }
     }
+    PH(1)
     // ---- hasCollisionTrajectory
     int any = 1;
     if (N >= 4) any = dev_has_collision(cp, N, bv, C, map, tid);
@@ -567,13 +583,20 @@ __device__ __forceinline__ void solve_one(const BatchView& bv, const VigoConst& 
       smp += floor((double)(N - TP_DEGREE) * C.p.ctrl_pt_ts / C.check_ts) + 1.0;
     }
     __syncthreads();
+    PH(2)
     // ---- loop body: success / failure / re-guide / weight doubling
     if (is_serial_warp) {
       dev_plan_step(lbv, C, map, st, W, PS, b, lane);
       if (lane == 0 && W.goal_unreachable) st.astar_unreach = 1;
     }
     __syncthreads();
+    PH(3)
   }
+#ifdef TP_LBFGS_TIMING
+  if (tid == 0 && st.lbfgs_iters > 1200)
+    printf("[solve] b %d N %d iters %d exp %d rounds %d | kcycles: total %lld init %lld lbfgs %lld collision %lld step %lld\n", b, N,
+           st.lbfgs_iters, st.astar_expansions, rounds_done, (clock64() - pstart) / 1000, ph[0] / 1000, ph[1] / 1000, ph[2] / 1000, ph[3] / 1000);
+#endif
   // ---- linearFeasibilityReparam
   if (st.status == TP_STATUS_SUCCESS) {
     double* q = sm + SL.plan;
@@ -624,7 +647,10 @@ __global__ void __launch_bounds__(TP_LB_THREADS, 4) k_solve(BatchView bv, VigoCo
   extern __shared__ double sm[];
   const int tid = threadIdx.x;
   const SolveLayout SL = solve_layout(class_max_n, MODE, C.p.lbfgs_m);
-  int* pick = reinterpret_cast<int*>(sm + SL.total);   // 2 ints past the layout (the launch reserves them)
+  int* pick = reinterpret_cast<int*>(sm + SL.total);   // 3 ints past the layout (the launch reserves 16 B)
+  uint32_t* tm_slot = reinterpret_cast<uint32_t*>(pick + 2);
+  uint32_t tbase = 0;
+  if (MODE == 3) tbase = tm_block_alloc(tm_slot, tid);   // the worker's L-BFGS history columns, held until it exits
   // ---- claim an A* node pool (one per resident worker) and a serial-warp role.  Warp w of every block lives on SM
   // sub-partition w, so the workers sharing an SM take DIFFERENT warps for their serial phases (A*, guide points, the
   // coefficient recurrences): a per-SM ticket rotates the role.
@@ -653,12 +679,13 @@ __global__ void __launch_bounds__(TP_LB_THREADS, 4) k_solve(BatchView bv, VigoCo
     __syncthreads();
     const int b = pick[0];
     if (b < 0) break;
-    solve_one<MODE>(bv, C, map, P, b, class_max_n, s_slot, sw, counters, timeline, resume, rounds_this_pass, sm);
+    solve_one<MODE>(bv, C, map, P, b, class_max_n, s_slot, sw, tbase, counters, timeline, resume, rounds_this_pass, sm);
   }
   if (tid == 0) {
     __threadfence();
     atomicExch(&slot_flags[s_slot], 0);
   }
+  if (MODE == 3) tm_block_free(tm_slot, tid);
 }
 
 // standalone A* (parity entry): one warp per (start, end) pair
@@ -1114,20 +1141,24 @@ __global__ void k_resolve_unknown(BatchView bv, VigoConst C, DevMap map) {
   pr.unknown = dm_unknown(map, d3(pr.p[0], pr.p[1], pr.p[2])) ? 1 : 0;
 }
 
-// which fused cost+L-BFGS kernel runs: 1 strict (bit-faithful), 2 vector-free (default), 0 classic two-loop
-// with tree reductions (lbfgs_m != 16, or TP_LBFGS_CLASSIC=1 for A/B measurements)
+// which fused cost+L-BFGS kernel runs: 1 strict (bit-faithful); 3 vector-free with the history in tensor memory
+// (default); 2 vector-free with the history in shared memory + FP64 MMA Gram update (TP_LBFGS_SMEM_HISTORY=1, for A/B
+// measurements); 0 classic two-loop with tree reductions (lbfgs_m != 16, or TP_LBFGS_CLASSIC=1)
 static int lbfgs_mode(const tp_vigo_params* p) {
   if (p->strict_order) return 1;
   static const bool classic = getenv("TP_LBFGS_CLASSIC") != nullptr;
-  return (p->lbfgs_m == VF_M && !classic) ? 2 : 0;
+  static const bool smem_hist = getenv("TP_LBFGS_SMEM_HISTORY") != nullptr;
+  return (p->lbfgs_m == VF_M && !classic) ? (smem_hist ? 2 : 3) : 0;
 }
 static size_t lbfgs_smem_bytes(const tp_vigo_params* p, int max_n) {
-  return lbfgs_mode(p) == 2 ? vf_smem_bytes(max_n) : lbfgs_smem_doubles(max_n, p->lbfgs_m) * 8;
+  const int mode = lbfgs_mode(p);
+  return mode >= 2 ? vf_smem_bytes(max_n, mode == 3) + 16 : lbfgs_smem_doubles(max_n, p->lbfgs_m) * 8;
 }
 template <class... A>
 static void launch_lbfgs(int mode, int grid, size_t smem, cudaStream_t s, A... args) {
   if (mode == 1) k_lbfgs<1><<<grid, TP_LB_THREADS, smem, s>>>(args...);
   else if (mode == 2) k_lbfgs<2><<<grid, TP_LB_THREADS, smem, s>>>(args...);
+  else if (mode == 3) k_lbfgs<3><<<grid, TP_LB_THREADS, smem, s>>>(args...);
   else k_lbfgs<0><<<grid, TP_LB_THREADS, smem, s>>>(args...);
 }
 
@@ -1140,6 +1171,7 @@ static int set_lbfgs_smem(tp_engine* e, size_t bytes) {
     CK(cudaFuncSetAttribute(k_lbfgs<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
     CK(cudaFuncSetAttribute(k_lbfgs<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
     CK(cudaFuncSetAttribute(k_lbfgs<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
+    CK(cudaFuncSetAttribute(k_lbfgs<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
     CK(cudaFuncSetAttribute(k_cost<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
     CK(cudaFuncSetAttribute(k_cost<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
     e->lbfgs_attr_set = true;
@@ -1580,6 +1612,8 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
     CK(cudaFuncSetAttribute(k_solve<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
     CK(cudaFuncSetAttribute(k_solve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
     CK(cudaFuncSetAttribute(k_solve<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
+    CK(cudaFuncSetAttribute(k_solve<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
+    CK(cudaFuncSetAttribute(k_solve<3>, cudaFuncAttributePreferredSharedMemoryCarveout, getenv("TP_CARVEOUT") ? atoi(getenv("TP_CARVEOUT")) : 100));
     CK(cudaFuncSetAttribute(k_solve<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CK(cudaFuncSetAttribute(k_solve<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CK(cudaFuncSetAttribute(k_solve<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -1600,7 +1634,12 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
   //   pass 2: the trajectories still colliding (~60 %), ordered by first-round work (L-BFGS iterations, A*
   //           expansions, guide pairs: correlation 0.86 with the remaining time), hardest first.
   // Every optimize() starts from a fresh L-BFGS state, so cutting a solve at a round boundary changes no result.
-  static const int class_lim[4] = {TP_MAX_CTRL, 104, 64, 40};   // upper N bound of each class, largest first
+  // upper N bound of each class, largest first.  With the history in tensor memory the shared-memory footprint is
+  // flat up to N = 88 (the A* scratch dominates) and grows only with the overflow elements beyond 2 per thread
+  // (+12 KB at N = 104): one class serves every path the reference accepts (max_path_length 20 m => N <= 105).
+  static const int class_lim_smem[4] = {TP_MAX_CTRL, 104, 64, 40};
+  static const int class_lim_tm[4] = {TP_MAX_CTRL, 160, 104, 0};
+  const int* class_lim = lbfgs_mode(p) == 3 ? class_lim_tm : class_lim_smem;
   auto class_of = [&](int b) {
     const int n = bs.h_off[b + 1] - bs.h_off[b];
     return n > class_lim[1] ? 0 : (n > class_lim[2] ? 1 : (n > class_lim[3] ? 2 : 3));
@@ -1703,6 +1742,7 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
         const int* ord = e->active[0].as<int>();
         if (mode == 1) k_solve<1><<<grid, TP_LB_THREADS, smem[c], cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, d_cb, d_cb + 5, c, nmax[c], e->pool_flags.as<int>(), e->counters_ptr(), tl, resume, rounds);
         else if (mode == 2) k_solve<2><<<grid, TP_LB_THREADS, smem[c], cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, d_cb, d_cb + 5, c, nmax[c], e->pool_flags.as<int>(), e->counters_ptr(), tl, resume, rounds);
+        else if (mode == 3) k_solve<3><<<grid, TP_LB_THREADS, smem[c], cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, d_cb, d_cb + 5, c, nmax[c], e->pool_flags.as<int>(), e->counters_ptr(), tl, resume, rounds);
         else k_solve<0><<<grid, TP_LB_THREADS, smem[c], cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, d_cb, d_cb + 5, c, nmax[c], e->pool_flags.as<int>(), e->counters_ptr(), tl, resume, rounds);
       }
       CK(cudaGetLastError());
