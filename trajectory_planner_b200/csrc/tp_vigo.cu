@@ -1141,14 +1141,15 @@ __global__ void k_resolve_unknown(BatchView bv, VigoConst C, DevMap map) {
   pr.unknown = dm_unknown(map, d3(pr.p[0], pr.p[1], pr.p[2])) ? 1 : 0;
 }
 
-// which fused cost+L-BFGS kernel runs: 1 strict (bit-faithful); 3 vector-free with the history in tensor memory
-// (default); 2 vector-free with the history in shared memory + FP64 MMA Gram update (TP_LBFGS_SMEM_HISTORY=1, for A/B
-// measurements); 0 classic two-loop with tree reductions (lbfgs_m != 16, or TP_LBFGS_CLASSIC=1)
+// which fused cost+L-BFGS kernel runs: 1 strict (bit-faithful); 2 vector-free with the history in shared memory +
+// FP64 MMA Gram update (default); 3 vector-free with the history in tensor memory (TP_LBFGS_TMEM=1: 4 workers per SM
+// instead of 3, measured slower per iteration so far); 0 classic two-loop with tree reductions (lbfgs_m != 16, or
+// TP_LBFGS_CLASSIC=1)
 static int lbfgs_mode(const tp_vigo_params* p) {
   if (p->strict_order) return 1;
   static const bool classic = getenv("TP_LBFGS_CLASSIC") != nullptr;
-  static const bool smem_hist = getenv("TP_LBFGS_SMEM_HISTORY") != nullptr;
-  return (p->lbfgs_m == VF_M && !classic) ? (smem_hist ? 2 : 3) : 0;
+  static const bool tmem_hist = getenv("TP_LBFGS_TMEM") != nullptr;
+  return (p->lbfgs_m == VF_M && !classic) ? (tmem_hist ? 3 : 2) : 0;
 }
 static size_t lbfgs_smem_bytes(const tp_vigo_params* p, int max_n) {
   const int mode = lbfgs_mode(p);
