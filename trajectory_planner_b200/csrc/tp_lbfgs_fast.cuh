@@ -25,6 +25,7 @@
 #define VF_M 16          // history pairs (bsplineTraj.cpp:697); other values use the classic kernel
 #define VF_GS 17         // Gram row stride (doubles): conflict-free row reads across lanes
 #define VF_PAIRS_SM 64   // guide pairs staged in shared memory (more -> read through L2)
+#define VF_PAIRS_TM 160  // same, tm layout (the history is not in shared memory: room for more)
 // One Gram buffer, indexed by AGE (0 = newest pair): SY[i][a] = s_i.y_a, YY[i][a] = y_i.y_a (row stride VF_GS),
 // Sg[i] = s_i.g, Yg[i] = y_i.g, inv[i] = 1/(s_i.y_i), tb = scratch.  Every iteration the blocks shift by one
 // age (old[i][a] -> new[i+1][a+1]) and the newest pair fills row / column 0.
@@ -49,6 +50,7 @@ struct VfLayout {  // offsets in doubles from the start of dynamic shared memory
   int ns;          // smem layout: padded history row stride, ns % 16 == 4 (conflict-free MMA fragment loads);
                    // tm layout: row stride of the overflow history (elements e >= VF_TM_ELEMS), 0 if none
   int cp, g, xp, gp, d, S, Y, gram, ca, cb, sc, red, gred, pair, pstart, total;
+  int pairs_cap;   // guide pairs the `pair` region holds
 };
 __host__ __device__ inline VfLayout vf_layout(int N, bool tm = false) {
   VfLayout L;
@@ -76,7 +78,8 @@ __host__ __device__ inline VfLayout vf_layout(int N, bool tm = false) {
   L.sc = o; o += 8;
   L.red = o; o += 2 * TP_LB_WARPS * 4;
   L.gred = o; o += tm ? TP_LB_WARPS * (2 * VF_M + 2) : 0;   // per-warp partial Gram sums (tm layout)
-  L.pair = o; o += VF_PAIRS_SM * 7;
+  L.pairs_cap = tm ? VF_PAIRS_TM : VF_PAIRS_SM;
+  L.pair = o; o += L.pairs_cap * 7;
   L.pstart = o; o += (N + 2 + 1) / 2;   // (N + 1) ints
   L.total = o;
   return L;
@@ -158,7 +161,7 @@ __device__ __forceinline__ void vf_height_term(const VigoConst& C, double cz, in
 __device__ void vf_stage_pairs(VfCtx& V, int tid) {
   int* pstart = reinterpret_cast<int*>(V.sm + V.L.pstart);
   double* ps = V.sm + V.L.pair;
-  V.pairs_in_sm = V.n_pairs <= VF_PAIRS_SM;
+  V.pairs_in_sm = V.n_pairs <= V.L.pairs_cap;
   if (!V.pairs_in_sm) return;   // uniform
   // counts per control point (thread per control point walks its list)
   for (int c = tid; c < V.N; c += TP_LB_THREADS) {
@@ -373,13 +376,11 @@ __device__ __forceinline__ void vf_gram_shift(const VfCtx& V, int gbuf_new, int 
 // memory and every lane applies one FMA to its own running sum.
 // `newest` = slot of the newest pair, gg = g.g.  Writes ca[slot], cb[slot] (coefficients of
 // s_slot, y_slot), sc[0] = coefficient of g, sc[1] = g.d (the line search's dginit).
-__device__ __noinline__ void vf_coeffs(const VfCtx& V, double* G, int newest, int bound, double gg, int lane) {
+// (noinline functions take plain pointers / scalars: a struct passed by reference would live in local memory)
+__device__ __noinline__ void vf_coeffs(double* G, double* ca, double* cb, double* sc, int newest, int bound, double gg, int lane) {
   const double* SY = G + VF_G_SY;
   const double* YY = G + VF_G_YY;
   double* tb = G + VF_G_TB;          // broadcast scratch (16 doubles)
-  double* ca = V.sm + V.L.ca;
-  double* cb = V.sm + V.L.cb;
-  double* sc = V.sm + V.L.sc;
   const unsigned FULL = 0xffffffffu;
   const int i = lane & (VF_M - 1);
   // 1/ys and 1/yy of the newest pair (two lanes divide concurrently)
@@ -551,7 +552,9 @@ __device__ __forceinline__ void vf_hist_zero(const VfCtx& V, int tid) {
 // y_new = g - g_prev by linearity (vf_gram_finish_tm).
 // The 32 sums over the warp's lanes are one recursive-halving reduce-scatter (31 double shuffles, 5 dependent steps,
 // fixed order => deterministic): lanes 0-15 end with s_lane.g, lanes 16-31 with y_(lane-16).g.
-__device__ __noinline__ void vf_gram_partial_tm(const VfCtx& V, int slot, int tid) {
+__device__ __noinline__ void vf_gram_partial_tm(double* sm_, int N_, uint32_t tbase, int slot, int tid) {
+  VfCtx V;   // only the fields the history accessors read
+  V.sm = sm_; V.N = N_; V.n = 3 * (N_ - 2 * TP_DEGREE); V.L = vf_layout(N_, true); V.tbase = tbase;
   const unsigned FULL = 0xffffffffu;
   const int lane = tid & 31, warp = tid >> 5, n = V.n, Q = vf_rounds(n);
   const double* cp = V.sm + V.L.cp;
@@ -643,7 +646,9 @@ __device__ __forceinline__ void vf_gram_finish_tm(const VfCtx& V, double* G, con
 }
 
 // d = cg g + sum_j ca[j] s_j + cb[j] y_j over all 16 slots (coefficients of slots not stored yet are zero)
-__device__ __noinline__ void vf_direction_tm(const VfCtx& V, double cg, int tid) {
+__device__ __noinline__ void vf_direction_tm(double* sm_, int N_, uint32_t tbase, double cg, int tid) {
+  VfCtx V;
+  V.sm = sm_; V.N = N_; V.n = 3 * (N_ - 2 * TP_DEGREE); V.L = vf_layout(N_, true); V.tbase = tbase;
   const int n = V.n, Q = vf_rounds(n);
   const double* g = V.sm + V.L.g;
   const double* ca = V.sm + V.L.ca;
@@ -820,18 +825,18 @@ __device__ void lbfgs_run_fast(const VigoConst& C, VfCtx& V, tp_lbfgs_result& ou
       gbuf ^= 1;
       if (TM) {
         vf_gram_shift(V, gbuf, tid);
-        vf_gram_partial_tm(V, end, tid);
+        vf_gram_partial_tm(sm, N, V.tbase, end, tid);
         __syncthreads();
         LT(tG)
         if ((tid >> 5) == V.serial_warp) {
           double* G = sm + V.L.gram + (size_t)gbuf * VF_GRAM;
           vf_gram_finish_tm(V, G, sm + V.L.gram + (size_t)(gbuf ^ 1) * VF_GRAM, end, tid & 31);
-          vf_coeffs(V, G, end, bound, gg, tid & 31);
+          vf_coeffs(G, sm + V.L.ca, sm + V.L.cb, sm + V.L.sc, end, bound, gg, tid & 31);
         }
         __syncthreads();
         LT(tC)
         dginit_next = sc[1];
-        vf_direction_tm(V, sc[0], tid);
+        vf_direction_tm(sm, N, V.tbase, sc[0], tid);
       } else {
         double* s = S + (size_t)end * ns;
         double* y = Y + (size_t)end * ns;
@@ -841,7 +846,8 @@ __device__ void lbfgs_run_fast(const VigoConst& C, VfCtx& V, tp_lbfgs_result& ou
         vf_gram_update(V, end, gbuf, tid);
         __syncthreads();
         LT(tG)
-        if ((tid >> 5) == V.serial_warp) vf_coeffs(V, sm + V.L.gram + (size_t)gbuf * VF_GRAM, end, bound, gg, tid & 31);
+        if ((tid >> 5) == V.serial_warp)
+          vf_coeffs(sm + V.L.gram + (size_t)gbuf * VF_GRAM, sm + V.L.ca, sm + V.L.cb, sm + V.L.sc, end, bound, gg, tid & 31);
         __syncthreads();
         LT(tC)
         const double cg = sc[0];

@@ -518,6 +518,9 @@ __device__ __forceinline__ void solve_one(const BatchView& bv, const VigoConst& 
   BatchView lbv = bv;                      // the outer-loop code reads control points through bv.ctrl + 3*off
   lbv.ctrl = cp - 3 * (size_t)st.off;
   Worker W = make_worker(C, P, s_slot, lane, &PS.as);
+#ifdef TP_LBFGS_TIMING
+  const long long pinit0 = clock64();
+#endif
   // ---- makePlan steps 1-3 (first pass only; a resumed trajectory continues its optimise / check / re-guide loop:
   // every optimize() starts from a fresh L-BFGS state, so splitting a solve at a round boundary changes nothing)
   if (!resume) {
@@ -530,7 +533,8 @@ __device__ __forceinline__ void solve_one(const BatchView& bv, const VigoConst& 
   int rounds_done = 0;
 #ifdef TP_LBFGS_TIMING
   long long ph[4] = {0, 0, 0, 0}, pt0 = clock64(), pt1;
-  const long long pstart = pt0;
+  const long long pstart = pinit0;
+  ph[0] = pt0 - pinit0;
 #define PH(i) { pt1 = clock64(); ph[i] += pt1 - pt0; pt0 = pt1; }
 #else
 #define PH(i)
@@ -593,7 +597,7 @@ __device__ __forceinline__ void solve_one(const BatchView& bv, const VigoConst& 
     PH(3)
   }
 #ifdef TP_LBFGS_TIMING
-  if (tid == 0 && st.lbfgs_iters > 1200)
+  if (tid == 0)
     printf("[solve] b %d N %d iters %d exp %d rounds %d | kcycles: total %lld init %lld lbfgs %lld collision %lld step %lld\n", b, N,
            st.lbfgs_iters, st.astar_expansions, rounds_done, (clock64() - pstart) / 1000, ph[0] / 1000, ph[1] / 1000, ph[2] / 1000, ph[3] / 1000);
 #endif
@@ -639,7 +643,7 @@ __device__ __forceinline__ void solve_one(const BatchView& bv, const VigoConst& 
 // every worker stays busy until the whole batch is drained.  Each class's list is ordered hardest-first.
 // cls_begin[5]: ranges of `order` per class (largest trajectories = class 0); cls_next[4]: atomic cursors.
 template <int MODE>
-__global__ void __launch_bounds__(TP_LB_THREADS, 4) k_solve(BatchView bv, VigoConst C, DevMap map, AStarPools P,
+__global__ void __launch_bounds__(TP_LB_THREADS, MODE == 3 ? 4 : 3) k_solve(const __grid_constant__ BatchView bv, const __grid_constant__ VigoConst C, const __grid_constant__ DevMap map, const __grid_constant__ AStarPools P,
                                                             const int* __restrict__ order, const int* __restrict__ cls_begin,
                                                             int* cls_next, int my_class, int class_max_n,
                                                             int* slot_flags, double* counters, long long* timeline,
