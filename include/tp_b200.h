@@ -256,6 +256,16 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
 int64_t tp_vigo_frontend_batch(const tp_map_t* m, const tp_vigo_params* p, int32_t B, const double* starts,
                                const double* goals, int32_t* offsets_out, double* ctrl_out, int64_t ctrl_cap,
                                uint8_t* valid);
+/* The same front end as ONE CUDA kernel (one warp per pair): seed KKT solve, resampling loop,
+ * inputPathCheck, updatePath and the least-squares B-spline fit (bspline.cpp:74-138) on the device, so that a batch of
+ * raw (start, goal) pairs never leaves HBM between the front end and tp_vigo_make_plan_batch (mem = TP_MEM_DEVICE:
+ * every pointer is device memory; TP_MEM_HOST: host buffers, copies inside).  Same operation order as the host
+ * version: control points are bit-identical wherever glibc's pow() is correctly rounded.  Paths that need more than
+ * 1024 samples per resampling pass or more than 160 points after inputPathCheck are reported invalid.
+ * Returns total control points or <0. */
+int64_t tp_vigo_frontend_batch_device(tp_engine_t* e, const tp_vigo_params* p, int32_t B, const double* starts,
+                                      const double* goals, int32_t* offsets_out, double* ctrl_out, int64_t ctrl_cap,
+                                      uint8_t* valid, int mem, void* stream);
 /* bsplineTraj::inputPathCheck (bsplineTraj.cpp:207-245): returns 1 when consecutive points are already
  * <= 1.5 * ctrl_pt_dist apart, 0 otherwise; `adjusted` (may be NULL) receives the adjusted path. */
 int tp_vigo_input_path_check(const tp_map_t* m, const tp_vigo_params* p, int32_t K, const double* path, double* adjusted,

@@ -532,3 +532,49 @@ def test_make_plan_on_octomap_rasters_strict_bit_faithful(tp, orc, name):
             assert not pl.has_collision(), b
     assert abs((res2["status"] == 1).mean() - st_o["success"].mean()) <= 0.15
     e.close()
+
+
+@pytest.mark.gpu
+def test_device_front_end_matches_host_and_oracle(tp, engine, orc, sq_map, sq_omap):
+    """(start, goal) pairs -> initial control points on the device (tp_vigo_frontend_batch_device, one warp per pair)
+    vs the host C++ front end (same operation order: bit-identical up to pow() roundings) and the numpy restatement
+    of src/bspline_node.cpp:332-371 / bsplineTraj.cpp:207-323 / bspline.cpp:74-138 (oracle/frontend_np.py, 1e-9)."""
+    from helpers import random_pairs
+    from oracle import frontend_np
+    rng = np.random.default_rng(7)
+    p = tp.default_params()
+    S, G = random_pairs(sq_omap, 400, rng, min_dist=0.05)
+    # edge cases: goal inside an obstacle, start == goal, very short and very long paths (max_path_length cut)
+    occ = np.argwhere(sq_map.grid("inflated") != 0)
+    info = sq_map.info()
+    bad_goal = np.array(info["origin"]) + (occ[len(occ) // 2] + 0.5) * info["res"]
+    S = np.vstack([S, S[:1], S[1:2], [[-9.4, -9.4, 1.0]], [[-9.4, 9.4, 1.0]]])
+    G = np.vstack([G, bad_goal[None], S[1:2], [[9.4, 9.4, 1.0]], [[9.4, -9.4, 1.0]]])
+    off_h, ctrl_h, valid_h = tp.frontend_batch(sq_map, p, S, G)
+    off_d, ctrl_d, valid_d = engine.frontend_batch(p, S, G)
+    assert np.array_equal(valid_h, valid_d)
+    assert np.array_equal(off_h, off_d)
+    assert valid_d[-4] == 0 and valid_d[-3] == 0
+    d = np.abs(ctrl_h - ctrl_d)
+    print(f"device vs host front end: {len(S)} pairs, {int(valid_d.sum())} valid, {off_d[-1]} control points, "
+          f"max |diff| {d.max():.3e}, bit-identical {float(np.mean(d == 0)):.4f}")
+    assert d.max() <= 1e-12
+    for b in list(range(0, 40)) + [len(S) - 2, len(S) - 1]:
+        want = frontend_np.start_goal_to_ctrl(S[b], G[b], sq_omap)
+        got = ctrl_d[off_d[b]:off_d[b + 1]]
+        if want is None:
+            assert len(got) == 0
+        else:
+            assert got.shape == want.shape and np.max(np.abs(got - want)) <= 1e-9
+    # the device front end feeds the solve: same makePlan result as from the host front end
+    keep = [b for b in range(len(S)) if valid_d[b] and off_d[b + 1] - off_d[b] >= 7][:64]
+    offs = np.concatenate([[0], np.cumsum([off_d[b + 1] - off_d[b] for b in keep])]).astype(np.int32)
+    cd = np.concatenate([ctrl_d[off_d[b]:off_d[b + 1]] for b in keep])
+    ch = np.concatenate([ctrl_h[off_h[b]:off_h[b + 1]] for b in keep])
+    p.strict_order = 1
+    out_d, res_d = engine.make_plan_batch(p, offs, cd)
+    out_h, res_h = engine.make_plan_batch(p, offs, ch)
+    same = [b for b in range(len(keep)) if np.array_equal(cd[offs[b]:offs[b + 1]], ch[offs[b]:offs[b + 1]])]
+    assert len(same) >= 0.9 * len(keep)
+    for b in same:
+        assert np.array_equal(out_d[offs[b]:offs[b + 1]], out_h[offs[b]:offs[b + 1]]) and res_d["status"][b] == res_h["status"][b]

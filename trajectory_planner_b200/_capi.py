@@ -77,7 +77,7 @@ SYMBOLS = [
     "tp_engine_set_map", "tp_engine_synchronize", "tp_engine_launch_count", "tp_engine_stream",
     "tp_vigo_default_params", "tp_query_points", "tp_query_unknown", "tp_query_lines", "tp_vigo_cost_batch",
     "tp_vigo_optimize_batch", "tp_vigo_has_collision_batch", "tp_vigo_find_collision_seg_batch", "tp_astar_batch",
-    "tp_vigo_init_guides_batch", "tp_vigo_make_plan_batch", "tp_vigo_frontend_batch", "tp_vigo_input_path_check", "tp_vigo_update_path", "tp_bspline_fit",
+    "tp_vigo_init_guides_batch", "tp_vigo_make_plan_batch", "tp_vigo_frontend_batch", "tp_vigo_frontend_batch_device", "tp_vigo_input_path_check", "tp_vigo_update_path", "tp_bspline_fit",
     "tp_bspline_eval", "tp_engine_profile_enable", "tp_engine_profile_get", "tp_microbench_fp64",
     "tp_microbench_gather", "tp_poly_default_params", "tp_minsnap_solve_batch", "tp_poly_check_batch",
     "tp_poly_box_collision", "tp_polytraj_make_plan_batch",
@@ -144,6 +144,8 @@ def load():
     L.tp_vigo_make_plan_batch.argtypes = [vp, PP, C.c_int32, vp, vp, vp, vp, C.c_int32, vp, vp, vp, C.c_int, vp]
     L.tp_vigo_frontend_batch.restype = C.c_int64
     L.tp_vigo_frontend_batch.argtypes = [vp, PP, C.c_int32, vp, vp, vp, vp, C.c_int64, vp]
+    L.tp_vigo_frontend_batch_device.restype = C.c_int64
+    L.tp_vigo_frontend_batch_device.argtypes = [vp, PP, C.c_int32, vp, vp, vp, vp, C.c_int64, vp, C.c_int, vp]
     L.tp_vigo_input_path_check.argtypes = [vp, PP, C.c_int32, vp, vp, C.c_int32, vp]
     L.tp_vigo_update_path.argtypes = [vp, PP, C.c_int32, vp, vp, vp, C.c_int32]
     L.tp_bspline_fit.argtypes = [C.c_double, C.c_int32, vp, vp, vp]

@@ -330,6 +330,20 @@ class Engine:
                             v=g_v[b, :n].copy()))
         return out
 
+    # ---- front end on the device: (start, goal) pairs -> initial control points (src/bspline_node.cpp:332-371)
+    def frontend_batch(self, params, starts, goals):
+        """Same contract as the module-level (host) frontend_batch, computed by one CUDA kernel on this engine's map."""
+        starts, goals = _f64(starts).reshape(-1, 3), _f64(goals).reshape(-1, 3)
+        B = len(starts)
+        cap = 162 * max(B, 1)
+        off = np.zeros(B + 1, np.int32)
+        ctrl = np.zeros((cap, 3))
+        valid = np.zeros(B, np.uint8)
+        n = self.L.tp_vigo_frontend_batch_device(self.h, C.byref(params), B, ptr(starts), ptr(goals), ptr(off), ptr(ctrl), cap,
+                                                 ptr(valid), TP_MEM_HOST, None)
+        check(int(n), "tp_vigo_frontend_batch_device")
+        return off, ctrl[:n].copy(), valid
+
     # ---- the batched entry point
     def make_plan_batch(self, params, offsets, ctrl, dyn=None):
         """Host buffers in, host buffers out (H2D + solve + D2H inside the call)."""

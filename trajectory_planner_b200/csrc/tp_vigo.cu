@@ -10,6 +10,7 @@
 
 #include "tp_lbfgs.cuh"
 #include "tp_lbfgs_fast.cuh"
+#include "tp_frontend.cuh"
 #include "tp_map.h"
 #include "tp_outer.cuh"
 
@@ -1802,6 +1803,74 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
     CK(cudaStreamSynchronize(s));
   }
   return TP_OK;
+}
+
+// ---- front end on the device: (start, goal) pairs -> ragged initial control points
+int64_t tp_vigo_frontend_batch_device(tp_engine_t* e, const tp_vigo_params* p, int32_t B, const double* starts, const double* goals,
+                                      int32_t* offsets_out, double* ctrl_out, int64_t ctrl_cap, uint8_t* valid, int mem,
+                                      void* stream) {
+  if (!e || !p || B < 0 || !starts || !goals || !offsets_out || !ctrl_out) return TP_ERR_INVALID_ARG;
+  int rc = check_params(e, p);
+  if (rc != TP_OK) return rc;
+  CK(cudaSetDevice(e->device));
+  cudaStream_t s = pick_stream(e, stream);
+  if (B == 0) {
+    const int32_t zero = 0;
+    if (mem == TP_MEM_HOST) offsets_out[0] = 0;
+    else CK(cudaMemcpyAsync(offsets_out, &zero, 4, cudaMemcpyHostToDevice, s));
+    return 0;
+  }
+  const size_t stride = (size_t)(FE_KMAX + 2) * 3;
+  // scratch_a: [starts | goals] (host mode), scratch_b: per-problem control points, scratch_c: counts + offsets + valid
+  if (e->scratch_b.ensure((size_t)B * stride * 8) != TP_OK || e->scratch_c.ensure((size_t)B * 9 + 64) != TP_OK) return TP_ERR_CUDA;
+  const double *ds = starts, *dg = goals;
+  if (mem == TP_MEM_HOST) {
+    if (e->scratch_a.ensure((size_t)B * 48) != TP_OK) return TP_ERR_CUDA;
+    CK(cudaMemcpyAsync(e->scratch_a.p, starts, (size_t)B * 24, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(e->scratch_a.as<double>() + 3 * (size_t)B, goals, (size_t)B * 24, cudaMemcpyHostToDevice, s));
+    ds = e->scratch_a.as<double>();
+    dg = ds + 3 * (size_t)B;
+  }
+  int* d_count = e->scratch_c.as<int>();
+  int* d_off = d_count + B;
+  unsigned char* d_valid = reinterpret_cast<unsigned char*>(d_off + B + 1);
+  static bool attr = false;
+  if (!attr) {
+    CK(cudaFuncSetAttribute(k_frontend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FeSmem)));
+    attr = true;
+  }
+  const int grid = std::min(B, e->sm_count * 5);
+  {
+    ProfScope ps(e, 3, s, grid);
+    k_frontend<<<grid, 32, sizeof(FeSmem), s>>>(e->dmap, *p, B, ds, dg, e->scratch_b.as<double>(), d_count);
+  }
+  int* off_dst = mem == TP_MEM_DEVICE ? offsets_out : d_off;
+  k_fe_scan<<<1, 1024, 0, s>>>(d_count, B, off_dst);
+  e->launches += 2;
+  CK(cudaGetLastError());
+  int32_t total = 0;
+  CK(cudaMemcpyAsync(&total, off_dst + B, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if ((int64_t)total > ctrl_cap) {
+    tp_set_error("tp_vigo_frontend_batch_device: ctrl_cap %lld < %d control points", (long long)ctrl_cap, total);
+    return TP_ERR_CAPACITY;
+  }
+  double* ctrl_dst = ctrl_out;
+  if (mem == TP_MEM_HOST) {
+    if (e->ctrl.ensure((size_t)std::max(total, 1) * 24) != TP_OK) return TP_ERR_CUDA;
+    ctrl_dst = e->ctrl.as<double>();
+  }
+  unsigned char* valid_dst = mem == TP_MEM_DEVICE ? valid : d_valid;
+  k_fe_gather<<<B, 64, 0, s>>>(e->scratch_b.as<double>(), off_dst, B, ctrl_dst, (long)ctrl_cap, valid_dst);
+  e->launches += 1;
+  CK(cudaGetLastError());
+  if (mem == TP_MEM_HOST) {
+    CK(cudaMemcpyAsync(offsets_out, d_off, (size_t)(B + 1) * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ctrl_out, ctrl_dst, (size_t)total * 24, cudaMemcpyDeviceToHost, s));
+    if (valid) CK(cudaMemcpyAsync(valid, d_valid, (size_t)B, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  return total;
 }
 
 // ---- measurement
