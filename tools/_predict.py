@@ -12,14 +12,19 @@ tl = np.fromfile("/tmp/tl.bin", dtype=np.int64).reshape(-1, 4)
 dur = (tl[:,1]-tl[:,0])/1e6
 hit = eng.has_collision_batch(p, off, out0)
 print("after round 0: colliding %.3f, astar-fail %.3f" % (hit.mean(), (r0['status']==0).mean()))
+eng_key = np.array([0.0]*len(N))
+try:
+    eng_key = eng.query_points(ctrl).astype(float)
+    eng_key = np.array([eng_key[off[b]:off[b+1]].sum() for b in range(len(N))])
+except Exception as ex: print('key failed', ex)
 feats = dict(N=N.astype(float), iters0=r0['lbfgs_iters'].astype(float), exp0=r0['astar_expansions'].astype(float), pairs0=r0['n_guide_pairs'].astype(float),
-             hit0=hit.astype(float), cost0=r0['final_cost'], combo=hit*(r0['lbfgs_iters']+0.3*r0['astar_expansions']+5*r0['n_guide_pairs']) )
-def makespan(order, d, P=520):
+             hit0=hit.astype(float), cost0=r0['final_cost'], key=eng_key, exp_or_key=r0['astar_expansions'].astype(float)+50*eng_key, hard=(r0['astar_expansions']>1500).astype(float)*1e6+eng_key, combo=hit*(r0['lbfgs_iters']+0.3*r0['astar_expansions']+5*r0['n_guide_pairs']) )
+def makespan(order, d, P=444):
     h=[0.0]*P; heapq.heapify(h); end=0
     for i in order:
         t=heapq.heappop(h); t2=t+d[i]; end=max(end,t2); heapq.heappush(h,t2)
     return end
-print("sum/P %.1f max %.1f" % (dur.sum()/520, dur.max()))
+print("sum/P %.1f max %.1f" % (dur.sum()/444, dur.max()))
 for k,f in feats.items():
     print("%-8s corr %.2f  simulated makespan %.1f ms" % (k, np.corrcoef(f,dur)[0,1], makespan(np.argsort(-f,kind='stable'), dur)))
 print("oracle order makespan %.1f" % makespan(np.argsort(-dur), dur))

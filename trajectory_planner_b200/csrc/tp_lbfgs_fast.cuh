@@ -392,31 +392,43 @@ __device__ __noinline__ void vf_coeffs(double* G, double* ca, double* cb, double
   const double inv_i = i == 0 ? inv0 : G[VF_G_INV + i];     // 0 for pairs not stored yet
   const double sg_i = G[VF_G_SG + i], yg_i = G[VF_G_YG + i];
   // Both recurrences run on ROW-SCALED quantities (r_i / ys_i, (y_i.d) / ys_i) so that the value a step broadcasts is
-  // a lane's running value itself: per step one register shuffle + one FMA on the dependent chain.
+  // a lane's running value itself, and on matrix rows preloaded into registers (masked to the strict triangle): per
+  // step ONE register shuffle + ONE FMA on the dependent chain.  All 16 steps always run: entries of pairs not
+  // stored yet are zero (so are their 1/ys), which makes their steps no-ops.
+  (void)bound;
+  double lo[VF_M];   // lo[a] = (s_i.y_a) / ys_i for a < i (pair i older than pair a), else 0
+#pragma unroll
+  for (int a = 0; a < VF_M; ++a) lo[a] = i > a ? SY[i * VF_GS + a] * inv_i : 0.0;
   // ---- first loop, newest -> oldest: alpha_a = (s_a.q)/ys_a; q -= alpha_a y_a  (q starts at -g)
   double rr = -sg_i * inv_i;
   double al = 0.0;
-  for (int a = 0; a < bound; ++a) {
+#pragma unroll
+  for (int a = 0; a < VF_M; ++a) {
     const double ala = __shfl_sync(FULL, rr, a);
-    const double l = SY[i * VF_GS + a] * inv_i;
     if (i == a) al = ala;
-    if (i > a) rr = fma(-ala, l, rr);
+    rr = fma(-ala, lo[a], rr);
   }
   // ---- acc_i = y_i.(gamma q) = -gamma (y_i.g + sum_a alpha_a y_i.y_a)
   if (lane < VF_M) tb[i] = al;
+  double up[VF_M];   // up[j] = (s_j.y_i) / ys_i for j > i, else 0
+#pragma unroll
+  for (int j = 0; j < VF_M; ++j) up[j] = i < j ? SY[j * VF_GS + i] * inv_i : 0.0;
   __syncwarp();
-  double t0 = yg_i, t1 = 0.0;
-  for (int a = 0; a < bound; a += 2) {
+  double t0 = yg_i, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+#pragma unroll
+  for (int a = 0; a < VF_M; a += 4) {
     t0 = fma(tb[a], YY[i * VF_GS + a], t0);
-    t1 = fma(tb[a + 1], YY[i * VF_GS + a + 1], t1);   // tb / YY of a pair not stored yet are zero
+    t1 = fma(tb[a + 1], YY[i * VF_GS + a + 1], t1);
+    t2 = fma(tb[a + 2], YY[i * VF_GS + a + 2], t2);
+    t3 = fma(tb[a + 3], YY[i * VF_GS + a + 3], t3);
   }
   // ---- second loop, oldest -> newest: beta_j = (y_j.d)/ys_j; d += (alpha_j - beta_j) s_j; accp_i = (y_i.d)/ys_i
-  double accp = (-gamma * (t0 + t1)) * inv_i;
-  for (int j = bound - 1; j >= 0; --j) {
+  double accp = (-gamma * ((t0 + t1) + (t2 + t3))) * inv_i;
+#pragma unroll
+  for (int j = VF_M - 1; j >= 0; --j) {
     const double bj = __shfl_sync(FULL, accp, j);   // final for pair j: later steps only touch i < j
-    const double l = SY[j * VF_GS + i] * inv_i;
-    const double u = fma(tb[j], l, accp);            // off the dependent chain
-    if (i < j) accp = fma(-bj, l, u);
+    const double u = fma(tb[j], up[j], accp);        // off the dependent chain
+    accp = fma(-bj, up[j], u);
   }
   const double aa = al - accp;
   const bool mine = lane < VF_M && i < bound;

@@ -470,6 +470,17 @@ __global__ void __launch_bounds__(32) k_plan_init(BatchView bv, VigoConst C, Dev
 // and the A* heap / tables alias each other (they are never live at the same time).
 // Blocks are issued longest trajectory first (`order`); the launch is per size class so that the
 // shared-memory footprint (and with it the blocks resident per SM) follows the trajectories' length.
+// Parked trajectories of one batch (see k_solve): per size class a list of ids (filled with -1 before the launch),
+// its tail (slots handed out), its head (slots claimed) and the number of trajectories that finished phase A.
+struct ParkQueue {
+  int* list;       // [4][stride]
+  int* tail;       // [4]
+  int* head;       // [4]
+  int* started;    // [4]
+  int stride;
+  int thresh;      // park when the initial searches took fewer A* expansions than this; < 0: parking disabled
+};
+
 struct SolveLayout {
   int st;      // TrajState (doubles offset)
   int vf;      // start of the solver region (cp first)
@@ -493,10 +504,12 @@ __host__ __device__ inline SolveLayout solve_layout(int N, int mode, int m) {
   return L;
 }
 
+// Returns 1 when the trajectory was PARKED after makePlan steps 1-3 (park_thresh >= 0 and its first A* searches took
+// fewer than park_thresh expansions): its state is back in HBM and a later solve_one(resume = 1) finishes it.
 template <int MODE>
-__device__ __forceinline__ void solve_one(const BatchView& bv, const VigoConst& C, const DevMap& map, const AStarPools& P,
-                                          int b, int class_max_n, int s_slot, int sw, uint32_t tbase, double* counters,
-                                          long long* timeline, int resume, int rounds_this_pass, double* sm) {
+__device__ __forceinline__ int solve_one(const BatchView& bv, const VigoConst& C, const DevMap& map, const AStarPools& P,
+                                         int b, int class_max_n, int s_slot, int sw, uint32_t tbase, double* counters,
+                                         long long* timeline, int resume, int rounds_this_pass, int park_thresh, double* sm) {
   const int tid = threadIdx.x, lane = tid & 31;
   long long t_start = 0;
   if (timeline && tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start));
@@ -530,6 +543,16 @@ __device__ __forceinline__ void solve_one(const BatchView& bv, const VigoConst& 
     W.flood_trigger = TP_FLOOD_TRIGGER_AGAIN;
   }
   __syncthreads();
+  if (!resume && park_thresh >= 0 && st.status == TS_ACTIVE && st.astar_expansions < park_thresh && !st.astar_unreach) {
+    // an easy start: park it (state only — the control points have not changed) and let the worker look for the
+    // batch's hard trajectories first; whoever drains the parked list resumes it at the optimise / check loop
+    const int* src = reinterpret_cast<const int*>(&st);
+    int* dst = reinterpret_cast<int*>(&bv.st[b]);
+    for (int i = tid; i < (int)(sizeof(TrajState) / 4); i += TP_LB_THREADS) dst[i] = src[i];
+    if (timeline && tid == 0) timeline[4 * (size_t)b] = t_start;
+    __syncthreads();
+    return 1;
+  }
   double fl = 0.0, its = 0.0, evs = 0.0, smp = 0.0;
   int rounds_done = 0;
 #ifdef TP_LBFGS_TIMING
@@ -648,7 +671,7 @@ __global__ void __launch_bounds__(TP_LB_THREADS, MODE == 3 ? 4 : 3) k_solve(cons
                                                             const int* __restrict__ order, const int* __restrict__ cls_begin,
                                                             int* cls_next, int my_class, int class_max_n,
                                                             int* slot_flags, double* counters, long long* timeline,
-                                                            int resume, int rounds_this_pass) {
+                                                            int resume, int rounds_this_pass, ParkQueue park) {
   extern __shared__ double sm[];
   const int tid = threadIdx.x;
   const SolveLayout SL = solve_layout(class_max_n, MODE, C.p.lbfgs_m);
@@ -671,20 +694,56 @@ __global__ void __launch_bounds__(TP_LB_THREADS, MODE == 3 ? 4 : 3) k_solve(cons
   __syncthreads();
   const int s_slot = pick[1] & 0xFFFFFF;
   const int sw = (pick[1] >> 24) & (TP_LB_WARPS - 1);
+  // ---- phase A: the class queues, hardest-looking first.  A trajectory whose makePlan steps 1-3 turn out cheap (few A*
+  // expansions) is parked after them; one that starts with long searches — the batch's tail if it started late — is
+  // solved to the end right away.
+  // ---- phase B (main queues drained): resume the parked trajectories, own class first, then the classes of shorter
+  // ones.  A claimed slot that is not filled yet is waited for while phase A is still running somewhere; once every
+  // trajectory of the class has been through phase A the list is final and slots beyond its end are given up.
+  int pb_class = -1;   // thread 0: >= 0 once this worker is in phase B
   for (;;) {
     if (tid == 0) {
-      int b = -1;
-      for (int c = my_class; c < 4 && b < 0; ++c) {
-        if (cls_begin[c + 1] == cls_begin[c]) continue;
-        const int i = cls_begin[c] + atomicAdd(&cls_next[c], 1);
-        if (i < cls_begin[c + 1]) b = order[i];
+      int b = -1, cc = 0, res = resume;
+      if (pb_class < 0) {
+        for (int c = my_class; c < 4 && b < 0; ++c) {
+          if (cls_begin[c + 1] == cls_begin[c]) continue;
+          const int i = cls_begin[c] + atomicAdd(&cls_next[c], 1);
+          if (i < cls_begin[c + 1]) { b = order[i]; cc = c; }
+        }
+        if (b < 0 && park.thresh >= 0) pb_class = my_class;
+      }
+      while (b < 0 && pb_class >= 0 && pb_class < 4) {
+        const int c = pb_class, csize = cls_begin[c + 1] - cls_begin[c];
+        if (csize == 0) { ++pb_class; continue; }
+        const int i = atomicAdd(&park.head[c], 1);
+        for (;;) {
+          b = *((volatile int*)&park.list[(size_t)c * park.stride + i]);
+          if (b >= 0) break;
+          if (*((volatile int*)&park.started[c]) >= csize && i >= *((volatile int*)&park.tail[c])) { b = -1; break; }
+          __nanosleep(200);
+        }
+        if (b < 0) ++pb_class;
+        else { __threadfence(); res = 1; cc = c; }
       }
       pick[0] = b;
+      pick[3] = cc | (res << 8);
     }
     __syncthreads();
     const int b = pick[0];
     if (b < 0) break;
-    solve_one<MODE>(bv, C, map, P, b, class_max_n, s_slot, sw, tbase, counters, timeline, resume, rounds_this_pass, sm);
+    const int res = pick[3] >> 8;
+    const int parked = solve_one<MODE>(bv, C, map, P, b, class_max_n, s_slot, sw, tbase, counters, timeline, res, rounds_this_pass,
+                                       res ? -1 : park.thresh, sm);
+    if (park.thresh >= 0 && !res && tid == 0) {
+      const int cc = pick[3] & 255;
+      if (parked) {
+        const int pos = atomicAdd(&park.tail[cc], 1);
+        __threadfence();                                  // the trajectory's state is in HBM before its id shows up
+        atomicExch(&park.list[(size_t)cc * park.stride + pos], b);
+      }
+      __threadfence();
+      atomicAdd(&park.started[cc], 1);                    // makePlan steps 1-3 of one more trajectory of class cc are done
+    }
   }
   if (tid == 0) {
     __threadfence();
@@ -833,7 +892,7 @@ struct tp_engine {
   bool solve_attr_set = false;
   int pools_key[8] = {0};
   // batch buffers
-  DevBuf off, ctrl, st, pairs, cp_head, cp_tail, active[2], counters, results, dyn, scratch_a, scratch_b, scratch_c;
+  DevBuf off, ctrl, st, pairs, cp_head, cp_tail, active[2], counters, results, dyn, scratch_a, scratch_b, scratch_c, parkq;
   int* h_counters = nullptr;  // pinned
   // pinned staging for host-memory calls
   void* h_stage = nullptr;
@@ -1263,7 +1322,7 @@ void tp_engine_destroy(tp_engine_t* e) {
   DevBuf* bufs[] = {&e->map_occ, &e->poly_scratch, &e->poly_tacc, &e->map_infl, &e->map_known, &e->t_check, &e->t_reparam, &e->a_line, &e->pool_nodes, &e->pool_heaps, &e->pool_heapn,
                     &e->pool_paths, &e->pool_sc, &e->pool_sclen, &e->pool_rounds, &e->pool_flags, &e->off, &e->ctrl, &e->st, &e->pairs,
                     &e->cp_head, &e->cp_tail, &e->active[0], &e->active[1], &e->counters, &e->results, &e->dyn,
-                    &e->scratch_a, &e->scratch_b, &e->scratch_c};
+                    &e->scratch_a, &e->scratch_b, &e->scratch_c, &e->parkq};
   for (DevBuf* b : bufs) b->release();
   if (e->h_counters) cudaFreeHost(e->h_counters);
   if (e->h_stage) cudaFreeHost(e->h_stage);
@@ -1734,6 +1793,23 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
     CK(cudaMemcpyAsync(d_cb, h_cb, 9 * 4, cudaMemcpyHostToDevice, s));
     CK(cudaEventRecord(e->ev_stage, s));
     e->stage_busy = true;
+    // parking (k_solve phases A / B): only when the batch outnumbers the resident workers — otherwise every trajectory
+    // starts at once anyway — and only for whole solves
+    ParkQueue pq;
+    pq.list = nullptr; pq.tail = pq.head = pq.started = nullptr; pq.stride = M; pq.thresh = -1;
+    {
+      static const int park_env = getenv("TP_PARK_THRESH") ? atoi(getenv("TP_PARK_THRESH")) : 1500;
+      int workers_total = 0;
+      for (int c = 0; c < 4; ++c) workers_total += best[c] * e->sm_count;
+      if (park_env >= 0 && !resume && rounds == 0x7fffffff && M > workers_total) {
+        if (e->parkq.ensure(((size_t)4 * M + 16) * 4) != TP_OK) return TP_ERR_CUDA;
+        int* base = e->parkq.as<int>();
+        CK(cudaMemsetAsync(base, 0, 16 * 4, s));
+        CK(cudaMemsetAsync(base + 16, 0xFF, (size_t)4 * M * 4, s));
+        pq.tail = base; pq.head = base + 4; pq.started = base + 8; pq.list = base + 16;
+        pq.thresh = park_env;
+      }
+    }
     CK(cudaEventRecord(e->ev_fork, s));
     int used = 0;
     for (int c = 0; c < 4; ++c) {
@@ -1746,10 +1822,10 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
       {
         ProfScope ps(e, 0, cs, grid);
         const int* ord = e->active[0].as<int>();
-        if (mode == 1) k_solve<1><<<grid, TP_LB_THREADS, smem[c], cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, d_cb, d_cb + 5, c, nmax[c], e->pool_flags.as<int>(), e->counters_ptr(), tl, resume, rounds);
-        else if (mode == 2) k_solve<2><<<grid, TP_LB_THREADS, smem[c], cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, d_cb, d_cb + 5, c, nmax[c], e->pool_flags.as<int>(), e->counters_ptr(), tl, resume, rounds);
-        else if (mode == 3) k_solve<3><<<grid, TP_LB_THREADS, smem[c], cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, d_cb, d_cb + 5, c, nmax[c], e->pool_flags.as<int>(), e->counters_ptr(), tl, resume, rounds);
-        else k_solve<0><<<grid, TP_LB_THREADS, smem[c], cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, d_cb, d_cb + 5, c, nmax[c], e->pool_flags.as<int>(), e->counters_ptr(), tl, resume, rounds);
+        if (mode == 1) k_solve<1><<<grid, TP_LB_THREADS, smem[c], cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, d_cb, d_cb + 5, c, nmax[c], e->pool_flags.as<int>(), e->counters_ptr(), tl, resume, rounds, pq);
+        else if (mode == 2) k_solve<2><<<grid, TP_LB_THREADS, smem[c], cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, d_cb, d_cb + 5, c, nmax[c], e->pool_flags.as<int>(), e->counters_ptr(), tl, resume, rounds, pq);
+        else if (mode == 3) k_solve<3><<<grid, TP_LB_THREADS, smem[c], cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, d_cb, d_cb + 5, c, nmax[c], e->pool_flags.as<int>(), e->counters_ptr(), tl, resume, rounds, pq);
+        else k_solve<0><<<grid, TP_LB_THREADS, smem[c], cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, d_cb, d_cb + 5, c, nmax[c], e->pool_flags.as<int>(), e->counters_ptr(), tl, resume, rounds, pq);
       }
       CK(cudaGetLastError());
       CK(cudaEventRecord(e->ev_join[used], cs));
