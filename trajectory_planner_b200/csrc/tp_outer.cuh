@@ -196,9 +196,16 @@ struct Heap {
 // it.  The component is flooded with a lane-per-cell worklist over two bitmaps that temporarily
 // take over the heap's shared memory (the heap is parked in the tail of its HBM spill area).
 // Returns -1 when the goal is reachable (the search resumes), else the component size.
-#define TP_FLOOD_TRIGGER 4096       // expansions after which a search checks reachability
+#ifndef TP_FLOOD_TRIGGER
+#define TP_FLOOD_TRIGGER 2048       // expansions after which a search checks reachability (a flood costs about as much as 500)
+#endif
 #define TP_FLOOD_TRIGGER_AGAIN 192  // ... once this trajectory has already had an unreachable goal
-#define TP_FLOOD_CAND (32 * 26)
+#define TP_FLOOD_ROUND (32 * 26)    // cells one round can add to the worklist
+// The flood runs on ONE shared-memory bitmap F over the pool's stored cells (bit (i PY + j) KL + kk): first every
+// enterable free cell is marked (one coalesced pass over the map words of the window, lane per (i, j) column — no map
+// gather inside the flood itself), then a lane-per-cell worklist claims neighbours by clearing their bits
+// (atomicAnd: a cell is enqueued exactly once).  F, the counters and the worklist ring take over the heap's shared
+// memory; the heap is parked in the tail of its HBM spill area meanwhile.
 __device__ __noinline__ int flood_component(const DevMap& map, const VigoConst& C, Worker& W, int heap_size, int si, int sj, int sk,
                                int ei, int ej, int ek, int k_lo) {
   AStarSmem& S = *W.sm;
@@ -206,100 +213,192 @@ __device__ __noinline__ int flood_component(const DevMap& map, const VigoConst& 
   const int PX = C.pool[0], PY = C.pool[1], PZ = C.pool[2], KL = C.pool_kl;
   const int ncell = PX * PY * KL;
   const int nw = (ncell + 31) >> 5;
-  // shared-memory plan (the heap's 24 KB): V bitmap [nw] | head, tail, ncand, pad | candidates | worklist ring Q[qcap]
-  uint32_t* V = reinterpret_cast<uint32_t*>(S.hk);   // seen: visited-free or known-blocked
-  volatile uint32_t* ctr = V + nw;                    // [0] head, [1] tail (monotonic), [2] candidates of this round
-  uint32_t* cand = V + nw + 4;                        // packed (i << 16 | j << 8 | kk) neighbours to look up
-  uint32_t* Q = cand + TP_FLOOD_CAND;                 // packed cells waiting to be expanded
-  const int qcap = (int)((sizeof(S.hk) + sizeof(S.hn)) / 4) - nw - 4 - TP_FLOOD_CAND;
-  if (qcap < 2 * TP_FLOOD_CAND || C.heap_cap < 3 * TP_HEAP_SMEM) return -1;
+  uint32_t* F = reinterpret_cast<uint32_t*>(S.hk);   // [nw + 1] (one spare word: two-word window reads)
+  uint32_t* Q = F + nw + 1 + 4;                       // worklist ring of packed cells (i << 16 | j << 8 | kk)
+  const int qcap = (int)((sizeof(S.hk) + sizeof(S.hn)) / 4) - nw - 5;
+  if (qcap < 2 * TP_FLOOD_ROUND || KL > 30 || C.heap_cap < 3 * TP_HEAP_SMEM) return -1;
   // park the heap
   const int keep = heap_size < TP_HEAP_SMEM ? heap_size : TP_HEAP_SMEM;
   double* pk = W.heap_k_gl + (C.heap_cap - TP_HEAP_SMEM);
   uint32_t* pn = W.heap_n_gl + (C.heap_cap - TP_HEAP_SMEM);
   for (int i = lane; i < keep; i += 32) { pk[i] = S.hk[i]; pn[i] = S.hn[i]; }
   __syncwarp();
-  for (int i = lane; i < nw + 4; i += 32) V[i] = 0u;
+  for (int i = lane; i < nw + 5; i += 32) F[i] = 0u;
   __syncwarp();
   const int klo_c = k_lo > 1 ? k_lo : 1;                                  // neighbour layers that can be entered
   const int khi_c = (k_lo + KL - 1) < (PZ - 2) ? (k_lo + KL - 1) : (PZ - 2);
-  // One round = up to 32 cells.  Phase 1 (lane per cell): bit tests only, unseen enterable neighbours go to the
-  // shared candidate list.  Phase 2 (lane per candidate, balanced across the warp): one map gather + one atomicOr
-  // each; first-time free cells join the worklist.
-  auto round = [&](int ci, int cj, int ck, bool valid) {
-    if (valid) {
-      uint32_t mine[26];
-      int nm = 0;
-      for (int dx = -1; dx <= 1; ++dx) {
-        const int ni = ci + dx;
-        if (ni < 1 || ni >= PX - 1) continue;
-        for (int dy = -1; dy <= 1; ++dy) {
-          const int nj = cj + dy;
-          if (nj < 1 || nj >= PY - 1) continue;
-          const int b0 = (ni * PY + nj) * KL - k_lo;
-          for (int dz = -1; dz <= 1; ++dz) {
-            const int nk = ck + dz;
-            if (nk < klo_c || nk > khi_c || !S.band[nk]) continue;
-            if (dx == 0 && dy == 0 && dz == 0) continue;
-            if (ni == si && nj == sj && nk == sk) continue;
-            const int b = b0 + nk;
-            if ((V[b >> 5] >> (b & 31)) & 1u) continue;
-            mine[nm++] = ((uint32_t)ni << 16) | ((uint32_t)nj << 8) | (uint32_t)(nk - k_lo);
-          }
+#ifdef TP_ASTAR_TIMING
+  const long long tz0 = clock64();
+#endif
+  // ---- F = enterable (astarOcc.cpp:181-202: inside the pool's interior and the height band) and free in the map,
+  // the start cell excluded (it is never re-opened).  Per layer kk: the map's z index and whether the layer can be
+  // entered at all (lane-invariant, so evaluated once); fast path when the layers map to consecutive bits of one word.
+  uint32_t layer_ok = 0;
+  int iz0 = -1;
+  bool affine = true;
+  for (int kk = 0; kk < KL; ++kk) {
+    const int nk = kk + k_lo;
+    if (nk < klo_c || nk > khi_c || !S.band[nk] || S.tz[nk] < 0) continue;
+    layer_ok |= 1u << kk;
+    const int iz = S.tz[nk];
+    if (iz0 < 0) iz0 = iz - kk;
+    if (iz - kk != iz0) affine = false;
+  }
+  if (iz0 < 0 || (iz0 >> 5) != ((iz0 + KL - 1) >> 5) || iz0 < 0) affine = false;
+  const int ncol = PX * PY;
+  int ci0 = lane / PY, cj0 = lane - ci0 * PY;   // (i, j) of column c0, advanced without divisions
+  for (int c0 = lane; c0 < ncol; c0 += 128) {
+    uint32_t wv[4], bits[4];
+    int cols[4];
+    int ii = ci0, jj = cj0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int col = c0 + 32 * u;
+      cols[u] = -1;
+      wv[u] = 0xFFFFFFFFu;
+      bits[u] = 0u;
+      const int i = ii, j = jj;
+      jj += 32;
+      while (jj >= PY) { jj -= PY; ++ii; }
+      if (col >= ncol || i < 1 || i >= PX - 1 || j < 1 || j >= PY - 1) continue;
+      const int ix = S.tx[i], iy = S.ty[j];
+      if (ix < 0 || iy < 0) continue;
+      cols[u] = col;
+      if (affine) {
+        wv[u] = __ldg(map.inflated + ((size_t)ix * map.dim[1] + iy) * map.wz + (iz0 >> 5));
+      } else {
+        const uint32_t* colw = map.inflated + ((size_t)ix * map.dim[1] + iy) * map.wz;
+        for (int kk = 0; kk < KL; ++kk) {
+          if (!((layer_ok >> kk) & 1u)) continue;
+          const int iz = S.tz[kk + k_lo];
+          if (!((__ldg(colw + (iz >> 5)) >> (iz & 31)) & 1u)) bits[u] |= 1u << kk;
         }
       }
-      if (nm) {
-        const uint32_t base = atomicAdd((uint32_t*)&ctr[2], (uint32_t)nm);
-        for (int q = 0; q < nm; ++q) cand[base + q] = mine[q];
+      if (i == si && j == sj && sk - k_lo >= 0 && sk - k_lo < KL) cols[u] |= 0x40000000;   // the start's column
+    }
+    ci0 = ii; cj0 = jj;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      // unconditional (possibly empty) ORs: eight shared-memory atomics in flight instead of eight divergent regions
+      uint32_t bt = 0u;
+      int b0 = 0;
+      if (cols[u] >= 0) {
+        bt = affine ? ((~wv[u] >> (iz0 & 31)) & layer_ok) : bits[u];
+        if (cols[u] & 0x40000000) bt &= ~(1u << (sk - k_lo));
+        b0 = (cols[u] & 0x3FFFFFFF) * KL;
+      }
+      const int sh = b0 & 31;
+      atomicOr(&F[b0 >> 5], bt << sh);
+      atomicOr(&F[(b0 >> 5) + 1], sh ? bt >> (32 - sh) : 0u);
+    }
+  }
+  __syncwarp();
+#ifdef TP_ASTAR_TIMING
+  const long long tb0 = clock64();
+  int n_rounds = 0;
+#endif
+  // ring index pos % qcap without an integer division (pos < 2^24: the float quotient is off by at most one)
+  const float inv_qcap = 1.0f / (float)qcap;
+  auto ring = [&](uint32_t pos) {
+    const uint32_t q = __float2uint_rz(__uint2float_rn(pos) * inv_qcap);
+    int r = (int)pos - (int)(q * (uint32_t)qcap);
+    if (r >= qcap) r -= qcap;
+    if (r < 0) r += qcap;
+    return (uint32_t)r;
+  };
+  // One round = up to 32 worklist cells, lane per cell: read the <= 3 candidate bits of each of the 9 neighbour
+  // columns through a two-word window, claim them with one atomicAnd per word (a cell is claimed by exactly one lane),
+  // then append the claimed cells to the ring at positions from a warp prefix sum (the worklist tail is warp-private).
+  uint32_t head = 0, tail = 0;
+  auto round = [&](int ci, int cj, int ck, bool valid) {
+    uint32_t got[9];
+    int lo = 0, mine = 0;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) got[q] = 0u;
+    if (valid) {
+      const int kc = ck - k_lo;
+      lo = kc - 1 > 0 ? kc - 1 : 0;
+      const int hi = kc + 1 < KL - 1 ? kc + 1 : KL - 1;
+      if (lo <= hi) {
+        const uint32_t wmask = (1u << (hi - lo + 1)) - 1u;
+        uint32_t v[9];
+        int bp[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+          const int ni = ci + q / 3 - 1, nj = cj + q % 3 - 1;
+          v[q] = 0u;
+          bp[q] = 0;
+          if (ni < 0 || ni >= PX || nj < 0 || nj >= PY) continue;
+          bp[q] = (ni * PY + nj) * KL + lo;
+          v[q] = __funnelshift_r(F[bp[q] >> 5], F[(bp[q] >> 5) + 1], bp[q] & 31) & wmask;
+        }
+        // claims: one (possibly empty) atomicAnd per word touched, all 18 in flight before any result is used
+        uint32_t o0[9], o1[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+          const int sh = bp[q] & 31;
+          o0[q] = atomicAnd(&F[bp[q] >> 5], ~(v[q] << sh));
+          o1[q] = atomicAnd(&F[(bp[q] >> 5) + 1], ~(sh ? v[q] >> (32 - sh) : 0u));
+        }
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+          const int sh = bp[q] & 31;
+          const uint32_t m0 = v[q] << sh, m1 = sh ? v[q] >> (32 - sh) : 0u;
+          const uint32_t c = ((o0[q] & m0) >> sh) | (sh ? (o1[q] & m1) << (32 - sh) : 0u);
+          got[q] = c;
+          mine += __popc(c);
+        }
       }
     }
-    __syncwarp();
-    const int nc = (int)ctr[2];
-    for (int t = lane; t < nc; t += 32) {
-      const uint32_t id = cand[t];
-      const int ni = (int)(id >> 16), nj = (int)((id >> 8) & 255u), kk = (int)(id & 255u);
-      const int b = (ni * PY + nj) * KL + kk;
-      const uint32_t bit = 1u << (b & 31);
-      bool blocked = true;
-      const int ix = S.tx[ni], iy = S.ty[nj], iz = S.tz[kk + k_lo];
-      if (ix >= 0 && iy >= 0 && iz >= 0) {
-        const uint32_t w = __ldg(&map.inflated[((size_t)ix * map.dim[1] + iy) * map.wz + (iz >> 5)]);
-        blocked = (w >> (iz & 31)) & 1u;
-      }
-      const uint32_t old = atomicOr(&V[b >> 5], bit);
-      if (!(old & bit) && !blocked) {
-        const uint32_t pos = atomicAdd((uint32_t*)&ctr[1], 1u);
-        Q[pos % (uint32_t)qcap] = id;
-      }
+    // exclusive prefix sum of `mine` over the warp
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
     }
-    __syncwarp();
-    if (lane == 0) ctr[2] = 0u;
+    uint32_t pos = ring(tail + (uint32_t)(incl - mine));
+    tail += (uint32_t)__shfl_sync(0xffffffffu, incl, 31);
+    // one loop over all claimed bits of the lane (bit 3 q + r = neighbour column q, layer lo + r)
+    uint32_t all = 0u;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) all |= got[q] << (3 * q);
+    while (all) {
+      const int t = __ffs(all) - 1;
+      all &= all - 1;
+      const int q = (t * 11) >> 5, r = t - 3 * q;       // t / 3, t % 3 for t < 27
+      const int qx = (q * 11) >> 5, qy = q - 3 * qx;
+      Q[pos] = ((uint32_t)(ci + qx - 1) << 16) | ((uint32_t)(cj + qy - 1) << 8) | (uint32_t)(lo + r);
+      pos = pos + 1 == (uint32_t)qcap ? 0u : pos + 1;
+    }
     __syncwarp();
   };
   round(si, sj, sk, lane == 0);
   bool bail = false;
   for (;;) {
-    const uint32_t h = ctr[0], t = ctr[1];
-    __syncwarp();
-    int n = (int)(t - h);
+    int n = (int)(tail - head);
     if (n == 0) break;
-    if (n > qcap - TP_FLOOD_CAND) { bail = true; break; }   // the ring could overflow during this round
+    if (n > qcap - TP_FLOOD_ROUND) { bail = true; break; }   // the ring could overflow during this round
     if (n > 32) n = 32;
+#ifdef TP_ASTAR_TIMING
+    ++n_rounds;
+#endif
     uint32_t cell = 0xFFFFFFFFu;
-    if (lane < n) cell = Q[(h + (uint32_t)lane) % (uint32_t)qcap];
-    if (lane == 0) ctr[0] = h + (uint32_t)n;
-    __syncwarp();
-    const bool valid = cell != 0xFFFFFFFFu;
-    round((int)(cell >> 16), (int)((cell >> 8) & 255u), (int)(cell & 255u) + k_lo, valid);
+    if (lane < n) cell = Q[ring(head + (uint32_t)lane)];
+    head += (uint32_t)n;
+    round((int)(cell >> 16), (int)((cell >> 8) & 255u), (int)(cell & 255u) + k_lo, cell != 0xFFFFFFFFu);
   }
-  const int count = (int)ctr[1] + 1;  // every free cell was enqueued exactly once, plus the start cell
-  // is the goal in the component?
+#ifdef TP_ASTAR_TIMING
+  if (lane == 0) printf("[flood-detail] build %lld bfs %lld rounds %d\n", tb0 - tz0, clock64() - tb0, n_rounds);
+#endif
+  const int count = (int)tail + 1;  // every free cell was enqueued exactly once, plus the start cell
+  // is the goal in the component?  (claimed cells have their bit cleared: ask the map whether it was free at all)
   bool reach = false;
   if (!bail) {
     if (ei == si && ej == sj && ek == sk) reach = true;
     else if (ek >= klo_c && ek <= khi_c && ei >= 1 && ei < PX - 1 && ej >= 1 && ej < PY - 1 && S.band[ek]) {
       const int b = (ei * PY + ej) * KL + (ek - k_lo);
-      if ((V[b >> 5] >> (b & 31)) & 1u) {   // seen: free (enqueued) or blocked -> ask the map
+      if (!((F[b >> 5] >> (b & 31)) & 1u)) {   // not (or no longer) marked: blocked, or free and reached
         const int ix = S.tx[ei], iy = S.ty[ej], iz = S.tz[ek];
         bool blocked = true;
         if (ix >= 0 && iy >= 0 && iz >= 0) {
