@@ -472,11 +472,12 @@ __global__ void __launch_bounds__(32) k_plan_init(BatchView bv, VigoConst C, Dev
 // shared-memory footprint (and with it the blocks resident per SM) follows the trajectories' length.
 // Parked trajectories of one batch (see k_solve): per size class a list of ids (filled with -1 before the launch),
 // its tail (slots handed out), its head (slots claimed) and the number of trajectories that finished phase A.
+#define TP_PARK_BUCKETS 4
 struct ParkQueue {
-  int* list;       // [4][stride]
-  int* tail;       // [4]
-  int* head;       // [4]
-  int* started;    // [4]
+  int* list;       // [4 classes][TP_PARK_BUCKETS][stride]
+  int* tail;       // [4][TP_PARK_BUCKETS]  slots handed out to parkers
+  int* head;       // [4][TP_PARK_BUCKETS]  slots claimed by resumers
+  int* started;    // [4]  trajectories of the class that are through phase A
   int stride;
   int thresh;      // park when the initial searches took fewer A* expansions than this; < 0: parking disabled
 };
@@ -715,15 +716,21 @@ __global__ void __launch_bounds__(TP_LB_THREADS, MODE == 3 ? 4 : 3) k_solve(cons
       while (b < 0 && pb_class >= 0 && pb_class < 4) {
         const int c = pb_class, csize = cls_begin[c + 1] - cls_begin[c];
         if (csize == 0) { ++pb_class; continue; }
-        const int i = atomicAdd(&park.head[c], 1);
-        for (;;) {
-          b = *((volatile int*)&park.list[(size_t)c * park.stride + i]);
-          if (b >= 0) break;
-          if (*((volatile int*)&park.started[c]) >= csize && i >= *((volatile int*)&park.tail[c])) { b = -1; break; }
-          __nanosleep(200);
+        // buckets of the class, hardest-looking first; only slots that a parker has already reserved are claimed
+        const bool final_pass = *((volatile int*)&park.started[c]) >= csize;   // read BEFORE the scan: lists are final
+        for (int k = 0; k < TP_PARK_BUCKETS && b < 0; ++k) {
+          const int q = c * TP_PARK_BUCKETS + k;
+          for (;;) {
+            const int h = *((volatile int*)&park.head[q]);
+            if (h >= *((volatile int*)&park.tail[q])) break;
+            if (atomicCAS(&park.head[q], h, h + 1) != h) continue;
+            while ((b = *((volatile int*)&park.list[(size_t)q * park.stride + h])) < 0) __nanosleep(100);
+            break;
+          }
         }
-        if (b < 0) ++pb_class;
-        else { __threadfence(); res = 1; cc = c; }
+        if (b >= 0) { __threadfence(); res = 1; cc = c; }
+        else if (final_pass) ++pb_class;
+        else __nanosleep(500);
       }
       pick[0] = b;
       pick[3] = cc | (res << 8);
@@ -737,9 +744,12 @@ __global__ void __launch_bounds__(TP_LB_THREADS, MODE == 3 ? 4 : 3) k_solve(cons
     if (park.thresh >= 0 && !res && tid == 0) {
       const int cc = pick[3] & 255;
       if (parked) {
-        const int pos = atomicAdd(&park.tail[cc], 1);
+        // bucket by the guide pairs the first searches produced (the best cheap predictor of the remaining work)
+        const int np = reinterpret_cast<const TrajState*>(sm + SL.st)->n_pairs;
+        const int q = cc * TP_PARK_BUCKETS + (np >= 24 ? 0 : (np >= 12 ? 1 : (np >= 4 ? 2 : 3)));
+        const int pos = atomicAdd(&park.tail[q], 1);
         __threadfence();                                  // the trajectory's state is in HBM before its id shows up
-        atomicExch(&park.list[(size_t)cc * park.stride + pos], b);
+        atomicExch(&park.list[(size_t)q * park.stride + pos], b);
       }
       __threadfence();
       atomicAdd(&park.started[cc], 1);                    // makePlan steps 1-3 of one more trajectory of class cc are done
@@ -1802,11 +1812,12 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
       int workers_total = 0;
       for (int c = 0; c < 4; ++c) workers_total += best[c] * e->sm_count;
       if (park_env >= 0 && !resume && rounds == 0x7fffffff && M > workers_total) {
-        if (e->parkq.ensure(((size_t)4 * M + 16) * 4) != TP_OK) return TP_ERR_CUDA;
+        const int nq = 4 * TP_PARK_BUCKETS;
+        if (e->parkq.ensure(((size_t)nq * M + 2 * nq + 16) * 4) != TP_OK) return TP_ERR_CUDA;
         int* base = e->parkq.as<int>();
-        CK(cudaMemsetAsync(base, 0, 16 * 4, s));
-        CK(cudaMemsetAsync(base + 16, 0xFF, (size_t)4 * M * 4, s));
-        pq.tail = base; pq.head = base + 4; pq.started = base + 8; pq.list = base + 16;
+        CK(cudaMemsetAsync(base, 0, (size_t)(2 * nq + 16) * 4, s));
+        CK(cudaMemsetAsync(base + 2 * nq + 16, 0xFF, (size_t)nq * M * 4, s));
+        pq.tail = base; pq.head = base + nq; pq.started = base + 2 * nq; pq.list = base + 2 * nq + 16;
         pq.thresh = park_env;
       }
     }
