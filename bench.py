@@ -189,6 +189,15 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of the kernel at the bench workload
+    (profiles/ncu_traffic.json, written from the capture committed beside it); None when there is no capture."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kernel]["bytes_per_step"]
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -312,7 +321,7 @@ def main():
     kern_ms = {k: v / K for k, v in prof["ms"].items()}
     bytes_per_step = float(2 * 24 * total_pts + 64 * B)   # control points in + out, result records
     roofline = dict(bound="fp64", achieved=ach, peak=fp64_peak, unit="TFLOP/s", frac=ach / fp64_peak if fp64_peak else None,
-                    traffic=None,
+                    traffic=ncu_traffic("k_solve"),
                     kernel="k_solve<vector-free> (bsplineTraj::makePlan per thread block: segments, A*, guide points, "
                            "fused cost+gradient+L-BFGS, collision check, re-parameterisation)",
                     peak_source="measured live: dependent-free FP64 FMA micro-benchmark (tp_microbench_fp64); "
@@ -329,7 +338,7 @@ def main():
     line = dict(metric="ViGO B-spline solves/sec", value=value, unit="solves/s", n_gpus=world, steps=K, warmup=W,
                 ms_per_step=total_ms / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
                 data="synthetic",
-                config=dict(workload="batch of 4,096 ViGO solves, random start/goal pairs on square_static_map.pcd "
+                config=dict(workload=f"batch of {B:,} ViGO solves, random start/goal pairs on square_static_map.pcd "
                                      "(0.1 m voxels, 400x400x30 grid), per GPU", batch_per_gpu=B, map="square_static",
                             seed=SEED, reduction_order=args.mode, l2="flushed between timed iterations (256 MB write)",
                             control_points=dict(min=int(Ns.min()), mean=float(Ns.mean()), max=int(Ns.max())),
@@ -390,6 +399,19 @@ def main():
                                       peak_source="MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650")
         line["l2_gather_gbs"] = eng.microbench_gather(12_500_000)
         del q, hit
+        # front end: the same (start, goal) pairs -> control points on the device vs on the host cores
+        rng = np.random.default_rng(SEED)
+        S, G = random_pairs(eng.query_points, B, rng)
+        eng.frontend_batch(p, S, G)
+        t0 = time.perf_counter()
+        off_d, ctrl_d, valid_d = eng.frontend_batch(p, S, G)
+        fe_dev = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        off_h, ctrl_h, valid_h = tp.frontend_batch(pmap, p, S, G)
+        fe_host = time.perf_counter() - t0
+        line["front_end"] = dict(pairs=B, device_ms=1e3 * fe_dev, host_1core_ms=1e3 * fe_host,
+                                 identical_offsets=bool(np.array_equal(off_d, off_h)),
+                                 max_abs_diff=float(np.max(np.abs(ctrl_d - ctrl_h))) if ctrl_d.shape == ctrl_h.shape else None)
         # CPU baseline on the host cores (bounded sample)
         threads = os.cpu_count() or 1
         v, info = cpu_baseline(tp, pmap, offsets, ctrl, args.cpu_sample, threads)

@@ -578,3 +578,42 @@ def test_device_front_end_matches_host_and_oracle(tp, engine, orc, sq_map, sq_om
     assert len(same) >= 0.9 * len(keep)
     for b in same:
         assert np.array_equal(out_d[offs[b]:offs[b + 1]], out_h[offs[b]:offs[b + 1]]) and res_d["status"][b] == res_h["status"][b]
+
+
+_TMEM_SCRIPT = r'''
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+import trajectory_planner_b200 as tp
+from helpers import flat_guides
+g = np.load(sys.argv[2])
+off, ctrl = g["offsets"], g["ctrl"]
+guides = (g["soft0_g_off"], g["soft0_g_cp"], g["soft0_g_p"], g["soft0_g_v"])
+eng = tp.Engine(0); eng.set_map(tp.OccMap.from_tpm(sys.argv[1] + "/data/maps/square_static.tpm"))
+p = tp.default_params()                      # fast order -> the tensor-memory kernel (TP_LBFGS_TMEM=1)
+ps = tp.default_params(); ps.strict_order = 1  # bit-faithful kernel, not affected by the variable
+c_t, r_t, _ = eng.optimize_batch(p, off, ctrl, guides)
+c_s, r_s, _ = eng.optimize_batch(ps, off, ctrl, guides)
+rel = np.abs(r_t["fx"] - r_s["fx"]) / np.abs(r_s["fx"])
+same = np.mean((r_t["iters"] == r_s["iters"]) & (r_t["evals"] == r_s["evals"]))
+print("optimize: final-cost rel diff median %.2e max %.2e, same (iters, evals) %.2f" % (np.median(rel), rel.max(), same))
+assert np.median(rel) <= 1e-3 and rel.max() <= 0.25 and same >= 0.2
+out, r = eng.make_plan_batch(p, off, ctrl)
+gs = g["soft0_plan_stats"]
+agree = np.mean((r["status"] == 1).astype(int) == gs["success"])
+print("makePlan: success agreement with the golden run %.3f" % agree)
+assert agree >= 0.9
+assert not np.any(eng.has_collision_batch(p, off, out)[r["status"] == 1])
+'''
+
+
+@pytest.mark.gpu
+def test_tensor_memory_history_variant_subprocess():
+    """The L-BFGS kernel with its history in tensor memory (TP_LBFGS_TMEM=1: tcgen05.alloc / st / ld, reduce-scatter
+    Gram update) is selected once per process, so it runs in a child: one optimize() against the bit-faithful kernel
+    (same statistics as the default fast kernel must meet) and the whole makePlan against the golden outcome."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, TP_LBFGS_TMEM="1")
+    r = subprocess.run([sys.executable, "-c", _TMEM_SCRIPT, root, _GOLD], env=env, capture_output=True, text=True, timeout=600)
+    print(r.stdout, r.stderr[-2000:])
+    assert r.returncode == 0
