@@ -617,3 +617,44 @@ def test_tensor_memory_history_variant_subprocess():
     r = subprocess.run([sys.executable, "-c", _TMEM_SCRIPT, root, _GOLD], env=env, capture_output=True, text=True, timeout=600)
     print(r.stdout, r.stderr[-2000:])
     assert r.returncode == 0
+
+
+_NOPARK_SCRIPT = r'''
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1])
+import trajectory_planner_b200 as tp
+z = np.load(sys.argv[2])
+eng = tp.Engine(0); eng.set_map(tp.OccMap.from_tpm(sys.argv[1] + "/data/maps/square_static.tpm"))
+outs = {}
+for strict in (0, 1):
+    p = tp.default_params(); p.strict_order = strict
+    out, res = eng.make_plan_batch(p, z["offsets"], z["ctrl"])
+    outs["out%d" % strict] = out; outs["res%d" % strict] = res
+np.savez(sys.argv[3], **outs)
+'''
+
+
+@pytest.mark.gpu
+def test_park_and_resume_scheduling_changes_no_result(tp, engine, sq_map, sq_omap, tmp_path):
+    """k_solve parks trajectories after makePlan steps 1-3 and resumes them later once the batch outnumbers the
+    resident workers (1 400 trajectories here; the other tests stay below that).  Scheduling must not change a single
+    bit of any result, in either reduction order: compare with a child process that runs with parking disabled
+    (TP_PARK_THRESH=-1)."""
+    import subprocess, sys
+    from helpers import make_problems
+    pr = make_problems(tp, sq_map, sq_omap, 1400, seed=77)
+    inp, outp = str(tmp_path / "in.npz"), str(tmp_path / "out.npz")
+    np.savez(inp, offsets=pr["offsets"], ctrl=pr["ctrl"])
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", _NOPARK_SCRIPT, root, inp, outp], env=dict(os.environ, TP_PARK_THRESH="-1"),
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = np.load(outp)
+    for strict in (0, 1):
+        p = tp.default_params()
+        p.strict_order = strict
+        out, res = engine.make_plan_batch(p, pr["offsets"], pr["ctrl"])
+        assert np.array_equal(out, ref["out%d" % strict]), strict
+        for f in ("status", "lbfgs_iters", "lbfgs_evals", "astar_expansions", "outer_rounds", "final_cost", "linear_factor"):
+            assert np.array_equal(res[f], ref["res%d" % strict][f]), (strict, f)
+        print(f"strict={strict}: 1400 trajectories bit-identical with and without parking; success rate {np.mean(res['status'] == 1):.3f}")

@@ -286,6 +286,7 @@ __device__ __forceinline__ void vf_eval_partial(const VigoConst& C, const VfCtx&
 
 #ifdef TP_LBFGS_TIMING
 __device__ long long g_tp_t_partial = 0, g_tp_t_sum = 0;
+__device__ unsigned long long g_tp_phase[8];   // whole-batch phase totals: total, eval, gram, coeffs, direction, iterations, evals
 #endif
 __device__ __forceinline__ void vf_eval(const VigoConst& C, const VfCtx& V, Red& R, bool with_d, double& f, double& dg,
                                         double& gg, double& xx, int tid) {
@@ -891,6 +892,15 @@ __device__ void lbfgs_run_fast(const VigoConst& C, VfCtx& V, tp_lbfgs_result& ou
            (double)(clock64() - tT0) / k, (double)tE / k, (double)tG / k, (double)tC / k, (double)tD / k,
            (double)g_tp_t_partial / evals, (double)g_tp_t_sum / evals);
   if (tid == 0) { g_tp_t_partial = 0; g_tp_t_sum = 0; }
+  if (tid == 0) {
+    atomicAdd(&g_tp_phase[0], (unsigned long long)(clock64() - tT0));
+    atomicAdd(&g_tp_phase[1], (unsigned long long)tE);
+    atomicAdd(&g_tp_phase[2], (unsigned long long)tG);
+    atomicAdd(&g_tp_phase[3], (unsigned long long)tC);
+    atomicAdd(&g_tp_phase[4], (unsigned long long)tD);
+    atomicAdd(&g_tp_phase[5], (unsigned long long)k);
+    atomicAdd(&g_tp_phase[6], (unsigned long long)evals);
+  }
 #endif
   out.ret = ret;
   out.iters = k;

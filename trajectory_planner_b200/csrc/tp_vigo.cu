@@ -1960,6 +1960,16 @@ int64_t tp_vigo_frontend_batch_device(tp_engine_t* e, const tp_vigo_params* p, i
   return total;
 }
 
+#ifdef TP_LBFGS_TIMING
+// development builds only (build_timing.sh): whole-batch L-BFGS phase cycle totals, reset on read
+extern "C" int tp_debug_phase_get(unsigned long long* out) {
+  unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (cudaMemcpyFromSymbol(out, g_tp_phase, sizeof(z)) != cudaSuccess) return -1;
+  cudaMemcpyToSymbol(g_tp_phase, z, sizeof(z));
+  return 0;
+}
+#endif
+
 // ---- measurement
 __global__ void k_fp64_fma(double* out, int iters) {
   double a0 = threadIdx.x * 1e-9 + 1.0, a1 = a0 + 0.1, a2 = a0 + 0.2, a3 = a0 + 0.3, a4 = a0 + 0.4, a5 = a0 + 0.5,
