@@ -480,6 +480,8 @@ struct ParkQueue {
   int* started;    // [4]  trajectories of the class that are through phase A
   int stride;
   int thresh;      // park when the initial searches took fewer A* expansions than this; < 0: parking disabled
+  int score_mode;  // difficulty score of a parked trajectory: 0 guide pairs, 1 pairs x N / 32, 2 pairs x 8 + expansions / 64
+  int b[3];        // bucket bounds on the score (descending)
 };
 
 struct SolveLayout {
@@ -745,8 +747,9 @@ __global__ void __launch_bounds__(TP_LB_THREADS, MODE == 3 ? 4 : 3) k_solve(cons
       const int cc = pick[3] & 255;
       if (parked) {
         // bucket by the guide pairs the first searches produced (the best cheap predictor of the remaining work)
-        const int np = reinterpret_cast<const TrajState*>(sm + SL.st)->n_pairs;
-        const int q = cc * TP_PARK_BUCKETS + (np >= 24 ? 0 : (np >= 12 ? 1 : (np >= 4 ? 2 : 3)));
+        const TrajState* ps = reinterpret_cast<const TrajState*>(sm + SL.st);
+        const int np = park.score_mode == 0 ? ps->n_pairs : (park.score_mode == 1 ? ps->n_pairs * ps->N / 32 : ps->n_pairs * 8 + ps->astar_expansions / 64);
+        const int q = cc * TP_PARK_BUCKETS + (np >= park.b[0] ? 0 : (np >= park.b[1] ? 1 : (np >= park.b[2] ? 2 : 3)));
         const int pos = atomicAdd(&park.tail[q], 1);
         __threadfence();                                  // the trajectory's state is in HBM before its id shows up
         atomicExch(&park.list[(size_t)q * park.stride + pos], b);
@@ -1807,6 +1810,7 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
     // starts at once anyway — and only for whole solves
     ParkQueue pq;
     pq.list = nullptr; pq.tail = pq.head = pq.started = nullptr; pq.stride = M; pq.thresh = -1;
+    pq.score_mode = 0; pq.b[0] = 16; pq.b[1] = 8; pq.b[2] = 2;
     {
       static const int park_env = getenv("TP_PARK_THRESH") ? atoi(getenv("TP_PARK_THRESH")) : 1500;
       int workers_total = 0;
@@ -1819,6 +1823,10 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
         CK(cudaMemsetAsync(base + 2 * nq + 16, 0xFF, (size_t)nq * M * 4, s));
         pq.tail = base; pq.head = base + nq; pq.started = base + 2 * nq; pq.list = base + 2 * nq + 16;
         pq.thresh = park_env;
+        pq.score_mode = getenv("TP_PARK_SCORE") ? atoi(getenv("TP_PARK_SCORE")) : 0;
+        pq.b[0] = getenv("TP_PARK_B0") ? atoi(getenv("TP_PARK_B0")) : 16;
+        pq.b[1] = getenv("TP_PARK_B1") ? atoi(getenv("TP_PARK_B1")) : 8;
+        pq.b[2] = getenv("TP_PARK_B2") ? atoi(getenv("TP_PARK_B2")) : 2;
       }
     }
     CK(cudaEventRecord(e->ev_fork, s));
