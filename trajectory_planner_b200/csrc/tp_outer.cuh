@@ -159,13 +159,35 @@ struct Heap {
       int hole = 0, second = 0;
       const int lim = (len - 1) / 2;
       if (size <= TP_HEAP_SMEM) {
+        // two levels per step: the keys / ids of both children AND of all four grandchildren are loaded together
+        // (12 independent LDS), then the two comparisons of std::__adjust_heap are resolved from registers
         while (second < lim) {
-          second = 2 * (second + 1);
-          double kr = lds_f64(sk + 8u * second);
-          const double kl = lds_f64(sk + 8u * second - 8u);
-          if (kr > kl) { --second; kr = kl; }
-          set_s(hole, kr, lds_u32(sn + 4u * second));
+          const int r1 = 2 * (second + 1), l1 = r1 - 1;
+          const int rr = 2 * (r1 + 1), lr = 2 * r1;             // right children of r1 / l1 (left ones: - 1)
+          const bool spec = rr < TP_HEAP_SMEM;
+          const double kr1 = lds_f64(sk + 8u * r1), kl1 = lds_f64(sk + 8u * l1);
+          const uint32_t nr1 = lds_u32(sn + 4u * r1), nl1 = lds_u32(sn + 4u * l1);
+          double krr = 0, krl = 0, klr = 0, kll = 0;
+          uint32_t nrr = 0, nrl = 0, nlr = 0, nll = 0;
+          if (spec) {
+            krr = lds_f64(sk + 8u * rr); krl = lds_f64(sk + 8u * rr - 8u);
+            klr = lds_f64(sk + 8u * lr); kll = lds_f64(sk + 8u * lr - 8u);
+            nrr = lds_u32(sn + 4u * rr); nrl = lds_u32(sn + 4u * rr - 4u);
+            nlr = lds_u32(sn + 4u * lr); nll = lds_u32(sn + 4u * lr - 4u);
+          }
+          const bool left1 = kr1 > kl1;
+          second = left1 ? l1 : r1;
+          set_s(hole, left1 ? kl1 : kr1, left1 ? nl1 : nr1);
           hole = second;
+          if (spec && second < lim) {
+            const int r2 = left1 ? lr : rr;
+            const double kr2 = left1 ? klr : krr, kl2 = left1 ? kll : krl;
+            const uint32_t nr2 = left1 ? nlr : nrr, nl2 = left1 ? nll : nrl;
+            const bool left2 = kr2 > kl2;
+            second = left2 ? r2 - 1 : r2;
+            set_s(hole, left2 ? kl2 : kr2, left2 ? nl2 : nr2);
+            hole = second;
+          }
         }
       } else {
         while (second < lim) {
@@ -309,7 +331,7 @@ __device__ __noinline__ int flood_component(const DevMap& map, const VigoConst& 
   // One round = up to 32 worklist cells, lane per cell: read the <= 3 candidate bits of each of the 9 neighbour
   // columns through a two-word window, claim them with one atomicAnd per word (a cell is claimed by exactly one lane),
   // then append the claimed cells to the ring at positions from a warp prefix sum (the worklist tail is warp-private).
-  uint32_t head = 0, tail = 0;
+  uint32_t head = 0, tail = 0, claimed = 0;
   auto round = [&](int ci, int cj, int ck, bool valid) {
     uint32_t got[9];
     int lo = 0, mine = 0;
@@ -358,7 +380,9 @@ __device__ __noinline__ int flood_component(const DevMap& map, const VigoConst& 
       if (lane >= o) incl += up;
     }
     uint32_t pos = ring(tail + (uint32_t)(incl - mine));
-    tail += (uint32_t)__shfl_sync(0xffffffffu, incl, 31);
+    const uint32_t got_all = (uint32_t)__shfl_sync(0xffffffffu, incl, 31);
+    tail += got_all;
+    claimed += got_all;
     // one loop over all claimed bits of the lane (bit 3 q + r = neighbour column q, layer lo + r)
     uint32_t all = 0u;
 #pragma unroll
@@ -375,10 +399,33 @@ __device__ __noinline__ int flood_component(const DevMap& map, const VigoConst& 
   };
   round(si, sj, sk, lane == 0);
   bool bail = false;
+  // The ring holds ~3 300 cells; a wide front (open rooms) outgrows it.  Order is irrelevant for a flood, so the oldest
+  // half of a full ring is moved to an overflow STACK in the heap's HBM spill area (below the parked heap) and fetched
+  // back when the ring runs dry.
+  uint32_t* ovf = reinterpret_cast<uint32_t*>(W.heap_k_gl);
+  const int ovf_cap = (C.heap_cap - TP_HEAP_SMEM) * 2;
+  int ovf_n = 0, n_spills = 0;
   for (;;) {
     int n = (int)(tail - head);
-    if (n == 0) break;
-    if (n > qcap - TP_FLOOD_ROUND) { bail = true; break; }   // the ring could overflow during this round
+    if (n == 0) {
+      if (ovf_n == 0) break;
+      const int m = ovf_n < qcap / 2 ? ovf_n : qcap / 2;
+      for (int i = lane; i < m; i += 32) Q[ring(tail + (uint32_t)i)] = ovf[ovf_n - m + i];
+      tail += (uint32_t)m;
+      ovf_n -= m;
+      __syncwarp();
+      continue;
+    }
+    if (n > qcap - TP_FLOOD_ROUND) {   // the ring could overflow during this round
+      const int m = n / 2;
+      if (ovf_n + m > ovf_cap) { bail = true; break; }
+      for (int i = lane; i < m; i += 32) ovf[ovf_n + i] = Q[ring(head + (uint32_t)i)];
+      head += (uint32_t)m;
+      ovf_n += m;
+      ++n_spills;
+      __syncwarp();
+      n -= m;
+    }
     if (n > 32) n = 32;
 #ifdef TP_ASTAR_TIMING
     ++n_rounds;
@@ -389,9 +436,10 @@ __device__ __noinline__ int flood_component(const DevMap& map, const VigoConst& 
     round((int)(cell >> 16), (int)((cell >> 8) & 255u), (int)(cell & 255u) + k_lo, cell != 0xFFFFFFFFu);
   }
 #ifdef TP_ASTAR_TIMING
-  if (lane == 0) printf("[flood-detail] build %lld bfs %lld rounds %d\n", tb0 - tz0, clock64() - tb0, n_rounds);
+  if (lane == 0) printf("[flood-detail] build %lld bfs %lld rounds %d spills %d bail %d cells %u\n", tb0 - tz0, clock64() - tb0, n_rounds, n_spills, (int)bail, claimed);
 #endif
-  const int count = (int)tail + 1;  // every free cell was enqueued exactly once, plus the start cell
+  (void)n_spills;
+  const int count = (int)claimed + 1;  // every free cell was claimed exactly once, plus the start cell
   // is the goal in the component?  (claimed cells have their bit cleared: ask the map whether it was free at all)
   bool reach = false;
   if (!bail) {
@@ -524,79 +572,94 @@ __device__ __noinline__ int astar_search(const DevMap& map, const VigoConst& C, 
 #define TICK(acc)
 #endif
   for (;;) {
-    // ---- pop (lane 0, shared memory)
+    // ---- next node = top of the open set.  Its neighbours' node records and map words are requested FIRST (one
+    // round of global loads in flight), then lane 0 runs pop_heap's sift-down in shared memory under that latency.
+    // (The sift-down moves heap entries, i.e. rewrites heap_pos fields: in-place updates below re-read theirs.)
     uint32_t cur = NODE_NONE;
-    if (lane == 0 && H.size > 0) cur = H.pop();
+    if (lane == 0 && H.size > 0) cur = H.node(0);
     cur = __shfl_sync(0xffffffffu, cur, 0);
     if (cur == NODE_NONE) break;  // open set empty
     ++num_iter;
     const int ci = (int)(cur >> 16), cj = (int)((cur >> 8) & 255u);
     const int ck = (cur & 255u) == AS_SPARE_KK ? sk : (int)(cur & 255u) + k_lo;
     if (ci == ei && cj == ej && ck == ek) {
+      if (lane == 0) H.pop();
       goal_id = cur;
       result = 0;
       break;
     }
-    TICK(tA)
     const uint32_t cur_lin = H.lin_of(cur);
     const double gcur = nodes[cur_lin].g;  // uniform address: one broadcast load, overlaps the loads below
-    if (lane == 0) nodes[cur_lin].stamp_state = (round << 2) | ST_CLOSED;
-    // ---- lane-parallel neighbour evaluation (astarOcc.cpp:173-229); lane L <-> (dx,dy,dz) in the
-    // reference's loop order
+    // ---- lane-parallel neighbour loads (astarOcc.cpp:173-229); lane L <-> (dx,dy,dz) in the reference's loop order
     int kind = 0;  // 0 skip, 1 push (new node), 2 in-place update
+    bool cand = false, is_start = false, band = false;
+    int ni = 0, nj = 0, nk = 0, d2 = 0;
+    uint32_t nl = 0, nid = 0;
+    uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+    uint32_t mapw = 0xFFFFFFFFu;
+    int mapbit = 0;
     if (lane < 27 && lane != 13) {
       const int dx = lane / 9 - 1, dy = (lane / 3) % 3 - 1, dz = lane % 3 - 1;
-      const int ni = ci + dx, nj = cj + dy, nk = ck + dz;
+      ni = ci + dx; nj = cj + dy; nk = ck + dz;
+      d2 = dx * dx + dy * dy + dz * dz;
       const bool inb = !(ni < 1 || ni >= PX - 1 || nj < 1 || nj >= PY - 1 || nk < 1 || nk >= PZ - 1);
       if (inb) {
-        const bool is_start = (ni == si && nj == sj && nk == sk);
-        const bool band = S.band[nk] != 0;
+        is_start = (ni == si && nj == sj && nk == sk);
+        band = S.band[nk] != 0;
         const bool layer_ok = nk >= k_lo && nk < k_lo + KL;
         if (band && !layer_ok && !is_start) err |= ERR_BAND;  // cannot happen (pool_kl has slack)
         // cells outside the band are rejected by :202 whatever their node state says, except that a
         // CLOSED start node is skipped one line earlier — same outcome (skip) either way.
         if ((band && layer_ok) || is_start) {
-          const uint32_t nid = is_start ? start_id : (((uint32_t)ni << 16) | ((uint32_t)nj << 8) | (uint32_t)(nk - k_lo));
-          const uint32_t nl = is_start ? spare : (uint32_t)((ni * PY + nj) * KL + (nk - k_lo));
-          const uint4 raw = *reinterpret_cast<const uint4*>(&nodes[nl]);  // stamp_state, parent, g
-          const uint32_t hpos = nodes[nl].heap_pos;                         // same sector, speculative
-          bool blocked_map = true;   // the map gather is issued before `raw` is consumed
+          cand = true;
+          nid = is_start ? start_id : (((uint32_t)ni << 16) | ((uint32_t)nj << 8) | (uint32_t)(nk - k_lo));
+          nl = is_start ? spare : (uint32_t)((ni * PY + nj) * KL + (nk - k_lo));
+          raw = *reinterpret_cast<const uint4*>(&nodes[nl]);  // stamp_state, parent, g
           if (band) {
             const int ix = S.tx[ni], iy = S.ty[nj], iz = S.tz[nk];
             if (ix >= 0 && iy >= 0 && iz >= 0) {
-              const uint32_t w = __ldg(&map.inflated[((size_t)ix * map.dim[1] + iy) * map.wz + (iz >> 5)]);
-              blocked_map = (w >> (iz & 31)) & 1u;
+              mapw = __ldg(&map.inflated[((size_t)ix * map.dim[1] + iy) * map.wz + (iz >> 5)]);
+              mapbit = iz & 31;
             }
           }
-          const bool explored = (raw.x >> 2) == round;
-          const uint32_t state = raw.x & 3u;
-          if (!(explored && state == ST_CLOSED)) {
-            if (blocked_map) {
-              // blocked this round: remember it so the map is not queried again (observably the same
-              // as the reference's stale-state handling: the cell is skipped on every visit)
-              nodes[nl].stamp_state = (round << 2) | ST_CLOSED;
-            } else {
-              const int d2 = dx * dx + dy * dy + dz * dz;
-              const double tentative = gcur + (d2 == 1 ? gstep1 : (d2 == 2 ? gstep2 : gstep3));
-              const double gold = __hiloint2double((int)raw.w, (int)raw.z);
-              if (!explored) {
-                kind = 1;
-                uint4 w;
-                w.x = (round << 2) | ST_OPEN;
-                w.y = cur;
-                w.z = (uint32_t)__double2loint(tentative);
-                w.w = (uint32_t)__double2hiint(tentative);
-                *reinterpret_cast<uint4*>(&nodes[nl]) = w;
-              } else if (tentative < gold) {
-                kind = 2;
-              }
-              if (kind) {
-                S.st_pos[lane] = hpos;
-                S.st_id[lane] = nid;
-                S.st_g[lane] = tentative;
-                S.st_f[lane] = tentative + as_heu(ni, nj, nk, ei, ej, ek);
-              }
-            }
+        }
+      }
+    }
+    // ---- pop (lane 0, shared memory) while the loads are in flight
+    if (lane == 0) {
+      H.pop();
+      nodes[cur_lin].stamp_state = (round << 2) | ST_CLOSED;
+    }
+    __syncwarp();
+    TICK(tA)
+    // ---- classification
+    if (cand) {
+      const bool blocked_map = (mapw >> mapbit) & 1u;
+      const bool explored = (raw.x >> 2) == round;
+      const uint32_t state = raw.x & 3u;
+      if (!(explored && state == ST_CLOSED)) {
+        if (blocked_map) {
+          // blocked this round: remember it so the map is not queried again (observably the same
+          // as the reference's stale-state handling: the cell is skipped on every visit)
+          nodes[nl].stamp_state = (round << 2) | ST_CLOSED;
+        } else {
+          const double tentative = gcur + (d2 == 1 ? gstep1 : (d2 == 2 ? gstep2 : gstep3));
+          const double gold = __hiloint2double((int)raw.w, (int)raw.z);
+          if (!explored) {
+            kind = 1;
+            uint4 w;
+            w.x = (round << 2) | ST_OPEN;
+            w.y = cur;
+            w.z = (uint32_t)__double2loint(tentative);
+            w.w = (uint32_t)__double2hiint(tentative);
+            *reinterpret_cast<uint4*>(&nodes[nl]) = w;
+          } else if (tentative < gold) {
+            kind = 2;
+          }
+          if (kind) {
+            S.st_id[lane] = nid;
+            S.st_g[lane] = tentative;
+            S.st_f[lane] = tentative + as_heu(ni, nj, nk, ei, ej, ek);
           }
         }
       }
@@ -620,7 +683,7 @@ __device__ __noinline__ int astar_search(const DevMap& map, const VigoConst& C, 
           const uint32_t nl = H.lin_of(nid);
           nodes[nl].parent = cur;
           nodes[nl].g = S.st_g[L];
-          const uint32_t pos = pushed ? nodes[nl].heap_pos : S.st_pos[L];
+          const uint32_t pos = nodes[nl].heap_pos;   // current position (the pop and earlier pushes may have moved it)
           H.set_key((int)pos, S.st_f[L]);
         } else {
           if (H.size >= C.heap_cap) { overflow = 1; break; }
