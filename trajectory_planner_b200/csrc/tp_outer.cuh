@@ -209,6 +209,64 @@ struct Heap {
     --size;
     return top;
   }
+  // Warp-cooperative pop_heap (all 32 lanes call it; the caller has read the top already).  std::__adjust_heap's
+  // DECISIONS — which child moves up at each level — depend only on keys the sift-down never rewrites, so every lane
+  // walks the root-to-leaf path redundantly (two levels per step from one batch of speculative loads) and lane l keeps
+  // the move of level l; the moves themselves (key, id, the node record's heap_pos: address arithmetic and a global
+  // store each) are then applied by their lanes in parallel instead of one after the other on lane 0.
+  // Same final heap as pop(): bit-identical A* behaviour.
+  __device__ __forceinline__ void pop_warp(int lane) {
+    const int sz = __shfl_sync(0xffffffffu, size, 0);
+    if (sz > TP_HEAP_SMEM) {   // spilled heap: sequential path (warp-uniform branch)
+      if (lane == 0) pop();
+      return;
+    }
+    if (sz > 1) {
+      const int len = sz - 1;
+      const double vk = lds_f64(sk + 8u * len);
+      const uint32_t vn = lds_u32(sn + 4u * len);
+      int hole = 0, second = 0, level = 0, my_from = -1, my_to = -1;
+      const int lim = (len - 1) / 2;
+      while (second < lim) {
+        const int r1 = 2 * (second + 1), l1 = r1 - 1;
+        const int rr = 2 * (r1 + 1), lr = 2 * r1;
+        const bool spec = rr < TP_HEAP_SMEM;
+        const double kr1 = lds_f64(sk + 8u * r1), kl1 = lds_f64(sk + 8u * l1);
+        double krr = 0, krl = 0, klr = 0, kll = 0;
+        if (spec) {
+          krr = lds_f64(sk + 8u * rr); krl = lds_f64(sk + 8u * rr - 8u);
+          klr = lds_f64(sk + 8u * lr); kll = lds_f64(sk + 8u * lr - 8u);
+        }
+        const bool left1 = kr1 > kl1;
+        second = left1 ? l1 : r1;
+        if (lane == level) { my_from = second; my_to = hole; }
+        hole = second;
+        ++level;
+        if (spec && second < lim) {
+          const int r2 = left1 ? lr : rr;
+          const bool left2 = (left1 ? klr : krr) > (left1 ? kll : krl);
+          second = left2 ? r2 - 1 : r2;
+          if (lane == level) { my_from = second; my_to = hole; }
+          hole = second;
+          ++level;
+        }
+      }
+      if ((len & 1) == 0 && second == (len - 2) / 2) {
+        second = 2 * (second + 1);
+        if (lane == level) { my_from = second - 1; my_to = hole; }
+        hole = second - 1;
+        ++level;
+      }
+      double mk = 0;
+      uint32_t mn = 0;
+      if (my_from >= 0) { mk = lds_f64(sk + 8u * my_from); mn = lds_u32(sn + 4u * my_from); }
+      __syncwarp();
+      if (my_from >= 0) set_s(my_to, mk, mn);
+      __syncwarp();
+      if (lane == 0) sift_up(hole, vk, vn);
+    }
+    if (lane == 0) --size;
+  }
 };
 
 // Reachability shortcut for searches that are about to exhaust their pool.  AstarSearch pops every
@@ -566,7 +624,7 @@ __device__ __noinline__ int astar_search(const DevMap& map, const VigoConst& C, 
   int num_iter = 0;
   uint32_t goal_id = NODE_NONE;
 #ifdef TP_ASTAR_TIMING
-  long long tA = 0, tB = 0, tC = 0, t0 = clock64(), t1;
+  long long tA = 0, tB = 0, tC = 0, tPop = 0, t0 = clock64(), t1;
 #define TICK(acc) { t1 = clock64(); acc += t1 - t0; t0 = t1; }
 #else
 #define TICK(acc)
@@ -626,11 +684,17 @@ __device__ __noinline__ int astar_search(const DevMap& map, const VigoConst& C, 
       }
     }
     // ---- pop (lane 0, shared memory) while the loads are in flight
-    if (lane == 0) {
-      H.pop();
-      nodes[cur_lin].stamp_state = (round << 2) | ST_CLOSED;
-    }
+#ifdef TP_ASTAR_TIMING
+    const long long tp0 = clock64();
+#endif
+    H.pop_warp(lane);
+    if (lane == 0) nodes[cur_lin].stamp_state = (round << 2) | ST_CLOSED;
     __syncwarp();
+#ifdef TP_ASTAR_TIMING
+    tPop += clock64() - tp0;
+    if ((raw.x ^ mapw) == 0x12345679u && gcur == 1.2345) err |= ERR_BAND;   // forces the loads to have landed
+    __syncwarp();
+#endif
     TICK(tA)
     // ---- classification
     if (cand) {
@@ -719,7 +783,7 @@ __device__ __noinline__ int astar_search(const DevMap& map, const VigoConst& C, 
   expansions = num_iter;
 #ifdef TP_ASTAR_TIMING
   if (lane == 0)
-    printf("[astar] exp %d heap %d cycles/exp: pop %.0f classify %.0f push %.0f\n", num_iter, H.size, (double)tA / num_iter,
+    printf("[astar] exp %d heap %d cycles/exp: sift %.0f pop+loadwait %.0f classify %.0f push %.0f\n", num_iter, H.size, (double)tPop / num_iter, (double)tA / num_iter,
            (double)tB / num_iter, (double)tC / num_iter);
 #endif
   if (result < 0) return -1;
