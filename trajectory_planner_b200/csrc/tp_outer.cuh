@@ -81,6 +81,13 @@ __device__ __forceinline__ double lds_f64(uint32_t a) {
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
   return v;
 }
+// key as its bit pattern: fScore >= 0 always, and for non-negative doubles the IEEE order is the order of the
+// 64-bit patterns — the sift comparisons run on the integer pipe
+__device__ __forceinline__ unsigned long long lds_k64(uint32_t a) {
+  unsigned long long v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
+  return v;
+}
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
@@ -231,11 +238,11 @@ struct Heap {
         const int r1 = 2 * (second + 1), l1 = r1 - 1;
         const int rr = 2 * (r1 + 1), lr = 2 * r1;
         const bool spec = rr < TP_HEAP_SMEM;
-        const double kr1 = lds_f64(sk + 8u * r1), kl1 = lds_f64(sk + 8u * l1);
-        double krr = 0, krl = 0, klr = 0, kll = 0;
+        const unsigned long long kr1 = lds_k64(sk + 8u * r1), kl1 = lds_k64(sk + 8u * l1);
+        unsigned long long krr = 0, krl = 0, klr = 0, kll = 0;
         if (spec) {
-          krr = lds_f64(sk + 8u * rr); krl = lds_f64(sk + 8u * rr - 8u);
-          klr = lds_f64(sk + 8u * lr); kll = lds_f64(sk + 8u * lr - 8u);
+          krr = lds_k64(sk + 8u * rr); krl = lds_k64(sk + 8u * rr - 8u);
+          klr = lds_k64(sk + 8u * lr); kll = lds_k64(sk + 8u * lr - 8u);
         }
         const bool left1 = kr1 > kl1;
         second = left1 ? l1 : r1;
