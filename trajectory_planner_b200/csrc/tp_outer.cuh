@@ -37,6 +37,7 @@ struct Worker {
   int lane;
   int flood_trigger;      // expansions after which astar_search checks reachability (adaptive per trajectory)
   int goal_unreachable;   // set by astar_search when the flood fill proved the goal unreachable
+  int flood_wasted;       // consecutive floods of this trajectory that found the goal reachable (nothing gained)
 };
 
 struct AStarFrame {  // per-search constants (uniform across the warp)
@@ -780,6 +781,7 @@ __device__ __noinline__ int astar_search(const DevMap& map, const VigoConst& C, 
       if (lane == 0) printf("[flood] result %d cycles %lld\n", comp, clock64() - tf0);
       t0 = clock64();
 #endif
+      W.flood_wasted = comp >= 0 ? 0 : W.flood_wasted + 1;
       if (comp >= 0) {  // goal unreachable: the search would pop the whole component and fail
         W.goal_unreachable = 1;
         num_iter = (C.p.astar_max_expansions > 0 && comp > C.p.astar_max_expansions) ? C.p.astar_max_expansions : comp;
@@ -1050,7 +1052,8 @@ __device__ __noinline__ int path_search(const DevMap& map, const VigoConst& C, c
     const D3 ps = ld3(ctrl, a), pe = ld3(ctrl, b2);
     int ex = 0;
     int len = astar_search(map, C, W, ps, pe, ex, err);
-    if (W.goal_unreachable) W.flood_trigger = TP_FLOOD_TRIGGER_AGAIN;   // this trajectory's next searches check early
+    // this trajectory's next searches check early — unless the early checks keep finding the goal reachable
+    if (W.goal_unreachable) W.flood_trigger = W.flood_wasted >= 2 ? TP_FLOOD_TRIGGER : TP_FLOOD_TRIGGER_AGAIN;
     if (lane == 0) {
       st.astar_searches += 1;
       st.astar_expansions += ex;

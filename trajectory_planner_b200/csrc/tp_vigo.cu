@@ -315,6 +315,7 @@ __device__ __forceinline__ Worker make_worker(const VigoConst& C, const AStarPoo
   W.lane = lane;
   W.flood_trigger = TP_FLOOD_TRIGGER;
   W.goal_unreachable = 0;
+  W.flood_wasted = 0;
   return W;
 }
 
