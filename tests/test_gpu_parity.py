@@ -658,3 +658,54 @@ def test_park_and_resume_scheduling_changes_no_result(tp, engine, sq_map, sq_oma
         for f in ("status", "lbfgs_iters", "lbfgs_evals", "astar_expansions", "outer_rounds", "final_cost", "linear_factor"):
             assert np.array_equal(res[f], ref["res%d" % strict][f]), (strict, f)
         print(f"strict={strict}: 1400 trajectories bit-identical with and without parking; success rate {np.mean(res['status'] == 1):.3f}")
+
+
+@pytest.mark.gpu
+def test_make_plan_batch_edge_cases(tp, engine, orc, sq_map, sq_omap):
+    """Empty batch; ragged batch mixing the smallest legal trajectory (7 control points = one free point), an illegal
+    one (6), lengths at the size-class boundaries (40/41, 64/65, 104/105) and long ones (150, 200 control points: the
+    largest class, history rows in shared memory up to the 227 KB limit); a trajectory beyond the kernel's capacity
+    must fail LOUDLY (error code + message), never silently."""
+    from trajectory_planner_b200 import TpError
+    p = tp.default_params()
+    p.strict_order = 1
+    out, res = engine.make_plan_batch(p, np.zeros(1, np.int32), np.zeros((0, 3)))
+    assert out.shape == (0, 3) and len(res) == 0
+    # straight paths across the map (through obstacles), resampled to the wanted number of control points
+    rng = np.random.default_rng(5)
+    lens = [7, 6, 8, 40, 41, 64, 65, 104, 105, 150, 200, 12, 7]
+    chunks = []
+    for n in lens:
+        a = np.array([-9.0 + rng.uniform(0, 1), -9.0 + rng.uniform(0, 18), 1.0])
+        d = np.array([1.0, rng.uniform(-0.3, 0.3), 0.0])
+        d /= np.linalg.norm(d)
+        step = min(0.25, 17.0 / max(n - 1, 1))
+        chunks.append(a[None, :] + np.arange(n)[:, None] * step * d[None, :])
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    ctrl = np.concatenate(chunks, 0)
+    out, res = engine.make_plan_batch(p, off, ctrl)
+    assert res["status"][1] == tp.TP_STATUS_INVALID
+    assert np.array_equal(out[off[1]:off[2]], ctrl[off[1]:off[2]])
+    legal = [b for b in range(len(lens)) if lens[b] >= 7]
+    o2 = np.concatenate([[0], np.cumsum([lens[b] for b in legal])]).astype(np.int32)
+    c2 = np.concatenate([chunks[b] for b in legal], 0)
+    out2, res2 = engine.make_plan_batch(p, o2, c2)
+    po = sq_omap.lib.default_params()
+    po.soft_atan2 = 1
+    _, out_o, st_o = orc.make_plan_batch(sq_omap, po, o2, c2, nthreads=4)
+    r = _plan_compare(o2, out2, res2, out_o, st_o)
+    print("edge cases, strict vs oracle:", r, "statuses", res2["status"].tolist())
+    assert r["agree"] == len(legal) and r["same_flow"] == len(legal) and r["exact"] == len(legal)
+    # the same trajectories give the same results inside the ragged batch that also holds the illegal one
+    for i, b in enumerate(legal):
+        assert np.array_equal(out[off[b]:off[b + 1]], out2[o2[i]:o2[i + 1]]) and res["status"][b] == res2["status"][i]
+    # default (fast) order on the same batch: runs, and successful trajectories are collision free
+    p.strict_order = 0
+    out3, res3 = engine.make_plan_batch(p, o2, c2)
+    hit = engine.has_collision_batch(p, o2, out3)
+    assert not np.any(hit[res3["status"] == 1])
+    # beyond capacity: 400 control points need more shared memory than a block can have
+    big = np.array([-9.5, 0.0, 1.0])[None, :] + np.arange(400)[:, None] * np.array([0.04, 0.0, 0.0])[None, :]
+    with pytest.raises(TpError) as ei:
+        engine.make_plan_batch(p, np.array([0, 400], np.int32), big)
+    assert "shared memory" in str(ei.value)

@@ -1658,7 +1658,12 @@ int tp_vigo_init_guides_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B
 int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, const int32_t* offsets,
                             const double* ctrl_in, double* ctrl_out, tp_vigo_result* results, int32_t n_dyn,
                             const double* dyn_pos, const double* dyn_vel, const double* dyn_size, int mem, void* stream) {
-  if (!e || !ctrl_out || !results) return TP_ERR_INVALID_ARG;
+  if (!e) return TP_ERR_INVALID_ARG;
+  if (B == 0) {   // an empty batch is a valid no-op (after the usual parameter / map checks)
+    const int rc0 = check_params(e, p);
+    return rc0;
+  }
+  if (!ctrl_out || !results) return TP_ERR_INVALID_ARG;
   if (n_dyn < 0 || (n_dyn > 0 && (!dyn_pos || !dyn_vel || !dyn_size))) return TP_ERR_INVALID_ARG;
   CK(cudaSetDevice(e->device));
   cudaStream_t s = pick_stream(e, stream);
