@@ -209,6 +209,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=2048)
     ap.add_argument("--ref-sample", type=int, default=1024)
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / sweeps / second mode")
+    ap.add_argument("--seed-offset", type=int, default=0, help="workload seed = SEED + rank + offset (rank r of an N-GPU run uses offset r)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -234,7 +235,7 @@ def main():
     eng.set_map(pmap)
     p = tp.default_params()
     p.strict_order = 1 if args.mode == "strict" else 0
-    offsets, ctrl = make_workload(tp, pmap, eng.query_points, B, SEED + rank, p)
+    offsets, ctrl = make_workload(tp, pmap, eng.query_points, B, SEED + rank + args.seed_offset, p)
     total_pts = int(offsets[-1])
     Ns = np.diff(offsets)
 

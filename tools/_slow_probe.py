@@ -3,7 +3,7 @@ import os, sys, time, numpy as np
 sys.path.insert(0,'/root/repo')
 import trajectory_planner_b200 as tp, bench
 pmap = tp.OccMap.from_tpm(bench.MAP_TPM); eng = tp.Engine(0); eng.set_map(pmap); p = tp.default_params()
-off, ctrl = bench.make_workload(tp, pmap, eng.query_points, 4096, bench.SEED, p)
+off, ctrl = bench.make_workload(tp, pmap, eng.query_points, 4096, bench.SEED + int(os.environ.get("PROBE_SEED_OFFSET", "0")), p)
 for b in [int(x) for x in os.environ.get("PROBE_IDS", "102,1983,3909,1045").split(",")]:
     c = ctrl[off[b]:off[b+1]]; o = np.array([0, len(c)], np.int32)
     eng.make_plan_batch(p, o, c)

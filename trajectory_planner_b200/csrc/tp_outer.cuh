@@ -743,10 +743,9 @@ __device__ __noinline__ int astar_search(const DevMap& map, const VigoConst& C, 
     TICK(tB)
     int overflow = 0;
     if (lane == 0) {
-      // heap_pos values staged above can be stale for entries moved by THIS expansion's earlier
-      // pushes; re-read those through the node record (only when an update follows a push).
+      // in-place updates read the entry's CURRENT heap position from the node record: the pop and this expansion's
+      // earlier pushes may have moved it
       unsigned m = mask_new | mask_upd;
-      bool pushed = false;
       while (m) {
         const int L = __ffs(m) - 1;
         m &= m - 1;
@@ -760,7 +759,6 @@ __device__ __noinline__ int astar_search(const DevMap& map, const VigoConst& C, 
         } else {
           if (H.size >= C.heap_cap) { overflow = 1; break; }
           H.push(nid, S.st_f[L]);
-          pushed = true;
         }
       }
     }

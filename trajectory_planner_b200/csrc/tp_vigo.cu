@@ -1710,14 +1710,13 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
     e->solve_attr_set = true;
   }
   // ---- issue order.  Size classes (by control-point count) so that shared memory per block — hence resident
-  // blocks per SM — follows the trajectory length; one launch per non-empty class, on sibling streams so that a
-  // class's tail overlaps the next class's start.  A hard trajectory issued late is the batch's tail, and how hard
-  // a trajectory is shows after its first round: the solve therefore runs in TWO PASSES of the same kernel.
-  //   pass 1: every trajectory through makePlan steps 1-3 and the first optimise / check / re-guide round, ordered
-  //           inside a class by the number of control points that start inside inflated obstacles;
-  //   pass 2: the trajectories still colliding (~60 %), ordered by first-round work (L-BFGS iterations, A*
-  //           expansions, guide pairs: correlation 0.86 with the remaining time), hardest first.
-  // Every optimize() starts from a fresh L-BFGS state, so cutting a solve at a round boundary changes no result.
+  // blocks per SM — follows the trajectory length; one launch of persistent workers per non-empty class, on sibling
+  // streams.  Inside a class the queue is ordered by the number of control points that start inside inflated
+  // obstacles.  How hard a trajectory really is shows only in its first A* searches, so the workers themselves
+  // re-order the batch: cheap starts are parked after makePlan steps 1-3 and resumed once the class queues are
+  // drained, expensive starts run to the end first (k_solve, phases A / B).  TP_TWO_PASS=1 keeps the older
+  // host-driven variant of the same idea (one round for everybody, sort by first-round work on the host, second
+  // launch) for A/B measurements.
   // upper N bound of each class, largest first.  With the history in tensor memory the shared-memory footprint is
   // flat up to N = 88 (the A* scratch dominates) and grows only with the overflow elements beyond 2 per thread
   // (+12 KB at N = 104): one class serves every path the reference accepts (max_path_length 20 m => N <= 105).
@@ -1770,7 +1769,9 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
     int best[4] = {0, 0, 0, 0};
     double bestT = 1e300;
     int bestN = 0;
-    const size_t smem_sm = 227 * 1024;
+    // budget below the 228 KB of an SM: a mix that fits only to the last KB on paper (measured: 90 + 67 + 67 KB) leaves
+    // its third launch waiting for a slot until the batch is over
+    const size_t smem_sm = 222 * 1024;
     int a[4];
     for (a[0] = 0; a[0] <= 4; ++a[0])
       for (a[1] = 0; a[0] + a[1] <= 4; ++a[1])
@@ -1780,7 +1781,7 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
             bool ok = true;
             for (int c = 0; c < 4; ++c) {
               if (a[c] > 0 && nmax[c] == 0) ok = false;
-              used_sm += (size_t)a[c] * (smem[c] + 1024);
+              used_sm += (size_t)a[c] * (((smem[c] + 1023) & ~(size_t)1023) + 1024);   // 1 KB granularity + 1 KB per block
             }
             if (!ok || used_sm > smem_sm) continue;
             double T = 0, wsum = 0;
