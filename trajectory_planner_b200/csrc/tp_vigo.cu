@@ -473,14 +473,14 @@ __global__ void __launch_bounds__(32) k_plan_init(BatchView bv, VigoConst C, Dev
 // shared-memory footprint (and with it the blocks resident per SM) follows the trajectories' length.
 // Parked trajectories of one batch (see k_solve): per size class a list of ids (filled with -1 before the launch),
 // its tail (slots handed out), its head (slots claimed) and the number of trajectories that finished phase A.
-#define TP_PARK_BUCKETS 4
+#define TP_PARK_BUCKETS 6
 struct ParkQueue {
   int* list;       // [4 classes][TP_PARK_BUCKETS][stride]
   int* tail;       // [4][TP_PARK_BUCKETS]  slots handed out to parkers
   int* head;       // [4][TP_PARK_BUCKETS]  slots claimed by resumers
   int* started;    // [4]  trajectories of the class that are through phase A
   int stride;
-  int thresh;      // park when the initial searches took fewer A* expansions than this; < 0: parking disabled
+  int thresh;      // A* expansions of makePlan steps 1-3 from which a trajectory counts as a hard start; < 0: parking disabled
   int score_mode;  // difficulty score of a parked trajectory: 0 guide pairs, 1 pairs x N / 32, 2 pairs x 8 + expansions / 64
   int b[3];        // bucket bounds on the score (descending)
 };
@@ -547,9 +547,11 @@ __device__ __forceinline__ int solve_one(const BatchView& bv, const VigoConst& C
     W.flood_trigger = TP_FLOOD_TRIGGER_AGAIN;
   }
   __syncthreads();
-  if (!resume && park_thresh >= 0 && st.status == TS_ACTIVE && st.astar_expansions < park_thresh && !st.astar_unreach) {
-    // an easy start: park it (state only — the control points have not changed) and let the worker look for the
-    // batch's hard trajectories first; whoever drains the parked list resumes it at the optimise / check loop
+  if (!resume && park_thresh >= 0 && is_serial_warp && lane == 0 && W.goal_unreachable) st.astar_unreach = 1;
+  __syncthreads();
+  if (!resume && park_thresh >= 0 && st.status == TS_ACTIVE) {
+    // park it (state only — the control points have not changed): the worker goes on sweeping the batch through
+    // makePlan steps 1-3, and whoever drains the parked lists resumes it at the optimise / check loop
     const int* src = reinterpret_cast<const int*>(&st);
     int* dst = reinterpret_cast<int*>(&bv.st[b]);
     for (int i = tid; i < (int)(sizeof(TrajState) / 4); i += TP_LB_THREADS) dst[i] = src[i];
@@ -698,12 +700,12 @@ __global__ void __launch_bounds__(TP_LB_THREADS, MODE == 3 ? 4 : 3) k_solve(cons
   __syncthreads();
   const int s_slot = pick[1] & 0xFFFFFF;
   const int sw = (pick[1] >> 24) & (TP_LB_WARPS - 1);
-  // ---- phase A: the class queues, hardest-looking first.  A trajectory whose makePlan steps 1-3 turn out cheap (few A*
-  // expansions) is parked after them; one that starts with long searches — the batch's tail if it started late — is
-  // solved to the end right away.
+  // ---- phase A: sweep the class queues through makePlan steps 1-3 (segments, A*, guide points) and park every
+  // trajectory that is still active, in a bucket that says how hard it looks NOW: long first searches / unreachable
+  // goals (the batch's tail if they started late) first, then by the number of guide pairs.
   // ---- phase B (main queues drained): resume the parked trajectories, own class first, then the classes of shorter
-  // ones.  A claimed slot that is not filled yet is waited for while phase A is still running somewhere; once every
-  // trajectory of the class has been through phase A the list is final and slots beyond its end are given up.
+  // ones, hardest bucket first.  Only slots a parker has reserved are claimed; once every trajectory of the class has
+  // been through phase A the lists are final and an empty scan ends the class.
   int pb_class = -1;   // thread 0: >= 0 once this worker is in phase B
   for (;;) {
     if (tid == 0) {
@@ -750,7 +752,10 @@ __global__ void __launch_bounds__(TP_LB_THREADS, MODE == 3 ? 4 : 3) k_solve(cons
         // bucket by the guide pairs the first searches produced (the best cheap predictor of the remaining work)
         const TrajState* ps = reinterpret_cast<const TrajState*>(sm + SL.st);
         const int np = park.score_mode == 0 ? ps->n_pairs : (park.score_mode == 1 ? ps->n_pairs * ps->N / 32 : ps->n_pairs * 8 + ps->astar_expansions / 64);
-        const int q = cc * TP_PARK_BUCKETS + (np >= park.b[0] ? 0 : (np >= park.b[1] ? 1 : (np >= park.b[2] ? 2 : 3)));
+        // buckets 0 / 1: long first searches (the batch's potential tail: resumed first); 2..5 by guide pairs
+        const int bk = (ps->astar_expansions >= 4 * park.thresh || ps->astar_unreach) ? 0 : (ps->astar_expansions >= park.thresh ? 1 :
+                       (np >= park.b[0] ? 2 : (np >= park.b[1] ? 3 : (np >= park.b[2] ? 4 : 5))));
+        const int q = cc * TP_PARK_BUCKETS + bk;
         const int pos = atomicAdd(&park.tail[q], 1);
         __threadfence();                                  // the trajectory's state is in HBM before its id shows up
         atomicExch(&park.list[(size_t)q * park.stride + pos], b);
