@@ -89,6 +89,17 @@ __device__ __forceinline__ unsigned long long lds_k64(uint32_t a) {
   asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
   return v;
 }
+// six keys at once (children + grandchildren of a heap node): ONE asm statement, so that all six loads are issued
+// before the first comparison consumes any of them
+__device__ __forceinline__ void lds_k64x6(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t a5,
+                                          unsigned long long& v0, unsigned long long& v1, unsigned long long& v2,
+                                          unsigned long long& v3, unsigned long long& v4, unsigned long long& v5) {
+  asm volatile(
+      "ld.shared.u64 %0, [%6];\n\tld.shared.u64 %1, [%7];\n\tld.shared.u64 %2, [%8];\n\t"
+      "ld.shared.u64 %3, [%9];\n\tld.shared.u64 %4, [%10];\n\tld.shared.u64 %5, [%11];"
+      : "=l"(v0), "=l"(v1), "=l"(v2), "=l"(v3), "=l"(v4), "=l"(v5)
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5));
+}
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
@@ -134,11 +145,13 @@ struct Heap {
   // std::__push_heap
   __device__ __forceinline__ void sift_up(int hole, double vk, uint32_t vn) {
     if (hole < TP_HEAP_SMEM) {
+      const unsigned long long vki = (unsigned long long)__double_as_longlong(vk);   // fScore >= 0: integer order
       while (hole > 0) {
         const int parent = (hole - 1) >> 1;
-        const double pk = lds_f64(sk + 8u * parent);
-        if (!(pk > vk)) break;
-        set_s(hole, pk, lds_u32(sn + 4u * parent));
+        const unsigned long long pki = lds_k64(sk + 8u * parent);
+        const uint32_t pn = lds_u32(sn + 4u * parent);
+        if (!(pki > vki)) break;
+        set_s(hole, __longlong_as_double((long long)pki), pn);
         hole = parent;
       }
       set_s(hole, vk, vn);
@@ -239,11 +252,13 @@ struct Heap {
         const int r1 = 2 * (second + 1), l1 = r1 - 1;
         const int rr = 2 * (r1 + 1), lr = 2 * r1;
         const bool spec = rr < TP_HEAP_SMEM;
-        const unsigned long long kr1 = lds_k64(sk + 8u * r1), kl1 = lds_k64(sk + 8u * l1);
-        unsigned long long krr = 0, krl = 0, klr = 0, kll = 0;
+        unsigned long long kr1, kl1, krr = 0, krl = 0, klr = 0, kll = 0;
         if (spec) {
-          krr = lds_k64(sk + 8u * rr); krl = lds_k64(sk + 8u * rr - 8u);
-          klr = lds_k64(sk + 8u * lr); kll = lds_k64(sk + 8u * lr - 8u);
+          lds_k64x6(sk + 8u * r1, sk + 8u * l1, sk + 8u * rr, sk + 8u * rr - 8u, sk + 8u * lr, sk + 8u * lr - 8u, kr1, kl1, krr,
+                    krl, klr, kll);
+        } else {
+          kr1 = lds_k64(sk + 8u * r1);
+          kl1 = lds_k64(sk + 8u * l1);
         }
         const bool left1 = kr1 > kl1;
         second = left1 ? l1 : r1;
