@@ -483,8 +483,10 @@ __device__ __noinline__ int flood_component(const DevMap& map, const VigoConst& 
   // The ring holds ~3 300 cells; a wide front (open rooms) outgrows it.  Order is irrelevant for a flood, so the oldest
   // half of a full ring is moved to an overflow STACK in the heap's HBM spill area (below the parked heap) and fetched
   // back when the ring runs dry.
-  uint32_t* ovf = reinterpret_cast<uint32_t*>(W.heap_k_gl);
-  const int ovf_cap = (C.heap_cap - TP_HEAP_SMEM) * 2;
+  // (above the heap entries that already live in the spill area: those beyond TP_HEAP_SMEM)
+  const int spilled = heap_size > TP_HEAP_SMEM ? heap_size - TP_HEAP_SMEM : 0;
+  uint32_t* ovf = reinterpret_cast<uint32_t*>(W.heap_k_gl + spilled);
+  const int ovf_cap = (C.heap_cap - TP_HEAP_SMEM - spilled) * 2;
   int ovf_n = 0, n_spills = 0;
   for (;;) {
     int n = (int)(tail - head);

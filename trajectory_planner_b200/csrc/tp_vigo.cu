@@ -918,6 +918,7 @@ struct tp_engine {
   size_t h_stage_cap = 0;
   bool lbfgs_attr_set = false;
   int max_smem_optin = 0;
+  bool fe_attr_set = false;
   // measurement
   bool profile = false;
   DevBuf dev_counters;  // 8 doubles
@@ -1941,10 +1942,9 @@ int64_t tp_vigo_frontend_batch_device(tp_engine_t* e, const tp_vigo_params* p, i
   int* d_count = e->scratch_c.as<int>();
   int* d_off = d_count + B;
   unsigned char* d_valid = reinterpret_cast<unsigned char*>(d_off + B + 1);
-  static bool attr = false;
-  if (!attr) {
+  if (!e->fe_attr_set) {   // per engine = per device (function attributes are per context)
     CK(cudaFuncSetAttribute(k_frontend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FeSmem)));
-    attr = true;
+    e->fe_attr_set = true;
   }
   const int grid = std::min(B, e->sm_count * 5);
   {
