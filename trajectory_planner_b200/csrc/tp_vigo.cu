@@ -1697,13 +1697,21 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
   }
   rc = ensure_pools(e, bs.C);
   if (rc != TP_OK) return rc;
-  const int mode = lbfgs_mode(p);
+  int mode = lbfgs_mode(p);
+  {
+    // Throughput-bound batches (several waves of trajectories per worker) do better with the history in tensor memory:
+    // 4 workers per SM instead of 3 (76.7 k vs 72.0 k solves/s at 16 384, 73.8 k vs 70.0 k at 8 192); batches whose makespan is a few long
+    // trajectories do better with the faster block of the shared-memory variant (67.7 k vs 65.2 k at 4 096).
+    static const bool forced = getenv("TP_LBFGS_TMEM") != nullptr || getenv("TP_LBFGS_SMEM_HISTORY") != nullptr;
+    static const int tm_batch = getenv("TP_TMEM_BATCH") ? atoi(getenv("TP_TMEM_BATCH")) : 8192;
+    if (mode == 2 && !forced && B >= tm_batch) mode = 3;
+  }
   if (!e->solve_attr_set) {
     CK(cudaFuncSetAttribute(k_solve<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
     CK(cudaFuncSetAttribute(k_solve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
     CK(cudaFuncSetAttribute(k_solve<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
     CK(cudaFuncSetAttribute(k_solve<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
-    CK(cudaFuncSetAttribute(k_solve<3>, cudaFuncAttributePreferredSharedMemoryCarveout, getenv("TP_CARVEOUT") ? atoi(getenv("TP_CARVEOUT")) : 100));
+    CK(cudaFuncSetAttribute(k_solve<3>, cudaFuncAttributePreferredSharedMemoryCarveout, getenv("TP_CARVEOUT") ? atoi(getenv("TP_CARVEOUT")) : 70));   // 4 x 33.5 KB of shared memory: leave the rest to L1
     CK(cudaFuncSetAttribute(k_solve<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CK(cudaFuncSetAttribute(k_solve<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CK(cudaFuncSetAttribute(k_solve<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -1728,7 +1736,7 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
   // (+12 KB at N = 104): one class serves every path the reference accepts (max_path_length 20 m => N <= 105).
   static const int class_lim_smem[4] = {TP_MAX_CTRL, 104, 64, 40};
   static const int class_lim_tm[4] = {TP_MAX_CTRL, 160, 104, 0};
-  const int* class_lim = lbfgs_mode(p) == 3 ? class_lim_tm : class_lim_smem;
+  const int* class_lim = mode == 3 ? class_lim_tm : class_lim_smem;
   auto class_of = [&](int b) {
     const int n = bs.h_off[b + 1] - bs.h_off[b];
     return n > class_lim[1] ? 0 : (n > class_lim[2] ? 1 : (n > class_lim[3] ? 2 : 3));
