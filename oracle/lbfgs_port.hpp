@@ -10,7 +10,7 @@
 // written as one self-contained class without the callback/progress plumbing the reference's
 // ViGO path never uses (proc_stepbound = proc_progress = NULL, past = 0; bsplineTraj.cpp:701).
 // `oracle/_ref` builds the same oracle against the reference header itself
-// (-DTP_ORACLE_REF_LBFGS) and tests/test_oracle_lbfgs.py pins this port to it bit-for-bit.
+// (-DTP_ORACLE_REF_LBFGS) and tests/test_oracle_cpu.py::test_lbfgs_port_is_pinned_to_reference_header pins this port to it bit-for-bit.
 #pragma once
 #include <cmath>
 #include <cstring>

@@ -13,7 +13,7 @@
 //  * The one piece that does compile standalone — solver/lbfgs.hpp — is pulled in directly
 //    from /root/reference by the `oracle/_ref` build (-DTP_ORACLE_REF_LBFGS) and this
 //    oracle's own L-BFGS restatement (lbfgs_port.hpp) is pinned to it bit-for-bit by
-//    tests/test_oracle_lbfgs.py.  => L-BFGS iterate: PINNED to reference code.
+//    tests/test_oracle_cpu.py::test_lbfgs_port_is_pinned_to_reference_header.  => L-BFGS iterate: PINNED to reference code.
 //  * Everything else (costs, de Boor, collision logic, A*, guide points): restated from the
 //    reference source by reading it; "parity unpinned" by reference-run outputs.  It is pinned
 //    by analytic known-answer tests and finite-difference gradient checks in tests/.
