@@ -25,7 +25,7 @@ class VigoParams(C.Structure):
         ("not_check_ratio", C.c_double), ("lbfgs_g_eps", C.c_double),
         ("plan_in_z", C.c_int), ("lbfgs_m", C.c_int), ("lbfgs_max_iter", C.c_int),
         ("lbfgs_max_linesearch", C.c_int), ("max_outer_rounds", C.c_int), ("astar_max_expansions", C.c_int),
-        ("use_ref_lbfgs", C.c_int), ("soft_atan2", C.c_int), ("vclock_budget", C.c_int), ("reserved2", C.c_int),
+        ("use_ref_lbfgs", C.c_int), ("soft_atan2", C.c_int), ("vclock_budget", C.c_int), ("fast_order", C.c_int),
     ]
 
 
@@ -90,6 +90,10 @@ class Lib:
         L.orc_planner_cost.restype = C.c_double
         L.orc_planner_cost.argtypes = [C.c_void_p, _dp, _dp, C.c_int, _dp]
         L.orc_planner_optimize.argtypes = [C.c_void_p, _ip, _dp, _dp]
+        L.orc_planner_cost_wform.restype = C.c_double
+        L.orc_planner_cost_wform.argtypes = [C.c_void_p, _dp, _dp, C.c_int]
+        L.orc_planner_wform_direction_check.restype = C.c_double
+        L.orc_planner_wform_direction_check.argtypes = [C.c_void_p, _ip]
         L.orc_planner_find_collision_seg.argtypes = [C.c_void_p, _ip, C.c_int]
         L.orc_planner_has_collision.argtypes = [C.c_void_p]
         L.orc_planner_init_guides.argtypes = [C.c_void_p]
@@ -242,6 +246,20 @@ class Planner:
         terms = np.zeros(4)
         f = self.lib.L.orc_planner_cost(self.h, _p(x), _p(g), len(x), _p(terms))
         return f, g, terms
+
+    def cost_wform(self, x):
+        """costFunction in the product's warp-form arithmetic (oracle/wform_port.hpp)."""
+        x = _d(x).ravel()
+        g = np.zeros_like(x)
+        f = self.lib.L.orc_planner_cost_wform(self.h, _p(x), _p(g), len(x))
+        return f, g
+
+    def wform_direction_check(self):
+        """One warp-form optimize(); returns (worst relative difference between the Gram-form direction and the
+        reference's two-loop recursion on the same (g, S, Y), stats)."""
+        out = np.zeros(3, np.int32)
+        worst = self.lib.L.orc_planner_wform_direction_check(self.h, _p(out, _ip))
+        return worst, dict(ret=int(out[0]), iters=int(out[1]), evals=int(out[2]))
 
     def optimize(self):
         out = np.zeros(4, np.int32)

@@ -20,6 +20,7 @@
 #include <utility>
 
 #include "lbfgs_port.hpp"
+#include "wform_port.hpp"
 #ifdef TP_ORACLE_REF_LBFGS
 // The reference's own header, straight from /root/reference (never copied into this repo).
 #include "trajectory_planner/solver/lbfgs.hpp"
@@ -603,6 +604,14 @@ struct Planner {
     int n = 3 * (N - 2 * bsplineDegree);
     std::vector<double> x(ctrl.begin() + 3 * bsplineDegree, ctrl.begin() + 3 * bsplineDegree + n);
     LbfgsStats st;
+    if (P.fast_order) {
+      // the product's default arithmetic (warp form, oracle/wform_port.hpp): operates in place on ctrl
+      wform::Problem wp;
+      fillWformProblem(wp);
+      wform::Solver ws(wp, P.fast_order == 1 ? 1 : 4);
+      ws.trace = wtrace;
+      st = ws.run(x.data());
+    } else
 #ifdef TP_ORACLE_REF_LBFGS
     if (P.use_ref_lbfgs) {
       lbfgs::lbfgs_parameter_t sp;
@@ -636,6 +645,52 @@ struct Planner {
     stats.final_cost = st.fx;
     last_x = x;
     return st;
+  }
+  wform::Trace* wtrace = nullptr;
+  // inputs of the warp-form solve, constants derived as the product's make_const (tp_vigo.cu) derives them
+  void fillWformProblem(wform::Problem& wp) {
+    wp.N = N;
+    wp.cp = ctrl.data();
+    wp.pstart.assign(N + 1, 0);
+    wp.pairs.clear();
+    for (int i = 0; i < N; ++i) {
+      for (size_t j = 0; j < guideP[i].size(); ++j) {
+        const V3& p = guideP[i][j];
+        const V3& v = guideV[i][j];
+        const double row[7] = {p.x, p.y, p.z, v.x, v.y, v.z, map->isUnknown(p) ? 1.0 : 0.0};
+        wp.pairs.insert(wp.pairs.end(), row, row + 7);
+      }
+      wp.pstart[i + 1] = (int)(wp.pairs.size() / 7);
+    }
+    wp.ctrl_pt_ts = P.ctrl_pt_ts; wp.ts = P.ts; wp.dthresh = P.dthresh; wp.dthresh_dyn = P.dthresh_dyn;
+    wp.w_dist = wDist; wp.w_smooth = P.w_smooth; wp.w_feas = P.w_feas; wp.w_dyn = wDyn;
+    wp.uncertain_factor = P.uncertain_factor; wp.min_height = P.min_height; wp.max_height = P.max_height;
+    wp.plan_in_z = P.plan_in_z;
+    wp.pred_num = (int)(P.pred_horizon / P.ts);
+    const double dth = P.dthresh, hth = 0.2, dd = P.dthresh_dyn;
+    wp.dist_a = 3.0 * dth; wp.dist_b = -3.0 * (dth * dth); wp.dist_c = std::pow(dth, 3);
+    wp.h_a = 3.0 * hth; wp.h_b = -3 * (hth * hth); wp.h_c = std::pow(hth, 3);
+    wp.dyn_a = 3.0 * dd; wp.dyn_b = -3 * (dd * dd); wp.dyn_c = std::pow(dd, 3);
+    wp.ts_inv_sqr = 1 / (P.ctrl_pt_ts * P.ctrl_pt_ts);
+    for (size_t j = 0; j < dynPos.size(); ++j) {
+      const double a[3] = {dynPos[j].x, dynPos[j].y, dynPos[j].z}, b[3] = {dynVel[j].x, dynVel[j].y, dynVel[j].z},
+                   c[3] = {dynSize[j].x, dynSize[j].y, dynSize[j].z};
+      wp.dyn_pos.insert(wp.dyn_pos.end(), a, a + 3);
+      wp.dyn_vel.insert(wp.dyn_vel.end(), b, b + 3);
+      wp.dyn_size.insert(wp.dyn_size.end(), c, c + 3);
+    }
+    wp.g_eps = P.lbfgs_g_eps; wp.max_iter = P.lbfgs_max_iter; wp.max_linesearch = P.lbfgs_max_linesearch;
+  }
+  // costFunction in the warp form's arithmetic (one evaluation at the current control points)
+  double costFunctionWform(double* grad, int n) {
+    wform::Problem wp;
+    fillWformProblem(wp);
+    wform::Solver ws(wp, P.fast_order == 1 ? 1 : 4);
+    double f, dg, gg, xx;
+    ws.f_const = ws.const_terms();
+    ws.eval(false, f, dg, gg, xx);
+    std::memcpy(grad, ws.g.data(), sizeof(double) * n);
+    return f;
   }
   std::vector<double> last_x;
   long long vclock = 0;  // virtual clock, 10 ns units (see VigoParams::vclock_budget)
@@ -1149,6 +1204,60 @@ int orc_planner_optimize(void* pl_, int* out4, double* fx, double* x_final) {
   *fx = st.fx;
   if (x_final) std::memcpy(x_final, pl->last_x.data(), sizeof(double) * pl->last_x.size());
   return st.ret;
+}
+// costFunction in the warp form's arithmetic at x (the benchmarked kernel's evaluation)
+double orc_planner_cost_wform(void* pl_, const double* x, double* grad, int n) {
+  Planner* pl = (Planner*)pl_;
+  std::memcpy(pl->ctrl.data() + 3 * bsplineDegree, x, n * sizeof(double));
+  return pl->costFunctionWform(grad, n);
+}
+// One warp-form optimize() with a per-iteration direction check: for the (g, S, Y) the warp form had at every iteration,
+// recompute the direction with the reference's two-loop recursion in its serial order (lbfgs.hpp:1293-1316) and return
+// the largest ||d_gram - d_twoloop|| / ||d_twoloop||; out3 = {ret, iters, evals}.
+double orc_planner_wform_direction_check(void* pl_, int* out3) {
+  Planner* pl = (Planner*)pl_;
+  const int keep = pl->P.fast_order;
+  if (!keep) pl->P.fast_order = 4;
+  wform::Trace tr;
+  pl->wtrace = &tr;
+  LbfgsStats st = pl->optimize();
+  pl->wtrace = nullptr;
+  pl->P.fast_order = keep;
+  out3[0] = st.ret; out3[1] = st.iters; out3[2] = st.evals;
+  const int m = 16;
+  double worst = 0.0;
+  for (size_t it = 0; it < tr.d.size(); ++it) {
+    const int n = (int)tr.g[it].size();
+    const std::vector<double>& S = tr.S[it];
+    const std::vector<double>& Y = tr.Y[it];
+    std::vector<double> d(n), alpha(m, 0.0);
+    for (int i = 0; i < n; ++i) d[i] = -tr.g[it][i];
+    const int newest = tr.end[it], bound = tr.bound[it];
+    const double ys = detail::dot(&Y[(size_t)newest * n], &S[(size_t)newest * n], n);
+    const double yy = detail::dot(&Y[(size_t)newest * n], &Y[(size_t)newest * n], n);
+    int j = (newest + 1) % m;
+    for (int i = 0; i < bound; ++i) {
+      j = (j + m - 1) % m;
+      alpha[j] = detail::dot(&S[(size_t)j * n], d.data(), n);
+      alpha[j] /= detail::dot(&Y[(size_t)j * n], &S[(size_t)j * n], n);
+      const double c = -alpha[j];
+      for (int e = 0; e < n; ++e) d[e] += c * Y[(size_t)j * n + e];
+    }
+    const double sc = ys / yy;
+    for (int e = 0; e < n; ++e) d[e] *= sc;
+    for (int i = 0; i < bound; ++i) {
+      double beta = detail::dot(&Y[(size_t)j * n], d.data(), n);
+      beta /= detail::dot(&Y[(size_t)j * n], &S[(size_t)j * n], n);
+      const double c = alpha[j] - beta;
+      for (int e = 0; e < n; ++e) d[e] += c * S[(size_t)j * n + e];
+      j = (j + 1) % m;
+    }
+    double num = 0.0, den = 0.0;
+    for (int e = 0; e < n; ++e) { const double df = tr.d[it][e] - d[e]; num += df * df; den += d[e] * d[e]; }
+    const double rel = std::sqrt(num) / std::sqrt(den);
+    if (rel > worst) worst = rel;
+  }
+  return worst;
 }
 int orc_planner_find_collision_seg(void* pl_, int* segs, int cap) {
   Planner* pl = (Planner*)pl_;

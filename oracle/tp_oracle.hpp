@@ -90,7 +90,8 @@ struct VigoParams {
   // path: ~0.1 us per control point per cost evaluation incl. its share of the two-loop recursion,
   // ~0.3 us per expansion), checked where the reference checks its clock.  0 disables it.
   int vclock_budget;         // default 3,000,000 (= 30 ms)
-  int reserved2;
+  int fast_order;            // 4 / 1: optimize() runs the product's lean-form arithmetic with a team of 4 warps (the
+                             // product's default) / 1 warp (oracle/wform_port.hpp); 0: reference order
 };
 
 struct PlanStats {

@@ -10,6 +10,7 @@
 
 #include "tp_lbfgs.cuh"
 #include "tp_lbfgs_fast.cuh"
+#include "tp_lbfgs_warp.cuh"
 #include "tp_frontend.cuh"
 #include "tp_map.h"
 #include "tp_outer.cuh"
@@ -123,6 +124,29 @@ __global__ void __launch_bounds__(TP_LB_THREADS) k_cost(BatchView bv, VigoConst 
   for (int e = tid; e < n; e += TP_LB_THREADS) go[e] = g[e];
 }
 
+// ---- costFunction in the team form (4 warps), the default evaluation
+__global__ void __launch_bounds__(TP_LB_THREADS) k_cost_t(BatchView bv, VigoConst C, double* f_out, double* grad_out) {
+  extern __shared__ double sm[];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const TrajState& st = bv.st[b];
+  const int N = st.N, n = 3 * (N - 2 * TP_DEGREE);
+  if (n <= 0) {
+    if (tid == 0) f_out[b] = 0.0;
+    return;
+  }
+  const WfLayout L = wf_layout(N);
+  for (int e = tid; e < 3 * N; e += TP_LB_THREADS) sm[L.cp + e] = bv.ctrl[3 * (size_t)st.off + e];
+  __syncthreads();
+  wf_setup<TP_LB_WARPS>(C, sm, N, bv.pairs + (size_t)b * C.gcap, bv.cp_head + st.off, st.n_pairs, st.w_dist, st.w_dyn, bv.n_dyn,
+                        bv.dyn_pos, bv.dyn_vel, bv.dyn_size, tid);
+  double ev[4];
+  wf_eval<TP_LB_WARPS>(C, sm, 0, ev, tid);
+  __syncthreads();
+  if (tid == 0) f_out[b] = ev[0];
+  double* go = grad_out + 3 * ((size_t)st.off - (size_t)2 * TP_DEGREE * b);
+  for (int e = tid; e < n; e += TP_LB_THREADS) go[e] = sm[L.g + e];
+}
+
 // ---- optimize(): fused cost + L-BFGS, one block per ACTIVE trajectory.
 // MODE 0: classic two-loop, tree reductions; 1: classic, serial-order (bit-faithful); 2: vector-free (tp_lbfgs_fast.cuh)
 template <int MODE>
@@ -142,7 +166,7 @@ __global__ void __launch_bounds__(TP_LB_THREADS, 4) k_lbfgs(BatchView bv, VigoCo
   if (n <= 0) {
     r.ret = LB_INVALID_N; r.iters = 0; r.evals = 0; r.reserved = 0; r.fx = 0;
   } else {
-    double* cp = sm;
+    double* cp = MODE == 4 ? sm + WF_CTX : sm;
     double* gctrl = bv.ctrl + 3 * (size_t)st.off;
     for (int e = tid; e < 3 * N; e += TP_LB_THREADS) cp[e] = gctrl[e];
     EvalCtx E;
@@ -152,7 +176,11 @@ __global__ void __launch_bounds__(TP_LB_THREADS, 4) k_lbfgs(BatchView bv, VigoCo
     E.w_dist = st.w_dist; E.w_dyn = st.w_dyn;
     E.n_dyn = bv.n_dyn; E.dyn_pos = bv.dyn_pos; E.dyn_vel = bv.dyn_vel; E.dyn_size = bv.dyn_size;
     double* xf = xfinal_out ? xfinal_out + 3 * ((size_t)st.off - (size_t)2 * TP_DEGREE * b) : nullptr;
-    if (MODE >= 2) {
+    if (MODE == 4) {
+      __syncthreads();
+      wf_setup<TP_LB_WARPS>(C, sm, N, E.pairs, E.head, st.n_pairs, E.w_dist, E.w_dyn, E.n_dyn, E.dyn_pos, E.dyn_vel, E.dyn_size, tid);
+      lbfgs_run_team<TP_LB_WARPS>(C, sm, N, 0, r, xf, tid);
+    } else if (MODE >= 2) {
       VfCtx V;
       V.N = N; V.n = n; V.sm = sm; V.L = vf_layout(N, MODE == 3);
       V.pairs = E.pairs; V.head = E.head; V.n_pairs = st.n_pairs; V.pairs_in_sm = false; V.serial_warp = 0;
@@ -497,8 +525,9 @@ __host__ __device__ inline SolveLayout solve_layout(int N, int mode, int m) {
   L.st = o; o += (int)((sizeof(TrajState) + 7) / 8);
   L.vf = o;
   const int cp_d = 3 * N + (N & 1);
-  const int solver = mode >= 2 ? vf_layout(N, mode == 3).total : (int)lbfgs_smem_doubles(N, m) + (N & 1);
-  L.plan = L.vf + cp_d;
+  // mode 4 (team form): the solver region starts with the WfShared context, then the control points
+  const int solver = mode == 4 ? wf_layout(N).total : (mode >= 2 ? vf_layout(N, mode == 3).total : (int)lbfgs_smem_doubles(N, m) + (N & 1));
+  L.plan = L.vf + cp_d + (mode == 4 ? WF_CTX : 0);
   const int plan_end = L.plan + (int)((sizeof(PlanSmem) + 7) / 8);
   const int rp_end = L.plan + 3 * (N - 1) + 3 * (N - 2) + 2 * TP_LB_WARPS + 4;
   int end = L.vf + solver;
@@ -519,7 +548,7 @@ __device__ __forceinline__ int solve_one(const BatchView& bv, const VigoConst& C
   if (timeline && tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start));
   const SolveLayout SL = solve_layout(class_max_n, MODE, C.p.lbfgs_m);
   TrajState& st = *reinterpret_cast<TrajState*>(sm + SL.st);
-  double* cp = sm + SL.vf;
+  double* cp = sm + SL.vf + (MODE == 4 ? WF_CTX : 0);
   PlanSmem& PS = *reinterpret_cast<PlanSmem*>(sm + SL.plan);
   // ---- load state + control points
   {
@@ -576,6 +605,10 @@ __device__ __forceinline__ int solve_one(const BatchView& bv, const VigoConst& C
     tp_lbfgs_result r;
     if (n <= 0) {
       r.ret = LB_INVALID_N; r.iters = 0; r.evals = 0; r.reserved = 0; r.fx = 0;
+    } else if (MODE == 4) {
+      wf_setup<TP_LB_WARPS>(C, sm + SL.vf, N, bv.pairs + (size_t)b * C.gcap, bv.cp_head + st.off, st.n_pairs, st.w_dist, st.w_dyn,
+                            bv.n_dyn, bv.dyn_pos, bv.dyn_vel, bv.dyn_size, tid);
+      lbfgs_run_team<TP_LB_WARPS>(C, sm + SL.vf, N, sw, r, nullptr, tid);
     } else if (MODE >= 2) {
       VfCtx V;
       V.N = N; V.n = n; V.sm = cp; V.L = vf_layout(N, MODE == 3);
@@ -666,6 +699,7 @@ __device__ __forceinline__ int solve_one(const BatchView& bv, const VigoConst& C
     }
   }
   __syncthreads();
+  return 0;
 }
 
 // Persistent workers: one launch per size class; a worker of class c owns shared memory for that class's longest
@@ -770,6 +804,8 @@ __global__ void __launch_bounds__(TP_LB_THREADS, MODE == 3 ? 4 : 3) k_solve(cons
   }
   if (MODE == 3) tm_block_free(tm_slot, tid);
 }
+
+#include "tp_solve_warp.cuh"
 
 // standalone A* (parity entry): one warp per (start, end) pair
 __global__ void __launch_bounds__(32) k_astar(VigoConst C, DevMap map, AStarPools P, int* queue, int S_,
@@ -1229,19 +1265,28 @@ __global__ void k_resolve_unknown(BatchView bv, VigoConst C, DevMap map) {
 // FP64 MMA Gram update (default); 3 vector-free with the history in tensor memory (TP_LBFGS_TMEM=1: 4 workers per SM
 // instead of 3, measured slower per iteration so far); 0 classic two-loop with tree reductions (lbfgs_m != 16, or
 // TP_LBFGS_CLASSIC=1)
+// 4 = lean team form (tp_lbfgs_warp.cuh) with a team of four warps per trajectory, the default; 5 = the same arithmetic
+// family with a team of ONE warp (TP_WARP_FORM=1: its results differ in rounding from mode 4's, both are pinned to the
+// oracle); TP_LBFGS_BLOCK=1 keeps the round-1 forms 2 / 3 for A/B measurements
 static int lbfgs_mode(const tp_vigo_params* p) {
   if (p->strict_order) return 1;
   static const bool classic = getenv("TP_LBFGS_CLASSIC") != nullptr;
   static const bool tmem_hist = getenv("TP_LBFGS_TMEM") != nullptr;
-  return (p->lbfgs_m == VF_M && !classic) ? (tmem_hist ? 3 : 2) : 0;
+  static const bool block_form = getenv("TP_LBFGS_BLOCK") != nullptr || tmem_hist;
+  static const bool warp_form = getenv("TP_WARP_FORM") != nullptr;
+  if (p->lbfgs_m != VF_M || classic) return 0;
+  return block_form ? (tmem_hist ? 3 : 2) : (warp_form ? 5 : 4);
 }
 static size_t lbfgs_smem_bytes(const tp_vigo_params* p, int max_n) {
   const int mode = lbfgs_mode(p);
+  if (mode >= 4) return (size_t)wf_layout(max_n).total * 8;
   return mode >= 2 ? vf_smem_bytes(max_n, mode == 3) + 16 : lbfgs_smem_doubles(max_n, p->lbfgs_m) * 8;
 }
 template <class... A>
 static void launch_lbfgs(int mode, int grid, size_t smem, cudaStream_t s, A... args) {
-  if (mode == 1) k_lbfgs<1><<<grid, TP_LB_THREADS, smem, s>>>(args...);
+  if (mode == 5) k_lbfgs_w<<<grid, 32, smem, s>>>(args...);
+  else if (mode == 4) k_lbfgs<4><<<grid, TP_LB_THREADS, smem, s>>>(args...);
+  else if (mode == 1) k_lbfgs<1><<<grid, TP_LB_THREADS, smem, s>>>(args...);
   else if (mode == 2) k_lbfgs<2><<<grid, TP_LB_THREADS, smem, s>>>(args...);
   else if (mode == 3) k_lbfgs<3><<<grid, TP_LB_THREADS, smem, s>>>(args...);
   else k_lbfgs<0><<<grid, TP_LB_THREADS, smem, s>>>(args...);
@@ -1259,6 +1304,10 @@ static int set_lbfgs_smem(tp_engine* e, size_t bytes) {
     CK(cudaFuncSetAttribute(k_lbfgs<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
     CK(cudaFuncSetAttribute(k_cost<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
     CK(cudaFuncSetAttribute(k_cost<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
+    CK(cudaFuncSetAttribute(k_lbfgs<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
+    CK(cudaFuncSetAttribute(k_cost_t, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
+    CK(cudaFuncSetAttribute(k_lbfgs_w, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
+    CK(cudaFuncSetAttribute(k_cost_w, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
     e->lbfgs_attr_set = true;
   }
   return TP_OK;
@@ -1476,10 +1525,14 @@ int tp_vigo_cost_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, const
   k_resolve_unknown<<<(int)(((long)B * bs.C.gcap + 255) / 256), 256, 0, s>>>(bs.bv, bs.C, e->dmap);
   const size_t nvar = (size_t)std::max<long>(3 * (bs.total - 6L * B), 1);
   if (e->scratch_a.ensure((size_t)B * 8) != TP_OK || e->scratch_b.ensure(nvar * 8) != TP_OK) return TP_ERR_CUDA;
-  const size_t smem = p->strict_order ? ((size_t)3 * bs.max_n + 3 * (size_t)bs.max_n + 40) * 8 : vf_smem_bytes(bs.max_n);
+  const int cmode = lbfgs_mode(p);
+  const size_t smem = p->strict_order ? ((size_t)3 * bs.max_n + 3 * (size_t)bs.max_n + 40) * 8
+                                      : (cmode >= 4 ? (size_t)wf_layout(bs.max_n).total * 8 : vf_smem_bytes(bs.max_n));
   rc = set_lbfgs_smem(e, smem);
   if (rc != TP_OK) return rc;
-  if (p->strict_order) k_cost<true><<<B, TP_LB_THREADS, smem, s>>>(bs.bv, bs.C, e->scratch_a.as<double>(), e->scratch_b.as<double>());
+  if (cmode == 4) k_cost_t<<<B, TP_LB_THREADS, smem, s>>>(bs.bv, bs.C, e->scratch_a.as<double>(), e->scratch_b.as<double>());
+  else if (cmode == 5) k_cost_w<<<B, 32, smem, s>>>(bs.bv, bs.C, e->scratch_a.as<double>(), e->scratch_b.as<double>());
+  else if (p->strict_order) k_cost<true><<<B, TP_LB_THREADS, smem, s>>>(bs.bv, bs.C, e->scratch_a.as<double>(), e->scratch_b.as<double>());
   else k_cost<false><<<B, TP_LB_THREADS, smem, s>>>(bs.bv, bs.C, e->scratch_a.as<double>(), e->scratch_b.as<double>());
   e->launches += 2;
   CK(cudaGetLastError());
@@ -1715,6 +1768,10 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
     CK(cudaFuncSetAttribute(k_solve<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CK(cudaFuncSetAttribute(k_solve<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CK(cudaFuncSetAttribute(k_solve<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK(cudaFuncSetAttribute(k_solve<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
+    CK(cudaFuncSetAttribute(k_solve<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK(cudaFuncSetAttribute(k_solve_w, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
+    CK(cudaFuncSetAttribute(k_solve_w, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     for (int i = 0; i < 8; ++i) {
       CK(cudaStreamCreateWithFlags(&e->class_stream[i], cudaStreamNonBlocking));
       CK(cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming));
@@ -1771,7 +1828,7 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
     size_t smem[4] = {0, 0, 0, 0};
     for (int c = 0; c < 4; ++c)
       if (nmax[c] > 0) {
-        smem[c] = (size_t)solve_layout(nmax[c], mode, p->lbfgs_m).total * 8 + 16;
+        smem[c] = mode == 5 ? (size_t)wsolve_layout(nmax[c]).total * 8 : (size_t)solve_layout(nmax[c], mode, p->lbfgs_m).total * 8 + 16;
         if ((int)smem[c] > e->max_smem_optin) {
           tp_set_error("a %d-control-point trajectory needs %zu B of shared memory (> %d B per block)", nmax[c], smem[c], e->max_smem_optin);
           return TP_ERR_CAPACITY;
@@ -1786,11 +1843,14 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
     // budget below the 228 KB of an SM: a mix that fits only to the last KB on paper (measured: 90 + 67 + 67 KB) leaves
     // its third launch waiting for a slot until the batch is over
     const size_t smem_sm = 222 * 1024;
+    // warp form: a worker is one warp (its own block of 32 threads); registers allow up to 12 per SM
+    static const int wf_max = getenv("TP_W_MAX") ? atoi(getenv("TP_W_MAX")) : 12;
+    const int maxw = mode == 5 ? wf_max : 4;
     int a[4];
-    for (a[0] = 0; a[0] <= 4; ++a[0])
-      for (a[1] = 0; a[0] + a[1] <= 4; ++a[1])
-        for (a[2] = 0; a[0] + a[1] + a[2] <= 4; ++a[2])
-          for (a[3] = 0; a[0] + a[1] + a[2] + a[3] <= 4; ++a[3]) {
+    for (a[0] = 0; a[0] <= maxw; ++a[0])
+      for (a[1] = 0; a[0] + a[1] <= maxw; ++a[1])
+        for (a[2] = 0; a[0] + a[1] + a[2] <= maxw; ++a[2])
+          for (a[3] = 0; a[0] + a[1] + a[2] + a[3] <= maxw; ++a[3]) {
             size_t used_sm = 0;
             bool ok = true;
             for (int c = 0; c < 4; ++c) {
@@ -1862,9 +1922,11 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
       {
         ProfScope ps(e, 0, cs, grid);
         const int* ord = e->active[0].as<int>();
-        if (mode == 1) k_solve<1><<<grid, TP_LB_THREADS, smem[c], cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, d_cb, d_cb + 5, c, nmax[c], e->pool_flags.as<int>(), e->counters_ptr(), tl, resume, rounds, pq);
+        if (mode == 5) k_solve_w<<<grid, 32, smem[c], cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, d_cb, d_cb + 5, c, nmax[c], (int)(smem[c] / 8), e->pool_flags.as<int>(), e->counters_ptr(), tl, resume, rounds, pq);
+        else if (mode == 1) k_solve<1><<<grid, TP_LB_THREADS, smem[c], cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, d_cb, d_cb + 5, c, nmax[c], e->pool_flags.as<int>(), e->counters_ptr(), tl, resume, rounds, pq);
         else if (mode == 2) k_solve<2><<<grid, TP_LB_THREADS, smem[c], cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, d_cb, d_cb + 5, c, nmax[c], e->pool_flags.as<int>(), e->counters_ptr(), tl, resume, rounds, pq);
         else if (mode == 3) k_solve<3><<<grid, TP_LB_THREADS, smem[c], cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, d_cb, d_cb + 5, c, nmax[c], e->pool_flags.as<int>(), e->counters_ptr(), tl, resume, rounds, pq);
+        else if (mode == 4) k_solve<4><<<grid, TP_LB_THREADS, smem[c], cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, d_cb, d_cb + 5, c, nmax[c], e->pool_flags.as<int>(), e->counters_ptr(), tl, resume, rounds, pq);
         else k_solve<0><<<grid, TP_LB_THREADS, smem[c], cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, d_cb, d_cb + 5, c, nmax[c], e->pool_flags.as<int>(), e->counters_ptr(), tl, resume, rounds, pq);
       }
       CK(cudaGetLastError());
@@ -1988,6 +2050,15 @@ int64_t tp_vigo_frontend_batch_device(tp_engine_t* e, const tp_vigo_params* p, i
   return total;
 }
 
+#ifdef TP_WF_TIMING
+// development builds only (build_timing.sh with EXTRA=-DTP_WF_TIMING): whole-batch warp-form phase cycle totals, reset on read
+extern "C" int tp_debug_wf_phase_get(unsigned long long* out) {
+  unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (cudaMemcpyFromSymbol(out, g_wf_phase, sizeof(z)) != cudaSuccess) return -1;
+  if (cudaMemcpyToSymbol(g_wf_phase, z, sizeof(z)) != cudaSuccess) return -1;
+  return 0;
+}
+#endif
 #ifdef TP_LBFGS_TIMING
 // development builds only (build_timing.sh): whole-batch L-BFGS phase cycle totals, reset on read
 extern "C" int tp_debug_phase_get(unsigned long long* out) {
