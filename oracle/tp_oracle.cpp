@@ -608,7 +608,7 @@ struct Planner {
       // the product's default arithmetic (warp form, oracle/wform_port.hpp): operates in place on ctrl
       wform::Problem wp;
       fillWformProblem(wp);
-      wform::Solver ws(wp, P.fast_order == 1 ? 1 : 4);
+      wform::Solver ws(wp, (P.fast_order >= 1 && P.fast_order <= 4 ? P.fast_order : 4));
       ws.trace = wtrace;
       st = ws.run(x.data());
     } else
@@ -685,7 +685,7 @@ struct Planner {
   double costFunctionWform(double* grad, int n) {
     wform::Problem wp;
     fillWformProblem(wp);
-    wform::Solver ws(wp, P.fast_order == 1 ? 1 : 4);
+    wform::Solver ws(wp, (P.fast_order >= 1 && P.fast_order <= 4 ? P.fast_order : 4));
     double f, dg, gg, xx;
     ws.f_const = ws.const_terms();
     ws.eval(false, f, dg, gg, xx);

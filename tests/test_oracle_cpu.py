@@ -226,3 +226,82 @@ def test_de_boor_matches_scipy_bspline(orc):
     wantd = BSpline(knots, c, 3).derivative(1)(t[:-1])
     gotd = orc.bspline_deriv_at(c, t[:-1], 1)
     assert np.max(np.abs(gotd - wantd)) <= 1e-10
+
+
+# ------------------------------------------------------------------------------------ the benchmarked arithmetic
+# oracle/wform_port.hpp restates the product's default kernel (lean team form).  The GPU tests pin the kernel to it bit
+# for bit; the tests below quantify, on the CPU, how that arithmetic relates to the REFERENCE-ORDER iterate.
+
+def test_fast_order_evaluation_and_direction_vs_reference_order(orc, sq_map, sq_omap, tp):
+    """(1) cost and gradient of the lean form vs the reference-order restatement: <= 1e-10 relative per evaluation
+    (north-star tolerance; measured ~1e-15).  (2) Every L-BFGS iteration of a lean-form solve: the Gram-form direction vs
+    the reference's two-loop recursion (lbfgs.hpp:1293-1316, serial order) on the SAME (g, S, Y): <= 1e-10 relative
+    (measured ~1e-14).  Both team sizes (1 and 4 warps)."""
+    pr = make_problems(tp, sq_map, sq_omap, 48, seed=5)
+    rng = np.random.default_rng(11)
+    for nw in (4, 1):
+        po = sq_omap.lib.default_params()
+        po.fast_order = nw
+        worst_f = worst_g = worst_d = 0.0
+        iters = 0
+        for b in range(48):
+            pl = orc.Planner(sq_omap, po)
+            c = traj(pr, b) + rng.normal(0, 0.1, traj(pr, b).shape)
+            pl.set_ctrl(traj(pr, b))
+            pl.init_guides()
+            guides = pl.get_guides()
+            pl2 = orc.Planner(sq_omap, po)
+            pl2.set_ctrl(c)
+            pl2.add_guides(*guides)
+            x = c[3:-3].ravel()
+            f0, g0, _ = pl2.cost(x)
+            f1, g1 = pl2.cost_wform(x)
+            worst_f = max(worst_f, abs(f0 - f1) / abs(f0))
+            worst_g = max(worst_g, float(np.max(np.abs(g0 - g1)) / np.max(np.abs(g0))))
+            w, st = pl.wform_direction_check()
+            worst_d = max(worst_d, w)
+            iters += st["iters"]
+        print(f"team of {nw} warp(s): evaluation rel diff cost {worst_f:.2e} grad {worst_g:.2e}; direction vs two-loop "
+              f"{worst_d:.2e} over {iters} iterations")
+        assert worst_f <= 1e-10 and worst_g <= 1e-10
+        assert worst_d <= 1e-10 and iters > 2000
+
+
+def test_fast_order_vs_reference_order_study(orc, sq_map, sq_omap, tp):
+    """4 096 seeded problems, whole makePlan on the CPU in both arithmetics (same deterministic atan2): the lean form is
+    the same algorithm with different roundings, and the solve amplifies roundings (jerk Hessian condition ~1e9, loose
+    g_epsilon) — any two reference builds differ the same way (libm vs soft atan2 flips 1/3 of the flows).  Asserted:
+    equal success rate within 1 %, equal final-cost distribution, every lean-form success collision free; recorded: the
+    fraction with identical control flow and, of those, within 1e-6 m."""
+    B = 4096
+    pr = make_problems(tp, sq_map, sq_omap, B, seed=20261018)
+    off, ctrl = pr["offsets"], pr["ctrl"]
+    po = sq_omap.lib.default_params()
+    po.soft_atan2 = 1
+    nthreads = os.cpu_count() or 4
+    _, out_r, st_r = orc.make_plan_batch(sq_omap, po, off, ctrl, nthreads=nthreads)
+    po.fast_order = 4
+    _, out_f, st_f = orc.make_plan_batch(sq_omap, po, off, ctrl, nthreads=nthreads)
+    keys = ["outer_rounds", "fail_count", "lbfgs_runs", "lbfgs_iters", "lbfgs_evals", "astar_searches", "astar_expansions"]
+    same = np.ones(B, bool)
+    for k in keys + ["success"]:
+        same &= st_r[k] == st_f[k]
+    d = np.array([np.abs(out_r[off[b]:off[b + 1]] - out_f[off[b]:off[b + 1]]).max() for b in range(B)])
+    sr, sf = st_r["success"].mean(), st_f["success"].mean()
+    both = (st_r["success"] == 1) & (st_f["success"] == 1)
+    fr, ff = st_r["final_cost"][both], st_f["final_cost"][both]
+    print(f"reference order: success {sr:.4f}, iterations/solve {st_r['lbfgs_iters'].mean():.1f}; lean form: success {sf:.4f}, "
+          f"iterations/solve {st_f['lbfgs_iters'].mean():.1f}; identical control flow {same.mean():.3f}, of those within 1e-6 m "
+          f"{(d[same] <= 1e-6).mean():.3f} (worst {d[same].max():.2e}); final cost median ref {np.median(fr):.4f} lean {np.median(ff):.4f}, "
+          f"median |rel diff| {np.median(np.abs(fr - ff) / fr):.2e}")
+    assert abs(sr - sf) <= 0.01
+    assert abs(st_r["lbfgs_iters"].mean() - st_f["lbfgs_iters"].mean()) <= 0.03 * st_r["lbfgs_iters"].mean()
+    assert abs(np.median(fr) - np.median(ff)) <= 1e-3 * np.median(fr)
+    assert np.median(np.abs(fr - ff) / fr) <= 1e-3
+    assert same.mean() >= 0.15
+    hit = 0
+    for b in np.flatnonzero(st_f["success"] == 1)[:512]:
+        pl = orc.Planner(sq_omap)
+        pl.set_ctrl(out_f[off[b]:off[b + 1]])
+        hit += pl.has_collision()
+    assert hit == 0

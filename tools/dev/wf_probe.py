@@ -6,6 +6,14 @@ import trajectory_planner_b200 as tp, bench
 from trajectory_planner_b200 import _capi
 pmap = tp.OccMap.from_tpm(bench.MAP_TPM); eng = tp.Engine(0); eng.set_map(pmap); p = tp.default_params()
 off_all, ctrl_all = bench.make_workload(tp, pmap, eng.query_points, 4096, bench.SEED, p)
+NMAX = int(os.environ.get("PROBE_NMAX", "0"))
+if NMAX:   # keep only trajectories with at most NMAX control points, repeated up to 4096
+    keep = [b for b in range(4096) if off_all[b + 1] - off_all[b] <= NMAX]
+    keep = (keep * (4096 // len(keep) + 1))[:4096]
+    chunks = [ctrl_all[off_all[b]:off_all[b + 1]] for b in keep]
+    off_all = np.concatenate([[0], np.cumsum([len(c) for c in chunks])]).astype(np.int32)
+    ctrl_all = np.concatenate(chunks, 0)
+    print("filtered to N <=", NMAX, "mean N", np.diff(off_all).mean())
 L = _capi.load()
 has = hasattr(L, "tp_debug_wf_phase_get")
 out = (C.c_ulonglong * 8)()

@@ -501,6 +501,9 @@ __global__ void __launch_bounds__(32) k_plan_init(BatchView bv, VigoConst C, Dev
 // shared-memory footprint (and with it the blocks resident per SM) follows the trajectories' length.
 // Parked trajectories of one batch (see k_solve): per size class a list of ids (filled with -1 before the launch),
 // its tail (slots handed out), its head (slots claimed) and the number of trajectories that finished phase A.
+#ifndef TP_TEAM_BLOCKS
+#define TP_TEAM_BLOCKS 3   // resident teams per SM the team-form kernel is compiled for (3: 168 registers, 4: 128)
+#endif
 #define TP_PARK_BUCKETS 6
 struct ParkQueue {
   int* list;       // [4 classes][TP_PARK_BUCKETS][stride]
@@ -707,7 +710,7 @@ __device__ __forceinline__ int solve_one(const BatchView& bv, const VigoConst& C
 // every worker stays busy until the whole batch is drained.  Each class's list is ordered hardest-first.
 // cls_begin[5]: ranges of `order` per class (largest trajectories = class 0); cls_next[4]: atomic cursors.
 template <int MODE>
-__global__ void __launch_bounds__(TP_LB_THREADS, MODE == 3 ? 4 : 3) k_solve(const __grid_constant__ BatchView bv, const __grid_constant__ VigoConst C, const __grid_constant__ DevMap map, const __grid_constant__ AStarPools P,
+__global__ void __launch_bounds__(TP_LB_THREADS, MODE == 3 ? 4 : (MODE == 4 ? TP_TEAM_BLOCKS : 3)) k_solve(const __grid_constant__ BatchView bv, const __grid_constant__ VigoConst C, const __grid_constant__ DevMap map, const __grid_constant__ AStarPools P,
                                                             const int* __restrict__ order, const int* __restrict__ cls_begin,
                                                             int* cls_next, int my_class, int class_max_n,
                                                             int* slot_flags, double* counters, long long* timeline,
@@ -1845,7 +1848,8 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
     const size_t smem_sm = 222 * 1024;
     // warp form: a worker is one warp (its own block of 32 threads); registers allow up to 12 per SM
     static const int wf_max = getenv("TP_W_MAX") ? atoi(getenv("TP_W_MAX")) : 12;
-    const int maxw = mode == 5 ? wf_max : 4;
+    static const int team_max = getenv("TP_TEAM_MAX") ? atoi(getenv("TP_TEAM_MAX")) : (mode == 4 ? TP_TEAM_BLOCKS : 4);
+    const int maxw = mode == 5 ? wf_max : (mode == 4 ? team_max : 4);
     int a[4];
     for (a[0] = 0; a[0] <= maxw; ++a[0])
       for (a[1] = 0; a[0] + a[1] <= maxw; ++a[1])
@@ -1876,6 +1880,26 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
             }
           }
     if (bestN == 0) { tp_set_error("no feasible worker mix"); return TP_ERR_CAPACITY; }
+    // Worker counts per class need not be whole numbers per SM: persistent workers pull from shared queues, so the grid
+    // of class c is sized to the chip (work share of the classes it serves first, shared memory of all 148 SMs) and the
+    // hardware block scheduler packs the three grids.  A mix like 92 + 67 + 46 KB leaves 17 KB of every SM idle; sized
+    // to the chip the same batch keeps ~3.5 instead of 3 teams per SM.
+    int grid_of[4] = {0, 0, 0, 0};
+    {
+      static const int frac_env = getenv("TP_MIX_FRAC") ? atoi(getenv("TP_MIX_FRAC")) : 0;   // measured: no gain while registers cap an SM at 3 teams
+      double wtot = 0, unit = 0;
+      for (int c = 0; c < 4; ++c) wtot += work[c];
+      for (int c = 0; c < 4; ++c)
+        if (work[c] > 0) unit += work[c] / wtot * (double)(((smem[c] + 1023) & ~(size_t)1023) + 1024);
+      const double chip = (double)smem_sm * e->sm_count * 0.96;
+      const int cap_blocks = e->sm_count * maxw;   // registers
+      const double total = std::min(chip / std::max(unit, 1.0), (double)cap_blocks);
+      for (int c = 0; c < 4; ++c) {
+        grid_of[c] = best[c] * e->sm_count;
+        if (frac_env && mode >= 4 && M > bestN * e->sm_count && wtot > 0)
+          grid_of[c] = work[c] > 0 ? std::max(1, (int)(work[c] / wtot * total + 0.5)) : 0;
+      }
+    }
     if (e->stage_busy) CK(cudaEventSynchronize(e->ev_stage));   // the previous copy out of the staging buffer
     if (ensure_stage(e, (size_t)M * 4 + 64) != TP_OK) return TP_ERR_CUDA;
     memcpy(e->h_stage, ids.data(), (size_t)M * 4);
@@ -1895,7 +1919,7 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
     {
       static const int park_env = getenv("TP_PARK_THRESH") ? atoi(getenv("TP_PARK_THRESH")) : 1500;
       int workers_total = 0;
-      for (int c = 0; c < 4; ++c) workers_total += best[c] * e->sm_count;
+      for (int c = 0; c < 4; ++c) workers_total += grid_of[c];
       if (park_env >= 0 && !resume && rounds == 0x7fffffff && M > workers_total) {
         const int nq = 4 * TP_PARK_BUCKETS;
         if (e->parkq.ensure(((size_t)nq * M + 2 * nq + 16) * 4) != TP_OK) return TP_ERR_CUDA;
@@ -1913,10 +1937,10 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
     CK(cudaEventRecord(e->ev_fork, s));
     int used = 0;
     for (int c = 0; c < 4; ++c) {
-      if (best[c] == 0) continue;
+      if (grid_of[c] == 0) continue;
       // no more workers than trajectories this class (and the ones it can steal) can feed
       const int feed = cb[4] - cb[c];
-      const int grid = std::min(best[c] * e->sm_count, std::max(feed, 1));
+      const int grid = std::min(grid_of[c], std::max(feed, 1));
       cudaStream_t cs = e->class_stream[used];
       CK(cudaStreamWaitEvent(cs, e->ev_fork, 0));
       {
@@ -1935,8 +1959,8 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
       ++used;
     }
     for (int i = 0; i < used; ++i) CK(cudaStreamWaitEvent(s, e->ev_join[i], 0));
-    if (getenv("TP_PROF_DUMP")) fprintf(stderr, "[tp-mix] workers/SM by class: %d %d %d %d (smem %zu %zu %zu %zu B), class sizes %d %d %d %d\n",
-                                        best[0], best[1], best[2], best[3], smem[0], smem[1], smem[2], smem[3], cb[1] - cb[0], cb[2] - cb[1],
+    if (getenv("TP_PROF_DUMP")) fprintf(stderr, "[tp-mix] grids by class: %d %d %d %d; whole workers/SM by class: %d %d %d %d (smem %zu %zu %zu %zu B), class sizes %d %d %d %d\n",
+                                        grid_of[0], grid_of[1], grid_of[2], grid_of[3], best[0], best[1], best[2], best[3], smem[0], smem[1], smem[2], smem[3], cb[1] - cb[0], cb[2] - cb[1],
                                         cb[3] - cb[2], cb[4] - cb[3]);
     return TP_OK;
   };

@@ -9,7 +9,9 @@
 #define TP_MAX_CTRL 512       // control points per trajectory the kernels accept
 #define TP_MAX_SEG_HARD 64    // hard cap on collision segments per trajectory
 #define TP_SC_CAP 64          // points per shortcut path kept for guide assignment
+#ifndef TP_LB_THREADS
 #define TP_LB_THREADS 128
+#endif
 #define TP_LB_WARPS (TP_LB_THREADS / 32)
 
 // trajectory status while the outer loop runs (final values are TP_STATUS_*)
