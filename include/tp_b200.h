@@ -208,12 +208,24 @@ int tp_vigo_cost_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, const
                        const double* ctrl, const int32_t* g_offsets, const int32_t* g_cp, const double* g_p,
                        const double* g_v, const double* w_override, double* f, double* grad, int mem, void* stream);
 
+/* Same with dynamic obstacles (bsplineTraj::updateDynamicObstacles, bsplineTraj.cpp:387-391; the term is
+ * getDynamicObstacleCost, :1001-1064): n_dyn obstacles, pos / vel / size 3 doubles each (host pointers). */
+int tp_vigo_cost_batch_dyn(tp_engine_t* e, const tp_vigo_params* p, int32_t B, const int32_t* offsets,
+                           const double* ctrl, const int32_t* g_offsets, const int32_t* g_cp, const double* g_p,
+                           const double* g_v, const double* w_override, int32_t n_dyn, const double* dyn_pos,
+                           const double* dyn_vel, const double* dyn_size, double* f, double* grad, int mem, void* stream);
+
 /* bsplineTraj::optimize (bsplineTraj.cpp:687-718): one fused cost+L-BFGS run per trajectory.
  * ctrl is updated in place (it keeps the last evaluated point, as the reference's callback
  * leaves it); x_final (may be NULL, 3 x sum(N-6)) receives the solver's own x.              */
 int tp_vigo_optimize_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, const int32_t* offsets, double* ctrl,
                            const int32_t* g_offsets, const int32_t* g_cp, const double* g_p, const double* g_v,
                            const double* w_override, tp_lbfgs_result* res, double* x_final, int mem, void* stream);
+
+int tp_vigo_optimize_batch_dyn(tp_engine_t* e, const tp_vigo_params* p, int32_t B, const int32_t* offsets, double* ctrl,
+                               const int32_t* g_offsets, const int32_t* g_cp, const double* g_p, const double* g_v,
+                               const double* w_override, int32_t n_dyn, const double* dyn_pos, const double* dyn_vel,
+                               const double* dyn_size, tp_lbfgs_result* res, double* x_final, int mem, void* stream);
 
 /* bsplineTraj::hasCollisionTrajectory (bsplineTraj.h:307-325): hit[B] */
 int tp_vigo_has_collision_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, const int32_t* offsets,
@@ -245,6 +257,17 @@ int tp_vigo_init_guides_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B
 int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, const int32_t* offsets,
                             const double* ctrl_in, double* ctrl_out, tp_vigo_result* results, int32_t n_dyn,
                             const double* dyn_pos, const double* dyn_vel, const double* dyn_size, int mem, void* stream);
+
+/* The same batch on SEVERAL engines of one host (one engine per GPU of the box; the map is replicated with
+ * tp_engine_set_map on each): independent trajectories, no exchange step.  One host thread per
+ * engine pulls contiguous chunks of `chunk` trajectories (<= 0: chosen by the library) from a shared cursor and runs
+ * them through tp_vigo_make_plan_batch; host buffers only.  Results are written at the trajectories' own positions
+ * and do not depend on the assignment; engine_of (may be NULL, [B]) reports which engine solved each trajectory.
+ * There is no counterpart in the reference (one bsplineTraj per process, bsplineTraj.cpp:333). */
+int tp_vigo_make_plan_batch_multi(tp_engine_t* const* engines, int32_t n_engines, const tp_vigo_params* p, int32_t B,
+                                  const int32_t* offsets, const double* ctrl_in, double* ctrl_out, tp_vigo_result* results,
+                                  int32_t n_dyn, const double* dyn_pos, const double* dyn_vel, const double* dyn_size,
+                                  int32_t chunk, int32_t* engine_of);
 
 /* ------------------------------------------------------------------------------------ front end (host side)
  * What src/bspline_node.cpp:332-371 does before makePlan, for B (start, goal) pairs: seed 1-segment
@@ -320,6 +343,11 @@ int tp_poly_box_collision(tp_engine_t* e, const tp_poly_params* p, int64_t n, co
 int tp_polytraj_make_plan_batch(tp_engine_t* e, const tp_poly_params* p, int32_t B, const int32_t* wp_offsets, const double* waypoints,
                                 int32_t* wp_offsets_out, double* waypoints_out, int64_t wp_cap, double* coef_out, double* times_out,
                                 uint8_t* valid_out, int32_t* iters_out);
+/* Same with per-path boundary conditions bc[B][12] = v0, v1, a0, a1 (polyTrajOctomap::updateInitVel / updateInitAcc,
+ * polyTrajOctomap.cpp:193-224; NULL = rest-to-rest).  The whole loop runs on the device, one thread block per path. */
+int tp_polytraj_make_plan_batch_bc(tp_engine_t* e, const tp_poly_params* p, int32_t B, const int32_t* wp_offsets, const double* waypoints,
+                                   const double* bc, int32_t* wp_offsets_out, double* waypoints_out, int64_t wp_cap, double* coef_out,
+                                   double* times_out, uint8_t* valid_out, int32_t* iters_out);
 
 #ifdef __cplusplus
 }

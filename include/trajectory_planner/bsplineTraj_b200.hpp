@@ -96,6 +96,9 @@ class bsplineTraj {
     if (rc != TP_OK) { std::printf("[BsplineTraj]: %s\n", tp_last_error()); return false; }
     if (res_.status == TP_STATUS_FAIL_ASTAR) std::printf("[BsplineTraj]: Fail because of A* failure.\n");
     if (res_.status != TP_STATUS_SUCCESS) return false;
+    // the committed trajectory (bspline_, bsplineTraj.cpp:376-377) and its re-parameterisation factor are replaced only
+    // by a SUCCESSFUL plan: after a failed replan the node keeps tracking the previous trajectory, as in the reference
+    traj_ = ctrl_;
     linearFactor_ = res_.linear_factor;
     return true;
   }
@@ -106,21 +109,23 @@ class bsplineTraj {
     return true;
   }
   // ---- queries (host side, bsplineTraj.cpp:1139-1145, 1402-1419, bsplineTraj.h:151-181)
-  Pose getPose(double t, bool yaw = true) const {
-    double p[3], v[3] = {1, 0, 0};
-    const int32_t N = (int32_t)(ctrl_.size() / 3);
-    tp_bspline_eval(N, ctrl_.data(), p_.ctrl_pt_ts, 0, 1, &t, p);
-    if (yaw) tp_bspline_eval(N, ctrl_.data(), p_.ctrl_pt_ts, 1, 1, &t, v);
+  Pose getPose(double t, bool yaw = true) const {   // evaluates the COMMITTED trajectory (bspline_)
+    double p[3] = {0, 0, 0}, v[3] = {1, 0, 0};
+    const int32_t N = (int32_t)(traj_.size() / 3);
+    if (N < 4) return {0, 0, 0, 0};
+    tp_bspline_eval(N, traj_.data(), p_.ctrl_pt_ts, 0, 1, &t, p);
+    if (yaw) tp_bspline_eval(N, traj_.data(), p_.ctrl_pt_ts, 1, 1, &t, v);
     return {p[0], p[1], p[2], yaw ? std::atan2(v[1], v[0]) : 0.0};
   }
-  double getDuration() const { return ((double)(ctrl_.size() / 3) - 3.0) * p_.ctrl_pt_ts; }
+  double getDuration() const { return traj_.size() < 12 ? 0.0 : ((double)(traj_.size() / 3) - 3.0) * p_.ctrl_pt_ts; }
+  const std::vector<double>& getTrajectoryControlPoints() const { return traj_; }   // bspline_'s control points
   double getTimestep() const { return p_.ts; }
   double getLinearFactor() const { return linearFactor_; }
   double getLinearReparamTime(double t) const { return linearFactor_ * t; }
   double getInitTs() const { return p_.ctrl_pt_dist / p_.max_vel; }
   double getControlPointTs() const { return p_.ctrl_pt_ts; }
   double getControlPointDist() const { return p_.ctrl_pt_dist; }
-  const std::vector<double>& getControlPoints() const { return ctrl_; }   // 3 x N column-major
+  const std::vector<double>& getControlPoints() const { return ctrl_; }   // optData_.controlPoints, 3 x N column-major
   const tp_vigo_result& lastResult() const { return res_; }
   bool isCurrTrajValid() {
     if (!init_ || !eng_ || !eng_->ok()) return false;
@@ -136,7 +141,8 @@ class bsplineTraj {
   const tp_map_t* map_ = nullptr;
   tp_vigo_params p_;
   tp_vigo_result res_{};
-  std::vector<double> ctrl_, dyn_;
+  std::vector<double> ctrl_, dyn_;   // working control points (optData_.controlPoints), dynamic obstacles
+  std::vector<double> traj_;         // control points of the committed trajectory (bspline_)
   int n_dyn_ = 0;
   bool init_ = false;
   double linearFactor_ = 1.0;

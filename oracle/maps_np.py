@@ -12,6 +12,8 @@ C++ loaders (trajectory_planner_b200/csrc/tp_map.cpp) and to build oracle maps.
   16 levels, key origin 32768 (octomap's OcTreeBaseImpl::readBinaryNode; call sites
   polyTrajOctomap.cpp:142-143, 573-599).
 """
+import struct
+
 import numpy as np
 
 
@@ -102,3 +104,27 @@ def bt_bbox(leaves, res, occupied_only=False):
     lo = (l[:, :3].min(0) - 32768) * res
     hi = ((l[:, :3] + l[:, 3:4]).max(0) - 32768) * res
     return lo, hi
+
+
+def read_tpm(path):
+    """This repo's compact raster format (trajectory_planner_b200/csrc/tp_map.cpp: "TPM1" | pad i32 | res f64 | origin
+    3 x f64 | dims 3 x i32 + pad | two RLE streams over the z-fastest bit-packed words: occupied, known).
+    -> dict(res, origin[3], dims[3], occupied[nx,ny,nz] uint8, known[nx,ny,nz] uint8).  Numpy only: lets the
+    reference arm of bench.py build its map without loading the product library."""
+    raw = open(path, "rb").read()
+    assert raw[:4] == b"TPM1", path
+    pos = 8
+    res = struct.unpack_from("<d", raw, pos)[0]; pos += 8
+    origin = np.frombuffer(raw, "<f8", 3, pos).copy(); pos += 24
+    dims = np.frombuffer(raw, "<i4", 4, pos)[:3].astype(int); pos += 16
+    wz = (dims[2] + 31) // 32
+    nw = int(dims[0]) * int(dims[1]) * int(wz)
+    grids = []
+    for _ in range(2):
+        npairs = struct.unpack_from("<Q", raw, pos)[0]; pos += 8
+        pairs = np.frombuffer(raw, "<u4", 2 * npairs, pos).reshape(-1, 2); pos += 8 * npairs
+        words = np.repeat(pairs[:, 1], pairs[:, 0])
+        assert len(words) == nw
+        bits = ((words[:, None] >> np.arange(32, dtype=np.uint32)[None, :]) & 1).astype(np.uint8)
+        grids.append(bits.reshape(dims[0], dims[1], wz * 32)[:, :, :dims[2]].copy())
+    return dict(res=float(res), origin=origin, dims=dims, occupied=grids[0], known=grids[1])

@@ -76,16 +76,22 @@ def test_cost_and_gradient_parity(tp, engine, orc, sq_omap, problems, strict):
         assert worst_f <= 1e-14 and worst_g <= 1e-14
 
 
-def test_cost_plan_in_z_and_dynamic_obstacles(tp, engine, orc, sq_omap, problems):
-    """Height barrier (x-row quirk), uncertain-aware factor and the dynamic-obstacle term."""
+@pytest.mark.parametrize("strict", [0, 1])
+def test_cost_plan_in_z_and_dynamic_obstacles(tp, engine, orc, sq_omap, problems, strict):
+    """Height barrier (x-row quirk), uncertain-aware factor and getDynamicObstacleCost (bsplineTraj.cpp:1001-1064) per
+    evaluation, in both reduction orders, with per-trajectory weightDistance_ / weightDynamicObstacle_ overrides:
+    <= 1e-10 relative vs the reference-order oracle (strict: <= 1e-14), and the default mode bit-identical to its own
+    restatement.  Then one optimize() with the obstacles: bit-identical in both modes."""
     B = 8
     off = problems["offsets"][:B + 1]
     p = tp.default_params()
     p.plan_in_z = 1
     p.uncertain_factor = 2.0
+    p.strict_order = strict
     po = sq_omap.lib.default_params()
     po.plan_in_z = 1
     po.uncertain_factor = 2.0
+    po.fast_order = 0 if strict else 4
     rng = np.random.default_rng(5)
     ctrl = problems["ctrl"][:off[B]].copy()
     ctrl += rng.normal(0, 0.2, ctrl.shape)
@@ -95,17 +101,49 @@ def test_cost_plan_in_z_and_dynamic_obstacles(tp, engine, orc, sq_omap, problems
         pl.set_ctrl(traj(problems, b))
         pl.init_guides()
         per.append(pl.get_guides())
-    dyn = (np.array([[0.0, 0.0, 1.0], [3.0, -2.0, 1.0]]), np.array([[0.5, 0.2, 0.0], [-0.3, 0.4, 0.0]]),
-           np.array([[0.6, 0.8, 1.7], [0.5, 0.5, 1.7]]))
-    f, g = engine.cost_batch(p, off, ctrl, flat_guides(per))
+    # obstacles next to the first trajectories' mid points (inside their distance threshold) and one far away
+    mids = np.array([traj(problems, b)[len(traj(problems, b)) // 2] for b in range(3)])
+    dyn = (np.vstack([mids + [0.3, -0.2, 0.0], [[30.0, 30.0, 1.0]]]),
+           np.array([[0.5, 0.2, 0.0], [-0.3, 0.4, 0.0], [0.0, 0.0, 0.0], [0.1, 0.1, 0.0]]),
+           np.array([[0.6, 0.8, 1.7], [0.5, 0.5, 1.7], [1.0, 0.4, 1.7], [0.5, 0.5, 1.7]]))
+    weights = np.column_stack([rng.choice([1.0, 4.0], B), rng.choice([1.0, 2.0, 8.0], B)])
+    f, g = engine.cost_batch(p, off, ctrl, flat_guides(per), weights, dyn=dyn)
+    dyn_active = 0
+    for b in range(B):
+        c = ctrl[off[b]:off[b + 1]]
+        pl = orc.Planner(sq_omap, po)
+        pl.set_ctrl(c)
+        pl.set_dyn(*dyn)
+        pl.add_guides(*per[b])
+        pl.set_weights(weights[b, 0], weights[b, 1])
+        fo, go, terms = pl.cost(c[3:-3].ravel())
+        dyn_active += terms[3] > 0
+        gs = g[3 * (off[b] - 6 * b): 3 * (off[b + 1] - 6 * (b + 1))]
+        tol = 1e-14 if strict else 1e-10
+        assert abs(f[b] - fo) <= tol * abs(fo), b
+        assert np.max(np.abs(gs - go)) <= tol * np.max(np.abs(go)), b
+        if not strict:
+            fw, gw = pl.cost_wform(c[3:-3].ravel())
+            assert f[b] == fw and np.array_equal(gs, gw), b
+    assert dyn_active >= 3   # the dynamic-obstacle term is really exercised
+    # one optimize() with the obstacles present
+    co, res, xf = engine.optimize_batch(p, off, ctrl, flat_guides(per), weights, dyn=dyn)
     for b in range(B):
         pl = orc.Planner(sq_omap, po)
         pl.set_ctrl(ctrl[off[b]:off[b + 1]])
+        pl.set_dyn(*dyn)
         pl.add_guides(*per[b])
-        fo, go, _ = pl.cost(ctrl[off[b]:off[b + 1]][3:-3].ravel())
-        gs = g[3 * (off[b] - 6 * b): 3 * (off[b + 1] - 6 * (b + 1))]
-        assert abs(f[b] - fo) <= 1e-10 * abs(fo)
-        assert np.max(np.abs(gs - go)) <= 1e-10 * np.max(np.abs(go))
+        pl.set_weights(weights[b, 0], weights[b, 1])
+        o = pl.optimize()
+        if strict:
+            # the reference-order oracle computes the obstacle radius with pow(x, 0.5); the device with sqrt: identical
+            # flow is the rule, not a guarantee
+            if (res["iters"][b], res["evals"][b], res["ret"][b]) != (o["iters"], o["evals"], o["ret"]):
+                continue
+            assert np.max(np.abs(pl.get_ctrl() - co[off[b]:off[b + 1]])) <= 1e-9, b
+        else:
+            assert (res["iters"][b], res["evals"][b], res["ret"][b], res["fx"][b]) == (o["iters"], o["evals"], o["ret"], o["fx"]), b
+            assert np.array_equal(pl.get_ctrl(), co[off[b]:off[b + 1]]), b
 
 
 @pytest.mark.parametrize("strict", [0, 1])
@@ -748,3 +786,37 @@ def test_make_plan_batch_edge_cases(tp, engine, orc, sq_map, sq_omap):
     with pytest.raises(TpError) as ei:
         engine.make_plan_batch(p, np.array([0, 400], np.int32), big)
     assert "shared memory" in str(ei.value)
+
+
+@pytest.mark.gpu
+def test_multi_engine_entry_matches_single_engine(tp, engine, sq_map, sq_omap):
+    """tp_vigo_make_plan_batch_multi (one host thread per engine, chunks from a shared cursor): two engines
+    — here both on GPU 0, on a multi-GPU box one per device — must return, for every trajectory, exactly what a single
+    engine returns for the whole batch, in both reduction orders, whichever engine solved it."""
+    from helpers import make_problems
+    pr = make_problems(tp, sq_map, sq_omap, 700, seed=321)
+    e2 = tp.Engine(0)
+    e2.set_map(sq_map)
+    ndev = tp._capi.load().tp_device_count()
+    e3 = None
+    if ndev > 1:   # a second GPU when the box has one
+        e3 = tp.Engine(1)
+        e3.set_map(sq_map)
+    engines = [engine, e3 if e3 is not None else e2]
+    for strict in (0, 1):
+        p = tp.default_params()
+        p.strict_order = strict
+        ref_out, ref_res = engine.make_plan_batch(p, pr["offsets"], pr["ctrl"])
+        out, res, who = tp.make_plan_batch_multi(engines, p, pr["offsets"], pr["ctrl"], chunk=128)
+        assert np.array_equal(out, ref_out)
+        for f in ("status", "lbfgs_iters", "lbfgs_evals", "astar_expansions", "outer_rounds", "final_cost", "linear_factor"):
+            assert np.array_equal(res[f], ref_res[f]), (strict, f)
+        assert set(np.unique(who)) == {0, 1}, "both engines must have taken chunks"
+        out2, res2, _ = tp.make_plan_batch_multi(engines, p, pr["offsets"], pr["ctrl"])   # library-chosen chunk size
+        assert np.array_equal(out2, ref_out)
+    # an empty batch and a bad argument
+    o, r, _ = tp.make_plan_batch_multi(engines, tp.default_params(), np.zeros(1, np.int32), np.zeros((0, 3)))
+    assert o.shape == (0, 3) and len(r) == 0
+    e2.close()
+    if e3 is not None:
+        e3.close()

@@ -75,12 +75,12 @@ SYMBOLS = [
     "tp_map_add_cells", "tp_map_load_pcd", "tp_map_load_bt", "tp_map_save_tpm", "tp_map_load_tpm", "tp_map_info_get",
     "tp_map_get_grid", "tp_bt_bbox", "tp_engine_default_cfg", "tp_engine_create", "tp_engine_destroy",
     "tp_engine_set_map", "tp_engine_synchronize", "tp_engine_launch_count", "tp_engine_stream",
-    "tp_vigo_default_params", "tp_query_points", "tp_query_unknown", "tp_query_lines", "tp_vigo_cost_batch",
+    "tp_vigo_default_params", "tp_query_points", "tp_query_unknown", "tp_query_lines", "tp_vigo_cost_batch", "tp_vigo_cost_batch_dyn", "tp_vigo_optimize_batch_dyn",
     "tp_vigo_optimize_batch", "tp_vigo_has_collision_batch", "tp_vigo_find_collision_seg_batch", "tp_astar_batch",
-    "tp_vigo_init_guides_batch", "tp_vigo_make_plan_batch", "tp_vigo_frontend_batch", "tp_vigo_frontend_batch_device", "tp_vigo_input_path_check", "tp_vigo_update_path", "tp_bspline_fit",
+    "tp_vigo_init_guides_batch", "tp_vigo_make_plan_batch", "tp_vigo_make_plan_batch_multi", "tp_vigo_frontend_batch", "tp_vigo_frontend_batch_device", "tp_vigo_input_path_check", "tp_vigo_update_path", "tp_bspline_fit",
     "tp_bspline_eval", "tp_engine_profile_enable", "tp_engine_profile_get", "tp_microbench_fp64",
     "tp_microbench_gather", "tp_poly_default_params", "tp_minsnap_solve_batch", "tp_poly_check_batch",
-    "tp_poly_box_collision", "tp_polytraj_make_plan_batch",
+    "tp_poly_box_collision", "tp_polytraj_make_plan_batch", "tp_polytraj_make_plan_batch_bc",
 ]
 
 
@@ -137,6 +137,9 @@ def load():
     PP = C.POINTER(VigoParams)
     L.tp_vigo_cost_batch.argtypes = [vp, PP, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp]
     L.tp_vigo_optimize_batch.argtypes = [vp, PP, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp]
+    L.tp_vigo_make_plan_batch_multi.argtypes = [vp, C.c_int32, PP, C.c_int32, vp, vp, vp, vp, C.c_int32, vp, vp, vp, C.c_int32, vp]
+    L.tp_vigo_cost_batch_dyn.argtypes = [vp, PP, C.c_int32, vp, vp, vp, vp, vp, vp, vp, C.c_int32, vp, vp, vp, vp, vp, C.c_int, vp]
+    L.tp_vigo_optimize_batch_dyn.argtypes = [vp, PP, C.c_int32, vp, vp, vp, vp, vp, vp, vp, C.c_int32, vp, vp, vp, vp, vp, C.c_int, vp]
     L.tp_vigo_has_collision_batch.argtypes = [vp, PP, C.c_int32, vp, vp, vp, C.c_int, vp]
     L.tp_vigo_find_collision_seg_batch.argtypes = [vp, PP, C.c_int32, vp, vp, vp, vp, C.c_int, vp]
     L.tp_astar_batch.argtypes = [vp, PP, C.c_int32, vp, vp, vp, vp, vp, C.c_int, vp]
@@ -156,6 +159,7 @@ def load():
     L.tp_poly_check_batch.argtypes = [vp, QP, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int32]
     L.tp_poly_box_collision.argtypes = [vp, QP, C.c_int64, vp, vp]
     L.tp_polytraj_make_plan_batch.argtypes = [vp, QP, C.c_int32, vp, vp, vp, vp, C.c_int64, vp, vp, vp, vp]
+    L.tp_polytraj_make_plan_batch_bc.argtypes = [vp, QP, C.c_int32, vp, vp, vp, vp, vp, C.c_int64, vp, vp, vp, vp]
     L.tp_engine_profile_enable.argtypes = [vp, C.c_int]
     L.tp_engine_profile_get.argtypes = [vp, C.POINTER(Profile)]
     L.tp_microbench_fp64.argtypes = [vp, _dp]

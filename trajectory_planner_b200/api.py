@@ -254,20 +254,29 @@ class Engine:
         g_off, g_cp, g_p, g_v = guides
         return _i32(g_off), _i32(g_cp), _f64(g_p).reshape(-1, 3), _f64(g_v).reshape(-1, 3)
 
-    def cost_batch(self, params, offsets, ctrl, guides=None, weights=None):
+    @staticmethod
+    def _dyn(dyn):
+        if dyn is None:
+            return 0, None, None, None
+        pos, vel, size = (_f64(a).reshape(-1, 3) for a in dyn)
+        return len(pos), pos, vel, size
+
+    def cost_batch(self, params, offsets, ctrl, guides=None, weights=None, dyn=None):
+        """costFunction per trajectory; dyn = (pos, vel, size) of the dynamic obstacles (updateDynamicObstacles)."""
         offsets, ctrl = _i32(offsets), _f64(ctrl).reshape(-1, 3)
         B = len(offsets) - 1
         g_off, g_cp, g_p, g_v = self._guides(guides, B)
         w = None if weights is None else _f64(weights).reshape(B, 2)
+        nd, dp, dv, ds = self._dyn(dyn)
         f = np.zeros(B)
         nvar = max(3 * (len(ctrl) - 6 * B), 1)
         grad = np.zeros(nvar)
-        check(self.L.tp_vigo_cost_batch(self.h, C.byref(params), B, ptr(offsets), ptr(ctrl), ptr(g_off), ptr(g_cp),
-                                        ptr(g_p), ptr(g_v), ptr(w), ptr(f), ptr(grad), TP_MEM_HOST, None),
-              "tp_vigo_cost_batch")
+        check(self.L.tp_vigo_cost_batch_dyn(self.h, C.byref(params), B, ptr(offsets), ptr(ctrl), ptr(g_off), ptr(g_cp),
+                                            ptr(g_p), ptr(g_v), ptr(w), nd, ptr(dp), ptr(dv), ptr(ds), ptr(f), ptr(grad),
+                                            TP_MEM_HOST, None), "tp_vigo_cost_batch_dyn")
         return f, grad
 
-    def optimize_batch(self, params, offsets, ctrl, guides=None, weights=None, want_x=True):
+    def optimize_batch(self, params, offsets, ctrl, guides=None, weights=None, want_x=True, dyn=None):
         offsets, ctrl = _i32(offsets), _f64(ctrl).reshape(-1, 3).copy()
         B = len(offsets) - 1
         g_off, g_cp, g_p, g_v = self._guides(guides, B)
@@ -275,9 +284,10 @@ class Engine:
         res = np.zeros(B, LBFGS_DTYPE)
         nvar = max(3 * (len(ctrl) - 6 * B), 1)
         xf = np.zeros(nvar) if want_x else None
-        check(self.L.tp_vigo_optimize_batch(self.h, C.byref(params), B, ptr(offsets), ptr(ctrl), ptr(g_off), ptr(g_cp),
-                                            ptr(g_p), ptr(g_v), ptr(w), ptr(res), ptr(xf), TP_MEM_HOST, None),
-              "tp_vigo_optimize_batch")
+        nd, dp, dv, ds = self._dyn(dyn)
+        check(self.L.tp_vigo_optimize_batch_dyn(self.h, C.byref(params), B, ptr(offsets), ptr(ctrl), ptr(g_off), ptr(g_cp),
+                                                ptr(g_p), ptr(g_v), ptr(w), nd, ptr(dp), ptr(dv), ptr(ds), ptr(res), ptr(xf),
+                                                TP_MEM_HOST, None), "tp_vigo_optimize_batch_dyn")
         return ctrl, res, xf
 
     def has_collision_batch(self, params, offsets, ctrl):
@@ -368,6 +378,25 @@ class Engine:
               "tp_vigo_make_plan_batch")
 
 
+def make_plan_batch_multi(engines, params, offsets, ctrl, dyn=None, chunk=0):
+    """One batch on several engines of this host (one per GPU, the map set on each): tp_vigo_make_plan_batch_multi.
+    -> (ctrl_out, results, engine_of)."""
+    L = _capi.load()
+    offsets, ctrl = _i32(offsets), _f64(ctrl).reshape(-1, 3)
+    B = len(offsets) - 1
+    out = np.empty_like(ctrl)
+    res = np.zeros(B, RESULT_DTYPE)
+    who = np.full(B, -1, np.int32)
+    n_dyn, dp, dv, ds = 0, None, None, None
+    if dyn is not None:
+        dp, dv, ds = (_f64(a).reshape(-1, 3) for a in dyn)
+        n_dyn = len(dp)
+    arr = (C.c_void_p * len(engines))(*[e.h for e in engines])
+    check(L.tp_vigo_make_plan_batch_multi(arr, len(engines), C.byref(params), B, ptr(offsets), ptr(ctrl), ptr(out), ptr(res),
+                                          n_dyn, ptr(dp), ptr(dv), ptr(ds), int(chunk), ptr(who)), "tp_vigo_make_plan_batch_multi")
+    return out, res, who
+
+
 def default_poly_params():
     p = _capi.PolyParams()
     _capi.load().tp_poly_default_params(C.byref(p))
@@ -433,11 +462,12 @@ class PolyTraj:
         check(self.engine.L.tp_poly_box_collision(self.engine.h, C.byref(self.params), len(xyz), ptr(xyz), ptr(out)), "tp_poly_box_collision")
         return out
 
-    def make_plan_batch(self, paths):
-        """polyTrajOctomap::makePlanAddingWaypoint for a list of waypoint arrays ->
+    def make_plan_batch(self, paths, bc=None):
+        """polyTrajOctomap::makePlanAddingWaypoint for a list of waypoint arrays (bc: optional [B, 12] v0, v1, a0, a1) ->
         list of dict(valid, iters, path, coef, times)."""
         off, wp = self._flat(paths)
         B = len(paths)
+        bcv = None if bc is None else _f64(bc).reshape(B, 12)
         cap = B * 64
         off_o = np.zeros(B + 1, np.int32)
         wp_o = np.zeros((cap, 3))
@@ -445,8 +475,9 @@ class PolyTraj:
         times = np.zeros(cap)
         valid = np.zeros(B, np.uint8)
         iters = np.zeros(B, np.int32)
-        check(self.engine.L.tp_polytraj_make_plan_batch(self.engine.h, C.byref(self.params), B, ptr(off), ptr(wp), ptr(off_o), ptr(wp_o),
-                                                        cap, ptr(coef), ptr(times), ptr(valid), ptr(iters)), "tp_polytraj_make_plan_batch")
+        check(self.engine.L.tp_polytraj_make_plan_batch_bc(self.engine.h, C.byref(self.params), B, ptr(off), ptr(wp), ptr(bcv), ptr(off_o),
+                                                           ptr(wp_o), cap, ptr(coef), ptr(times), ptr(valid), ptr(iters)),
+              "tp_polytraj_make_plan_batch_bc")
         sols = _poly_split(off_o, coef, times)
         return [dict(valid=bool(valid[b]), iters=int(iters[b]), path=wp_o[off_o[b]:off_o[b + 1]].copy(), coef=sols[b][0], times=sols[b][1])
                 for b in range(B)]

@@ -15,6 +15,7 @@ struct DevMap {
   const uint32_t* __restrict__ inflated;
   const uint32_t* __restrict__ known;
   double res;
+  double inv_res;   // 1 / res: candidate quotient, confirmed or replaced by the true division (dm_cell)
   double mn[3];
   int dim[3];
   int wz;
@@ -40,11 +41,19 @@ __device__ __forceinline__ D3 cross3(const D3& a, const D3& b) {
   return d3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
 
+// floor(d / res) with the TRUE division's result (bit-exact voxel index) at the price of a multiplication: d * (1/res)
+// is within 2 ulp of d / res, so the two floors can differ only when the quotient is within ~1e-12 of an integer;
+// anything closer than 1e-6 to an integer (and every non-finite / huge value) takes the division.
+__device__ __forceinline__ double dm_cell(double d, double res, double inv_res) {
+  const double t = d * inv_res;
+  if (!(fabs(t - rint(t)) >= 1e-6)) return floor(d / res);
+  return floor(t);
+}
 // posToIndex = floor((p - origin)/res) (true division); false when outside the grid
 __device__ __forceinline__ bool dm_index(const DevMap& m, double x, double y, double z, int& ix, int& iy, int& iz) {
-  const double fx = floor((x - m.mn[0]) / m.res);
-  const double fy = floor((y - m.mn[1]) / m.res);
-  const double fz = floor((z - m.mn[2]) / m.res);
+  const double fx = dm_cell(x - m.mn[0], m.res, m.inv_res);
+  const double fy = dm_cell(y - m.mn[1], m.res, m.inv_res);
+  const double fz = dm_cell(z - m.mn[2], m.res, m.inv_res);
   // the comparisons are false for NaN -> outside
   const bool in = (fx >= 0.0) && (fx < (double)m.dim[0]) && (fy >= 0.0) && (fy < (double)m.dim[1]) && (fz >= 0.0) &&
                   (fz < (double)m.dim[2]);

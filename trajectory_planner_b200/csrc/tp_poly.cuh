@@ -75,43 +75,36 @@ struct PolySolveArgs {
   int* queue;
 };
 
-__global__ void __launch_bounds__(PL_THREADS) k_minsnap_solve(PolySolveArgs A) {
-  __shared__ int s_b, s_piv, s_bad;
+// One min-snap solve by the whole block: waypoints wp[nwp] (+ boundary conditions bc[12] = v0, v1, a0, a1 or null) ->
+// knots times[nwp], coefficients coef[3][8 K] (axis-major).  M (n x n) and R (n x 3) are the block's scratch, n = 14 K.
+// Returns (to every thread) 0 ok, -1 singular KKT, -2 too many segments, -3 fewer than two waypoints.
+__device__ int poly_solve_one(const double* wp, int nwp, const double* bc, double desired_vel, int cont, double* coef,
+                              double* times, double* M, double* R) {
+  __shared__ int s_piv, s_bad;
   __shared__ double s_red[PL_THREADS / 32];
   __shared__ int s_redi[PL_THREADS / 32];
   __shared__ double s_dt[PL_MAX_SEG + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double* M = A.scratch + (size_t)blockIdx.x * ((size_t)A.nmax * A.nmax + 3 * (size_t)A.nmax);
-  double* R = M + (size_t)A.nmax * A.nmax;   // rhs, [n][3]
-  for (;;) {
-    if (tid == 0) s_b = atomicAdd(A.queue, 1);
-    __syncthreads();
-    const int b = s_b;
-    if (b >= A.B) break;
-    const int w0 = A.wp_off[b], nwp = A.wp_off[b + 1] - w0, K = nwp - 1;
-    const size_t coff = (size_t)3 * PL_NC * (w0 - b);
-    if (K < 1 || K > PL_MAX_SEG) {
-      if (tid == 0) A.status[b] = K < 1 ? -3 : -2;
-      __syncthreads();
-      continue;
-    }
+  {
+    const int K = nwp - 1;
+    if (K < 1 || K > PL_MAX_SEG) return K < 1 ? -3 : -2;
     const int nvar = PL_NC * K;
-    const int ncon = (2 + 2 * (K - 1)) + 2 * (2 + (K - 1)) + (K - 1) * (A.cont - 2);
+    const int ncon = (2 + 2 * (K - 1)) + 2 * (2 + (K - 1)) + (K - 1) * (cont - 2);
     const int n = nvar + ncon;
-    const double* wp = A.wp + 3 * (size_t)w0;
     // ---- time allocation (avgTimeAllocation): knots accumulate distance / desiredVel
     if (tid == 0) {
       double tt = 0.0;
-      A.times[w0] = 0.0;
+      times[0] = 0.0;
       for (int i = 1; i < nwp; ++i) {
         const double dx = wp[3 * i] - wp[3 * i - 3], dy = wp[3 * i + 1] - wp[3 * i - 2], dz = wp[3 * i + 2] - wp[3 * i - 1];
-        const double dur = sqrt(dx * dx + dy * dy + dz * dz) / A.desired_vel;
+        const double dur = sqrt(dx * dx + dy * dy + dz * dz) / desired_vel;
         s_dt[i - 1] = dur;
         tt += dur;
-        A.times[w0 + i] = tt;
+        times[i] = tt;
       }
       s_bad = 0;
     }
+    __syncthreads();
     for (size_t e = tid; e < (size_t)n * n; e += PL_THREADS) M[e] = 0.0;
     for (int e = tid; e < 3 * n; e += PL_THREADS) R[e] = 0.0;
     __syncthreads();
@@ -125,7 +118,7 @@ __global__ void __launch_bounds__(PL_THREADS) k_minsnap_solve(PolySolveArgs A) {
     }
     // ---- A (and A^T) + b: rows in the reference's order (constructA / constructBound)
     if (tid == 0) {
-      const double* bc = A.bc ? A.bc + 12 * (size_t)b : nullptr;
+      
       int r = nvar;
       auto put = [&](int row, int seg, double t1, int order, double scale, double sign) {
         // derivative row of segment `seg` at normalised time 0 (t1 = 0) or 1: c_d * t^(d-order)
@@ -159,7 +152,7 @@ __global__ void __launch_bounds__(PL_THREADS) k_minsnap_solve(PolySolveArgs A) {
           ++r;
         }
       }
-      for (int order = 3; order <= A.cont; ++order)
+      for (int order = 3; order <= cont; ++order)
         for (int i = 0; i < K - 1; ++i) {
           double sl = 1.0, sr = 1.0;
           for (int k = 0; k < order; ++k) { sl *= s_dt[i + 1]; sr *= s_dt[i]; }
@@ -216,9 +209,8 @@ __global__ void __launch_bounds__(PL_THREADS) k_minsnap_solve(PolySolveArgs A) {
       __syncthreads();
     }
     if (s_bad) {
-      if (tid == 0) A.status[b] = -1;
       __syncthreads();
-      continue;
+      return -1;
     }
     // ---- back substitution, one warp per axis
     if (warp < 3) {
@@ -234,10 +226,28 @@ __global__ void __launch_bounds__(PL_THREADS) k_minsnap_solve(PolySolveArgs A) {
     // ---- de-normalise: c_d /= dt^d (solveX..Z, :874-878)
     for (int e = tid; e < 3 * nvar; e += PL_THREADS) {
       const int a = e / nvar, q = e - a * nvar, s = q / PL_NC, d = q - s * PL_NC;
-      A.coef[coff + (size_t)a * nvar + q] = R[3 * q + a] / pow(s_dt[s], (double)d);
+      coef[(size_t)a * nvar + q] = R[3 * q + a] / pow(s_dt[s], (double)d);
     }
-    if (tid == 0) A.status[b] = 0;
     __syncthreads();
+  }
+  return 0;
+}
+
+__global__ void __launch_bounds__(PL_THREADS) k_minsnap_solve(PolySolveArgs A) {
+  __shared__ int s_b;
+  const int tid = threadIdx.x;
+  double* M = A.scratch + (size_t)blockIdx.x * ((size_t)A.nmax * A.nmax + 3 * (size_t)A.nmax);
+  double* R = M + (size_t)A.nmax * A.nmax;   // rhs, [n][3]
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_b = atomicAdd(A.queue, 1);
+    __syncthreads();
+    const int b = s_b;
+    if (b >= A.B) break;
+    const int w0 = A.wp_off[b], nwp = A.wp_off[b + 1] - w0;
+    const int st = poly_solve_one(A.wp + 3 * (size_t)w0, nwp, A.bc ? A.bc + 12 * (size_t)b : nullptr, A.desired_vel, A.cont,
+                                  A.coef + (size_t)3 * PL_NC * (w0 - b), A.times + w0, M, R);
+    if (tid == 0) A.status[b] = st;
   }
 }
 
@@ -277,6 +287,45 @@ __device__ __forceinline__ void poly_eval(const double* coef, const double* knot
   }
 }
 
+// getTrajectory + checkCollisionTraj for one path by the whole block: samples t_acc[s] < T plus the appended last
+// waypoint; marks seg_hit[K]; returns (to every thread) whether any sample collides; *n_traj = trajectory entries.
+__device__ int poly_check_one(const PolyMap& map, const double* wp, int K, const double* coef, const double* knots,
+                              const double* t_acc, int n_t_acc, const double box[3], double map_res, uint8_t* seg_hit,
+                              int* n_traj, double* samples, uint8_t* sample_hit, int samp_cap) {
+  const int tid = threadIdx.x;
+  const double T = knots[K];
+  for (int i = tid; i < K; i += PL_THREADS) seg_hit[i] = 0;
+  __syncthreads();
+  // number of polynomial samples: t_acc[s] < T
+  int lo = 0, hi = n_t_acc;   // first s with t_acc[s] >= T
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (t_acc[mid] < T) lo = mid + 1; else hi = mid;
+  }
+  const int npoly = lo, ntraj = npoly + 1;
+  int any = 0;
+  for (int s = tid; s < ntraj; s += PL_THREADS) {
+    double p[3];
+    if (s < npoly) poly_eval(coef, knots, K, t_acc[s], p);
+    else { p[0] = wp[3 * (size_t)K]; p[1] = wp[3 * (size_t)K + 1]; p[2] = wp[3 * (size_t)K + 2]; }
+    const bool hit = pm_collision_box(map, p[0], p[1], p[2], box, map_res);
+    if (samples && s < samp_cap) {
+      double* o = samples + (size_t)s * 3;
+      o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+      sample_hit[s] = hit ? 1 : 0;
+    }
+    if (hit) {
+      any = 1;
+      const double t = s < n_t_acc ? t_acc[s] : 1e300;   // checkCollisionTraj's own accumulated t (:639,654)
+      for (int i = 0; i < K; ++i)
+        if (t >= knots[i] && t <= knots[i + 1]) { seg_hit[i] = 1; break; }
+    }
+  }
+  any = __syncthreads_or(any);
+  *n_traj = ntraj;
+  return any;
+}
+
 __global__ void __launch_bounds__(PL_THREADS) k_poly_check(PolyCheckArgs A, PolyMap map) {
   const int b = blockIdx.x, tid = threadIdx.x;
   const int w0 = A.wp_off[b], nwp = A.wp_off[b + 1] - w0, K = nwp - 1;
@@ -284,39 +333,124 @@ __global__ void __launch_bounds__(PL_THREADS) k_poly_check(PolyCheckArgs A, Poly
     if (tid == 0) { A.valid[b] = 1; A.n_samples[b] = 0; }
     return;
   }
-  const double* knots = A.times + w0;
-  const double* coef = A.coef + (size_t)3 * PL_NC * (w0 - b);
-  uint8_t* seg_hit = A.seg_hit + (w0 - b);
-  const double T = knots[K];
-  for (int i = tid; i < K; i += PL_THREADS) seg_hit[i] = 0;
-  __syncthreads();
-  // number of polynomial samples: t_acc[s] < T
-  int lo = 0, hi = A.n_t_acc;   // first s with t_acc[s] >= T
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (A.t_acc[mid] < T) lo = mid + 1; else hi = mid;
-  }
-  const int npoly = lo, ntraj = npoly + 1;
-  int any = 0;
-  for (int s = tid; s < ntraj; s += PL_THREADS) {
-    double p[3];
-    if (s < npoly) poly_eval(coef, knots, K, A.t_acc[s], p);
-    else { p[0] = A.wp[3 * (size_t)(w0 + K)]; p[1] = A.wp[3 * (size_t)(w0 + K) + 1]; p[2] = A.wp[3 * (size_t)(w0 + K) + 2]; }
-    const bool hit = pm_collision_box(map, p[0], p[1], p[2], A.box, A.map_res);
-    if (A.samples && s < A.samp_cap) {
-      double* o = A.samples + ((size_t)b * A.samp_cap + s) * 3;
-      o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
-      A.sample_hit[(size_t)b * A.samp_cap + s] = hit ? 1 : 0;
-    }
-    if (hit) {
-      any = 1;
-      const double t = s < A.n_t_acc ? A.t_acc[s] : 1e300;   // checkCollisionTraj's own accumulated t (:639,654)
-      for (int i = 0; i < K; ++i)
-        if (t >= knots[i] && t <= knots[i + 1]) { seg_hit[i] = 1; break; }
-    }
-  }
-  any = __syncthreads_or(any);
+  int ntraj = 0;
+  const int any = poly_check_one(map, A.wp + 3 * (size_t)w0, K, A.coef + (size_t)3 * PL_NC * (w0 - b), A.times + w0, A.t_acc, A.n_t_acc,
+                                 A.box, A.map_res, A.seg_hit + (w0 - b), &ntraj, A.samples ? A.samples + (size_t)b * A.samp_cap * 3 : nullptr,
+                                 A.sample_hit ? A.sample_hit + (size_t)b * A.samp_cap : nullptr, A.samp_cap);
   if (tid == 0) { A.valid[b] = any ? 0 : 1; A.n_samples[b] = ntraj; }
+}
+
+// ------------------------------------------------------------------------------------------- the whole loop on the device
+// polyTrajOctomap::makePlanAddingWaypoint (polyTrajOctomap.cpp:259-321) for one path per thread block, start to finish:
+// solve -> sample + box check -> insert a midpoint waypoint into every colliding segment (highest index first, :179-185)
+// -> re-solve, until the trajectory is collision free, maxIter is exceeded or the waypoint cap is reached.  No host round
+// trip per iteration (round 1: one solve launch + one check launch + two copies + a host-side insertion per iteration).
+// Outputs go to fixed-stride staging rows (cap waypoints per path); a scan + gather pass packs them.
+struct PolyLoopArgs {
+  int B;
+  const int* wp_off;       // [B+1]
+  const double* wp;        // [3 * total]
+  const double* bc;        // [B * 12] or null
+  double desired_vel;
+  int cont, max_iter, cap; // cap = waypoints per path the staging rows hold (<= PL_MAX_SEG + 1)
+  const double* t_acc;
+  int n_t_acc;
+  double box[3];
+  double map_res;
+  double* wp_st;           // [B][cap][3]
+  double* coef_st;         // [B][3 * 8 * (cap - 1)]
+  double* times_st;        // [B][cap]
+  int* n_wp;               // [B]
+  uint8_t* valid;          // [B]
+  int* iters;              // [B]
+  double* scratch;         // [grid * (nmax*nmax + 3*nmax)]
+  int nmax;
+  int* queue;
+};
+
+__global__ void __launch_bounds__(PL_THREADS) k_polytraj_loop(PolyLoopArgs A, PolyMap map) {
+  __shared__ int s_b, s_n, s_go, s_it;
+  __shared__ uint8_t s_seg[PL_MAX_SEG + 1];
+  const int tid = threadIdx.x;
+  double* M = A.scratch + (size_t)blockIdx.x * ((size_t)A.nmax * A.nmax + 3 * (size_t)A.nmax);
+  double* R = M + (size_t)A.nmax * A.nmax;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_b = atomicAdd(A.queue, 1);
+    __syncthreads();
+    const int b = s_b;
+    if (b >= A.B) break;
+    const int w0 = A.wp_off[b], nwp0 = A.wp_off[b + 1] - w0;
+    double* wp = A.wp_st + (size_t)b * A.cap * 3;
+    double* coef = A.coef_st + (size_t)b * 3 * PL_NC * (A.cap - 1);
+    double* times = A.times_st + (size_t)b * A.cap;
+    for (int e = tid; e < 3 * nwp0; e += PL_THREADS) wp[e] = A.wp[3 * (size_t)w0 + e];
+    if (tid == 0) { s_n = nwp0; A.valid[b] = 0; A.iters[b] = 0; }
+    __syncthreads();
+    if (nwp0 < 2) {   // single-point path (:262-266)
+      if (tid == 0) { A.valid[b] = 1; A.n_wp[b] = nwp0; }
+      continue;
+    }
+    int it = 0;
+    for (;;) {
+      const int nwp = s_n, K = nwp - 1;
+      const int st = poly_solve_one(wp, nwp, A.bc ? A.bc + 12 * (size_t)b : nullptr, A.desired_vel, A.cont, coef, times, M, R);
+      ++it;
+      int any = 1, ntraj = 0;
+      if (st == 0) any = poly_check_one(map, wp, K, coef, times, A.t_acc, A.n_t_acc, A.box, A.map_res, s_seg, &ntraj, nullptr, nullptr, 0);
+      else {
+        for (int i = tid; i < K; i += PL_THREADS) s_seg[i] = 0;   // an unsolved path has no trajectory to check
+        __syncthreads();
+      }
+      if (tid == 0) {
+        int go = 0;
+        s_it = it;
+        if (st == 0 && !any) A.valid[b] = 1;
+        else if (it <= A.max_iter) {   // ++countIter; if (countIter > maxIter_) break;  (:302-305)
+          int add = 0;
+          for (int i = 0; i < K; ++i) add += s_seg[i];
+          if (add == 0) {
+            // a colliding sample outside every knot interval (or an unsolvable path): nothing to insert, so every further
+            // iteration would re-solve the same path until maxIter — jump there
+            s_it = A.max_iter + 1;
+          } else if (nwp + add <= A.cap) {
+            // insertWaypoint: midpoints of the colliding segments, highest index first
+            int n = nwp;
+            for (int i = K - 1; i >= 0; --i)
+              if (s_seg[i]) {
+                for (int q = n - 1; q > i; --q)
+                  for (int a = 0; a < 3; ++a) wp[3 * (q + 1) + a] = wp[3 * q + a];
+                for (int a = 0; a < 3; ++a) wp[3 * (i + 1) + a] = (wp[3 * i + a] + wp[3 * (i + 2) + a]) / 2;
+                ++n;
+              }
+            s_n = n;
+            go = 1;
+          }
+        }
+        s_go = go;
+      }
+      __syncthreads();
+      if (!s_go) break;
+    }
+    if (tid == 0) { A.n_wp[b] = s_n; A.iters[b] = s_it; }
+  }
+}
+
+// pack the staging rows: waypoints / knots by waypoint offset, coefficients by segment offset
+__global__ void k_polytraj_pack(PolyLoopArgs A, const int* __restrict__ off_out, double* wp_out, double* coef_out, double* times_out,
+                                long wp_cap) {
+  const int b = blockIdx.x;
+  if (b >= A.B) return;
+  const int o = off_out[b], n = off_out[b + 1] - o;
+  if ((long)o + n > wp_cap) return;
+  const double* wp = A.wp_st + (size_t)b * A.cap * 3;
+  const double* coef = A.coef_st + (size_t)b * 3 * PL_NC * (A.cap - 1);
+  const double* times = A.times_st + (size_t)b * A.cap;
+  for (int e = threadIdx.x; e < 3 * n; e += blockDim.x) wp_out[3 * (size_t)o + e] = wp[e];
+  if (n >= 2) {
+    for (int e = threadIdx.x; e < n; e += blockDim.x) times_out[o + e] = times[e];
+    for (int e = threadIdx.x; e < 3 * PL_NC * (n - 1); e += blockDim.x) coef_out[(size_t)3 * PL_NC * (o - b) + e] = coef[e];
+  }
 }
 
 // box collision check on caller-supplied positions (parity entry: decisions are bit-exact functions of the position)

@@ -2,10 +2,13 @@
 // sm_100a only; compiled with --fmad=false (see tp_device.cuh).  No CPU fallback: every compute
 // entry point needs a CUDA device.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "tp_lbfgs.cuh"
@@ -28,10 +31,30 @@
 // ---- map queries (occMap::isInflatedOccupied / isUnknown / isInflatedOccupiedLine)
 // One thread per query; xyz is read as three coalesced FP64 streams per warp (24 B/query) and the
 // map word through the read-only path (one 32 B sector per random gather).
-__global__ void k_query_points(DevMap map, long n, const double* __restrict__ xyz, uint8_t* __restrict__ out, int unknown) {
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+// Four consecutive queries per thread and iteration: 96 B of coordinates as six 16-byte streaming loads (all issued
+// before the first use), four independent map gathers, four flags as one 4-byte store (the arrays are 16- / 4-byte
+// aligned at query indices that are multiples of four).
+__device__ __forceinline__ unsigned dq_flag(const DevMap& map, const D3& p, int unknown) {
+  return unknown ? (dm_unknown(map, p) ? 1u : 0u) : (dm_inflated(map, p) ? 1u : 0u);
+}
+__global__ void __launch_bounds__(256) k_query_points(DevMap map, long n, const double* __restrict__ xyz, uint8_t* __restrict__ out, int unknown) {
+  const long stride = (long)gridDim.x * blockDim.x;
+  const long nquad = n >> 2;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(xyz) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 3) == 0);
+  if (aligned) {
+    const double2* __restrict__ v = reinterpret_cast<const double2*>(xyz);
+    for (long j = blockIdx.x * (long)blockDim.x + threadIdx.x; j < nquad; j += stride) {
+      const double2 a = __ldcs(v + 6 * j), b = __ldcs(v + 6 * j + 1), c = __ldcs(v + 6 * j + 2), d = __ldcs(v + 6 * j + 3),
+                    e = __ldcs(v + 6 * j + 4), f = __ldcs(v + 6 * j + 5);
+      const unsigned h0 = dq_flag(map, d3(a.x, a.y, b.x), unknown), h1 = dq_flag(map, d3(b.y, c.x, c.y), unknown),
+                     h2 = dq_flag(map, d3(d.x, d.y, e.x), unknown), h3 = dq_flag(map, d3(e.y, f.x, f.y), unknown);
+      __stcs(reinterpret_cast<unsigned*>(out) + j, h0 | (h1 << 8) | (h2 << 16) | (h3 << 24));
+    }
+  }
+  // the last n % 4 queries, or everything when the buffers are not aligned
+  for (long i = (aligned ? 4 * nquad : 0) + blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += stride) {
     const D3 p = d3(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
-    out[i] = unknown ? (dm_unknown(map, p) ? 1 : 0) : (dm_inflated(map, p) ? 1 : 0);
+    out[i] = (uint8_t)dq_flag(map, p, unknown);
   }
 }
 __global__ void k_query_lines(DevMap map, long n, const double* __restrict__ a, const double* __restrict__ b,
@@ -1438,6 +1461,7 @@ int tp_engine_set_map(tp_engine_t* e, const tp_map_t* m) {
   e->dmap.inflated = e->map_infl.as<uint32_t>();
   e->dmap.known = e->map_known.as<uint32_t>();
   e->dmap.res = m->res;
+  e->dmap.inv_res = 1.0 / m->res;
   for (int a = 0; a < 3; ++a) { e->dmap.mn[a] = m->origin[a]; e->dmap.dim[a] = m->dims[a]; }
   e->dmap.wz = m->wz();
   e->map_res = m->res;
@@ -1478,7 +1502,9 @@ static int query_common(tp_engine_t* e, int64_t n, const double* a, const double
     dout = e->scratch_c.as<uint8_t>();
   }
   const int threads = 256;
-  const long blocks = std::min<long>((n + threads - 1) / threads, (long)e->sm_count * 8);
+  // point queries: four per thread and iteration, a grid of whole waves (8 blocks of 256 threads fit an SM)
+  const long work = kind == 2 ? n : (n + 3) / 4;
+  const long blocks = std::min<long>((work + threads - 1) / threads, (long)e->sm_count * 8);
   {
     ProfScope ps(e, 5, s);
     if (kind == 2) k_query_lines<<<(int)blocks, threads, 0, s>>>(e->dmap, (long)n, da, db, dout);
@@ -1513,15 +1539,42 @@ static int make_identity_active(tp_engine* e, int B, cudaStream_t s) {
   return TP_OK;
 }
 
+// dynamic obstacles (always host pointers: a handful of values) -> the batch view
+static int upload_dyn(tp_engine* e, BatchSetup& bs, int n_dyn, const double* dyn_pos, const double* dyn_vel, const double* dyn_size,
+                      cudaStream_t s) {
+  if (n_dyn < 0 || (n_dyn > 0 && (!dyn_pos || !dyn_vel || !dyn_size))) { tp_set_error("dynamic obstacles: bad arguments"); return TP_ERR_INVALID_ARG; }
+  if (n_dyn == 0) return TP_OK;
+  if (e->dyn.ensure((size_t)n_dyn * 72) != TP_OK) return TP_ERR_CUDA;
+  double* d = e->dyn.as<double>();
+  CK(cudaMemcpyAsync(d, dyn_pos, (size_t)n_dyn * 24, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d + 3 * (size_t)n_dyn, dyn_vel, (size_t)n_dyn * 24, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d + 6 * (size_t)n_dyn, dyn_size, (size_t)n_dyn * 24, cudaMemcpyHostToDevice, s));
+  bs.bv.n_dyn = n_dyn;
+  bs.bv.dyn_pos = d;
+  bs.bv.dyn_vel = d + 3 * (size_t)n_dyn;
+  bs.bv.dyn_size = d + 6 * (size_t)n_dyn;
+  return TP_OK;
+}
+
 int tp_vigo_cost_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, const int32_t* offsets, const double* ctrl,
                        const int32_t* g_offsets, const int32_t* g_cp, const double* g_p, const double* g_v,
                        const double* w_override, double* f, double* grad, int mem, void* stream) {
+  return tp_vigo_cost_batch_dyn(e, p, B, offsets, ctrl, g_offsets, g_cp, g_p, g_v, w_override, 0, nullptr, nullptr, nullptr, f, grad,
+                                mem, stream);
+}
+
+int tp_vigo_cost_batch_dyn(tp_engine_t* e, const tp_vigo_params* p, int32_t B, const int32_t* offsets, const double* ctrl,
+                           const int32_t* g_offsets, const int32_t* g_cp, const double* g_p, const double* g_v,
+                           const double* w_override, int32_t n_dyn, const double* dyn_pos, const double* dyn_vel,
+                           const double* dyn_size, double* f, double* grad, int mem, void* stream) {
   if (mem != TP_MEM_HOST) { tp_set_error("tp_vigo_cost_batch: host memory only"); return TP_ERR_INVALID_ARG; }
   if (!e || !f || !grad) return TP_ERR_INVALID_ARG;
   CK(cudaSetDevice(e->device));
   cudaStream_t s = pick_stream(e, stream);
   BatchSetup bs;
   int rc = setup_batch(e, p, B, offsets, ctrl, mem, s, bs, true);
+  if (rc != TP_OK) return rc;
+  rc = upload_dyn(e, bs, n_dyn, dyn_pos, dyn_vel, dyn_size, s);
   if (rc != TP_OK) return rc;
   rc = upload_guides(e, bs, g_offsets, g_cp, g_p, g_v, w_override, s);
   if (rc != TP_OK) return rc;
@@ -1549,12 +1602,22 @@ int tp_vigo_cost_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, const
 int tp_vigo_optimize_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, const int32_t* offsets, double* ctrl,
                            const int32_t* g_offsets, const int32_t* g_cp, const double* g_p, const double* g_v,
                            const double* w_override, tp_lbfgs_result* res, double* x_final, int mem, void* stream) {
+  return tp_vigo_optimize_batch_dyn(e, p, B, offsets, ctrl, g_offsets, g_cp, g_p, g_v, w_override, 0, nullptr, nullptr, nullptr, res,
+                                    x_final, mem, stream);
+}
+
+int tp_vigo_optimize_batch_dyn(tp_engine_t* e, const tp_vigo_params* p, int32_t B, const int32_t* offsets, double* ctrl,
+                               const int32_t* g_offsets, const int32_t* g_cp, const double* g_p, const double* g_v,
+                               const double* w_override, int32_t n_dyn, const double* dyn_pos, const double* dyn_vel,
+                               const double* dyn_size, tp_lbfgs_result* res, double* x_final, int mem, void* stream) {
   if (mem != TP_MEM_HOST) { tp_set_error("tp_vigo_optimize_batch: host memory only"); return TP_ERR_INVALID_ARG; }
   if (!e) return TP_ERR_INVALID_ARG;
   CK(cudaSetDevice(e->device));
   cudaStream_t s = pick_stream(e, stream);
   BatchSetup bs;
   int rc = setup_batch(e, p, B, offsets, ctrl, mem, s, bs, true);
+  if (rc != TP_OK) return rc;
+  rc = upload_dyn(e, bs, n_dyn, dyn_pos, dyn_vel, dyn_size, s);
   if (rc != TP_OK) return rc;
   rc = upload_guides(e, bs, g_offsets, g_cp, g_p, g_v, w_override, s);
   if (rc != TP_OK) return rc;
@@ -1739,18 +1802,8 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
   }
   int rc = setup_batch(e, p, B, offsets, mem == TP_MEM_DEVICE ? ctrl_out : ctrl_in, mem, s, bs, true);
   if (rc != TP_OK) return rc;
-  // dynamic obstacles (always host pointers: a handful of values)
-  if (n_dyn > 0) {
-    if (e->dyn.ensure((size_t)n_dyn * 72) != TP_OK) return TP_ERR_CUDA;
-    double* d = e->dyn.as<double>();
-    CK(cudaMemcpyAsync(d, dyn_pos, (size_t)n_dyn * 24, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(d + 3 * (size_t)n_dyn, dyn_vel, (size_t)n_dyn * 24, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(d + 6 * (size_t)n_dyn, dyn_size, (size_t)n_dyn * 24, cudaMemcpyHostToDevice, s));
-    bs.bv.n_dyn = n_dyn;
-    bs.bv.dyn_pos = d;
-    bs.bv.dyn_vel = d + 3 * (size_t)n_dyn;
-    bs.bv.dyn_size = d + 6 * (size_t)n_dyn;
-  }
+  rc = upload_dyn(e, bs, n_dyn, dyn_pos, dyn_vel, dyn_size, s);
+  if (rc != TP_OK) return rc;
   rc = ensure_pools(e, bs.C);
   if (rc != TP_OK) return rc;
   int mode = lbfgs_mode(p);
@@ -2003,6 +2056,60 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
     CK(cudaMemcpyAsync(ctrl_out, bs.bv.ctrl, (size_t)bs.total * 24, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(results, dres, (size_t)B * sizeof(tp_vigo_result), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+  }
+  return TP_OK;
+}
+
+// ---- one host, several GPUs: independent trajectories, no exchange step.  One host thread per engine
+// pulls contiguous chunks of the batch from a shared cursor (dynamic load balance: the engines of a box rarely finish
+// equal shares at the same time — per-shard tails differ) and runs them through tp_vigo_make_plan_batch with host
+// buffers; every engine holds its own replica of the map.  Results land at the trajectories' own positions, so the
+// output is independent of which engine solved what (each trajectory's result does not depend on its batch).
+int tp_vigo_make_plan_batch_multi(tp_engine_t* const* engines, int32_t n_engines, const tp_vigo_params* p, int32_t B,
+                                  const int32_t* offsets, const double* ctrl_in, double* ctrl_out, tp_vigo_result* results,
+                                  int32_t n_dyn, const double* dyn_pos, const double* dyn_vel, const double* dyn_size,
+                                  int32_t chunk, int32_t* engine_of) {
+  if (!engines || n_engines < 1 || !p) { tp_set_error("tp_vigo_make_plan_batch_multi: no engines / params"); return TP_ERR_INVALID_ARG; }
+  for (int i = 0; i < n_engines; ++i)
+    if (!engines[i]) { tp_set_error("tp_vigo_make_plan_batch_multi: engine %d is null", i); return TP_ERR_INVALID_ARG; }
+  if (B == 0) return check_params(engines[0], p);
+  if (B < 0 || !offsets || !ctrl_in || !ctrl_out || !results) return TP_ERR_INVALID_ARG;
+  if (offsets[0] != 0) { tp_set_error("offsets[0] must be 0"); return TP_ERR_INVALID_ARG; }
+  if (chunk <= 0) {
+    // about four chunks per engine (balance) but not below 1,024 trajectories (a chunk's makespan ends in its tail)
+    chunk = std::max(1024, (B + 4 * n_engines - 1) / (4 * n_engines));
+  }
+  const int n_chunks = (B + chunk - 1) / chunk;
+  std::atomic<int> cursor(0), first_err(TP_OK);
+  std::vector<std::string> err_msg((size_t)n_engines);
+  auto worker = [&](int ei) {
+    std::vector<int32_t> loc;
+    for (;;) {
+      const int c = cursor.fetch_add(1);
+      if (c >= n_chunks || first_err.load() != TP_OK) break;
+      const int b0 = c * chunk, b1 = std::min(B, b0 + chunk);
+      loc.resize((size_t)(b1 - b0) + 1);
+      for (int b = b0; b <= b1; ++b) loc[(size_t)(b - b0)] = offsets[b] - offsets[b0];
+      const int rc = tp_vigo_make_plan_batch(engines[ei], p, b1 - b0, loc.data(), ctrl_in + 3 * (size_t)offsets[b0],
+                                             ctrl_out + 3 * (size_t)offsets[b0], results + b0, n_dyn, dyn_pos, dyn_vel, dyn_size,
+                                             TP_MEM_HOST, nullptr);
+      if (rc != TP_OK) {
+        int expect = TP_OK;
+        if (first_err.compare_exchange_strong(expect, rc)) err_msg[(size_t)ei] = tp_last_error();
+        break;
+      }
+      if (engine_of)
+        for (int b = b0; b < b1; ++b) engine_of[b] = ei;
+    }
+  };
+  std::vector<std::thread> th;
+  for (int i = 1; i < n_engines; ++i) th.emplace_back(worker, i);
+  worker(0);
+  for (auto& t : th) t.join();
+  if (first_err.load() != TP_OK) {
+    for (const auto& m : err_msg)
+      if (!m.empty()) tp_set_error("%s", m.c_str());
+    return first_err.load();
   }
   return TP_OK;
 }
@@ -2381,73 +2488,71 @@ int tp_poly_box_collision(tp_engine_t* e, const tp_poly_params* p, int64_t n, co
 int tp_polytraj_make_plan_batch(tp_engine_t* e, const tp_poly_params* p, int32_t B, const int32_t* wp_offsets, const double* waypoints,
                                 int32_t* wp_offsets_out, double* waypoints_out, int64_t wp_cap, double* coef_out, double* times_out,
                                 uint8_t* valid_out, int32_t* iters_out) {
+  return tp_polytraj_make_plan_batch_bc(e, p, B, wp_offsets, waypoints, nullptr, wp_offsets_out, waypoints_out, wp_cap, coef_out,
+                                        times_out, valid_out, iters_out);
+}
+
+int tp_polytraj_make_plan_batch_bc(tp_engine_t* e, const tp_poly_params* p, int32_t B, const int32_t* wp_offsets, const double* waypoints,
+                                   const double* bc, int32_t* wp_offsets_out, double* waypoints_out, int64_t wp_cap, double* coef_out,
+                                   double* times_out, uint8_t* valid_out, int32_t* iters_out) {
   int rc = poly_check_params(e, p, true);
   if (rc != TP_OK) return rc;
   if (B <= 0 || !wp_offsets || !waypoints || !wp_offsets_out || !waypoints_out || !coef_out || !times_out || !valid_out || !iters_out)
     return TP_ERR_INVALID_ARG;
-  const int cap_wp = std::min(p->max_waypoints > 1 ? p->max_waypoints : 64, PL_MAX_SEG + 1);
-  std::vector<std::vector<double>> path((size_t)B), coef((size_t)B), tms((size_t)B);
-  std::vector<int> active;
-  for (int b = 0; b < B; ++b) {
-    path[b].assign(waypoints + 3 * (size_t)wp_offsets[b], waypoints + 3 * (size_t)wp_offsets[b + 1]);
-    valid_out[b] = 0;
-    iters_out[b] = 0;
-    if (wp_offsets[b + 1] - wp_offsets[b] < 2) { valid_out[b] = 1; continue; }   // single-point path (:262-266)
-    if (wp_offsets[b + 1] - wp_offsets[b] > cap_wp) { tp_set_error("path %d has more than %d waypoints", b, cap_wp); return TP_ERR_CAPACITY; }
-    active.push_back(b);
+  const int cap = std::min(p->max_waypoints > 1 ? p->max_waypoints : 64, PL_MAX_SEG + 1);
+  for (int b = 0; b < B; ++b)
+    if (wp_offsets[b + 1] - wp_offsets[b] > cap) { tp_set_error("path %d has more than %d waypoints", b, cap); return TP_ERR_CAPACITY; }
+  CK(cudaSetDevice(e->device));
+  cudaStream_t s = e->stream;
+  rc = poly_ensure_tacc(e, p->delT, s);
+  if (rc != TP_OK) return rc;
+  const int total = wp_offsets[B];
+  const int nmax = 14 * (cap - 1);
+  const int grid = std::min(B, e->sm_count * 8);
+  const size_t st_wp = (size_t)B * cap * 3, st_coef = (size_t)B * 24 * (cap - 1), st_t = (size_t)B * cap;
+  // staging rows | packed outputs (sized for wp_cap)
+  const size_t packed = (size_t)wp_cap * 3 + (size_t)wp_cap * 24 + (size_t)wp_cap;
+  if (e->off.ensure((size_t)(B + 1) * 4) != TP_OK || e->ctrl.ensure((size_t)std::max(total, 1) * 24) != TP_OK ||
+      e->poly_scratch.ensure((size_t)grid * ((size_t)nmax * nmax + 3 * (size_t)nmax) * 8) != TP_OK ||
+      e->scratch_a.ensure((st_wp + st_coef + st_t) * 8) != TP_OK || e->scratch_b.ensure(packed * 8) != TP_OK ||
+      e->scratch_c.ensure((size_t)B * 16 + 64) != TP_OK || e->counters.ensure(64 * 4) != TP_OK || (bc && e->dyn.ensure((size_t)B * 96) != TP_OK))
+    return TP_ERR_CUDA;
+  CK(cudaMemcpyAsync(e->off.p, wp_offsets, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(e->ctrl.p, waypoints, (size_t)total * 24, cudaMemcpyHostToDevice, s));
+  if (bc) CK(cudaMemcpyAsync(e->dyn.p, bc, (size_t)B * 96, cudaMemcpyHostToDevice, s));
+  CK(cudaMemsetAsync(e->counters.p, 0, 64 * 4, s));
+  PolyLoopArgs A;
+  A.B = B; A.wp_off = e->off.as<int>(); A.wp = e->ctrl.as<double>(); A.bc = bc ? e->dyn.as<double>() : nullptr;
+  A.desired_vel = p->desired_vel; A.cont = p->cont; A.max_iter = p->max_iter; A.cap = cap;
+  A.t_acc = e->poly_tacc.as<double>(); A.n_t_acc = e->poly_tacc_n;
+  for (int a = 0; a < 3; ++a) A.box[a] = p->box[a];
+  A.map_res = p->map_res;
+  A.wp_st = e->scratch_a.as<double>(); A.coef_st = A.wp_st + st_wp; A.times_st = A.coef_st + st_coef;
+  A.n_wp = e->scratch_c.as<int>(); A.iters = A.n_wp + B;
+  int* d_off_out = A.iters + B;            // [B + 1]
+  A.valid = reinterpret_cast<uint8_t*>(d_off_out + B + 1);
+  A.scratch = e->poly_scratch.as<double>(); A.nmax = nmax; A.queue = e->counters.as<int>();
+  {
+    ProfScope ps(e, 6, s, B);
+    k_polytraj_loop<<<grid, PL_THREADS, 0, s>>>(A, make_polymap(e));
   }
-  std::vector<int> off;
-  std::vector<double> wp, c, t;
-  std::vector<int> st;
-  std::vector<uint8_t> val, seg;
-  std::vector<int> ns;
-  while (!active.empty()) {
-    const int nb = (int)active.size();
-    off.assign(1, 0);
-    wp.clear();
-    for (int b : active) {
-      wp.insert(wp.end(), path[b].begin(), path[b].end());
-      off.push_back((int)(wp.size() / 3));
-    }
-    const int total = off[nb], nseg = total - nb;
-    c.resize((size_t)24 * nseg); t.resize((size_t)total); st.resize(nb); val.resize(nb); seg.resize(nseg); ns.resize(nb);
-    rc = tp_minsnap_solve_batch(e, p, nb, off.data(), wp.data(), nullptr, c.data(), t.data(), st.data());
-    if (rc != TP_OK) return rc;
-    rc = tp_poly_check_batch(e, p, nb, off.data(), wp.data(), c.data(), t.data(), val.data(), seg.data(), ns.data(), nullptr, nullptr, 0);
-    if (rc != TP_OK) return rc;
-    std::vector<int> next;
-    for (int q = 0; q < nb; ++q) {
-      const int b = active[q];
-      const int K = off[q + 1] - off[q] - 1;
-      coef[b].assign(c.begin() + (size_t)24 * (off[q] - q), c.begin() + (size_t)24 * (off[q] - q) + (size_t)24 * K);
-      tms[b].assign(t.begin() + off[q], t.begin() + off[q + 1]);
-      iters_out[b] += 1;
-      if (st[q] == 0 && val[q]) { valid_out[b] = 1; continue; }
-      if (iters_out[b] > p->max_iter) continue;   // ++countIter; if (countIter > maxIter_) break;  (:302-305)
-      int add = 0;
-      for (int i = 0; i < K; ++i) add += seg[off[q] - q + i];
-      if ((int)path[b].size() / 3 + add > cap_wp) continue;
-      for (int i = K - 1; i >= 0; --i)
-        if (seg[off[q] - q + i]) {
-          double mid[3];
-          for (int a = 0; a < 3; ++a) mid[a] = (path[b][3 * i + a] + path[b][3 * (i + 1) + a]) / 2;
-          path[b].insert(path[b].begin() + 3 * (i + 1), mid, mid + 3);
-        }
-      next.push_back(b);
-    }
-    active.swap(next);
-  }
-  int64_t tot = 0;
-  wp_offsets_out[0] = 0;
-  for (int b = 0; b < B; ++b) {
-    const int64_t n = (int64_t)path[b].size() / 3;
-    if (tot + n > wp_cap) { tp_set_error("tp_polytraj_make_plan_batch: wp_cap too small"); return TP_ERR_CAPACITY; }
-    memcpy(waypoints_out + 3 * tot, path[b].data(), path[b].size() * 8);
-    if (!tms[b].empty()) memcpy(times_out + tot, tms[b].data(), tms[b].size() * 8);
-    if (!coef[b].empty()) memcpy(coef_out + 24 * (tot - b), coef[b].data(), coef[b].size() * 8);
-    tot += n;
-    wp_offsets_out[b + 1] = (int32_t)tot;
-  }
+  k_fe_scan<<<1, 1024, 0, s>>>(A.n_wp, B, d_off_out);
+  double* d_wp_out = e->scratch_b.as<double>();
+  double* d_coef_out = d_wp_out + (size_t)wp_cap * 3;
+  double* d_times_out = d_coef_out + (size_t)wp_cap * 24;
+  k_polytraj_pack<<<B, 64, 0, s>>>(A, d_off_out, d_wp_out, d_coef_out, d_times_out, (long)wp_cap);
+  e->launches += 3;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(wp_offsets_out, d_off_out, (size_t)(B + 1) * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(valid_out, A.valid, (size_t)B, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(iters_out, A.iters, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  const int64_t tot = wp_offsets_out[B];
+  if (tot > wp_cap) { tp_set_error("tp_polytraj_make_plan_batch: wp_cap too small (%lld waypoints)", (long long)tot); return TP_ERR_CAPACITY; }
+  CK(cudaMemcpyAsync(waypoints_out, d_wp_out, (size_t)tot * 24, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(times_out, d_times_out, (size_t)tot * 8, cudaMemcpyDeviceToHost, s));
+  if (tot > B) CK(cudaMemcpyAsync(coef_out, d_coef_out, (size_t)(tot - B) * 24 * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
   return TP_OK;
 }
 
