@@ -18,7 +18,7 @@ int main(int argc, char** argv) {
   planner.updateMaxAcc(3.0);
   // seed path: here simply the straight segment sampled every 0.2 m (the node uses a 1-segment min-snap polynomial)
   trajPlanner::Path path;
-  for (int i = 0; i <= 80; ++i) path.push_back({-8.0 + 0.2 * i, -8.0 + 0.2 * i, 1.0});
+  for (int i = 0; i <= 80; ++i) path.push_back({-6.0 + 0.15 * i, -6.0 + 0.15 * i, 1.0});
   trajPlanner::Path adjusted;
   double finalTime = 0;
   planner.inputPathCheck(path, adjusted, planner.getInitTs(), finalTime);

@@ -300,8 +300,18 @@ int tp_vigo_update_path(const tp_map_t* m, const tp_vigo_params* p, int32_t K, c
                         double* ctrl_out, int32_t cap);
 /* bspline::parameterizeToBspline (bspline.cpp:74-138): K points (+ v0,v1,a0,a1) -> K+2 control points */
 int tp_bspline_fit(double ts, int32_t K, const double* points, const double* start_end4, double* ctrl_out);
-/* bspline::at / getDerivative().at (bspline.cpp:32-72), host side (pose-at-time queries stay on the host) */
+/* bspline::at / getDerivative().at (bspline.cpp:32-72), host side: one trajectory, nt times */
 int tp_bspline_eval(int32_t N, const double* ctrl, double ts, int32_t deriv, int32_t nt, const double* t, double* out);
+/* The same for a whole batch on the device: bsplineTraj::getPose (bsplineTraj.cpp:1402-1419) /
+ * evalTraj (:1438-1447) / evalTrajToMsg (:1502-1518) for B trajectories in one launch.  Trajectory b (control points
+ * offsets[b] .. offsets[b+1]-1 of ctrl) is sampled at the times t[t_offsets[b] .. t_offsets[b+1]-1]; outputs are
+ * indexed by sample: pos[3 T] (bspline_.at(t)), and when non-NULL vel[3 T], acc[3 T] (the derivative splines' at(t)) and
+ * yaw[T] = atan2(v_y, v_x) (tp_atan2 of tp_device.cuh: IEEE +,-,*,/ only, within 2 ulp of libm's).  pos / vel / acc are
+ * bit-identical to tp_bspline_eval.  mem = TP_MEM_DEVICE: all pointers are device pointers, the launch is asynchronous
+ * on `stream`. */
+int tp_vigo_sample_batch(tp_engine_t* e, double ctrl_pt_ts, int32_t B, const int32_t* offsets, const double* ctrl,
+                         const int32_t* t_offsets, const double* t, double* pos, double* vel, double* acc, double* yaw,
+                         int mem, void* stream);
 
 /* ------------------------------------------------------------------------------------ min-snap / polyTraj (secondary path)
  * polyTrajSolver's QP (polyTrajSolver.cpp:241-904; degree 7, differential degree 4) solved exactly through its KKT
@@ -348,6 +358,44 @@ int tp_polytraj_make_plan_batch(tp_engine_t* e, const tp_poly_params* p, int32_t
 int tp_polytraj_make_plan_batch_bc(tp_engine_t* e, const tp_poly_params* p, int32_t B, const int32_t* wp_offsets, const double* waypoints,
                                    const double* bc, int32_t* wp_offsets_out, double* waypoints_out, int64_t wp_cap, double* coef_out,
                                    double* times_out, uint8_t* valid_out, int32_t* iters_out);
+
+
+/* ---- corridor constraints (polyTrajOctomap `mode: false`, the reference's default config cfg/planner_interactive.yaml:31)
+ * polyTrajSolver::solve with setCorridorConstraint(corridorSizeVec, corridorRes) (polyTrajSolver.cpp:960-1012, rows of
+ * constructA :555-579 / constructBound :813-840): per axis  min 1/2 c'Pc  s.t. the min-snap equality rows and
+ * mid_j - r_s <= p_s(t_j) <= mid_j + r_s at the corridor samples t = 0; t <= 1; t += 1/ceil(duration_s corridorRes) of every
+ * segment s (mid_j on the straight segment).  Solved to convergence by an interior-point method (the reference's OSQP
+ * stops at eps 1e-3).  corridor_size[sum K]: radius of segment s of path b at wp_offsets[b] - b + s (0 is not supported:
+ * the reference skips such segments).  status[3 B] per axis: 0 converged, 1 infeasible or not converged, -1 singular,
+ * -2 / -3 too many / too few waypoints, -4 more than 4096 corridor rows.  coef / times in the layouts above. */
+int tp_corridor_solve_batch(tp_engine_t* e, const tp_poly_params* p, int32_t B, const int32_t* wp_offsets, const double* waypoints,
+                            const double* bc, const double* corridor_size, double corridor_res, double* coef, double* times,
+                            int32_t* status);
+/* polyTrajOctomap::makePlanCorridorConstraint (polyTrajOctomap.cpp:388-530) for B paths, the whole loop on the device (one
+ * thread block per path): corridors of radius init_r (initial_radius), solve, sample + box collision check, radius of the
+ * colliding segments *= fs (shrinking_factor), until collision free or maxIter.  An infeasible / unconverged QP ends a
+ * path's loop with valid = 0 (the reference keeps its previous solution there, polyTrajSolver.cpp:871, which can never
+ * become valid).  The waypoints do not change; r_out (may be NULL, [sum K]) = final radii, status_out (may be NULL, [3 B]). */
+int tp_polytraj_corridor_plan_batch(tp_engine_t* e, const tp_poly_params* p, int32_t B, const int32_t* wp_offsets,
+                                    const double* waypoints, const double* bc, double init_r, double fs, double corridor_res,
+                                    double* coef_out, double* times_out, uint8_t* valid_out, int32_t* iters_out, double* r_out,
+                                    int32_t* status_out);
+
+/* polyTrajSolver::getPose (polyTrajSolver.cpp:1026-1049) on one solution in the coef / times layout above (K segments):
+ * out[4 nt] = x, y, z, yaw = atan2(dy, dx), with the reference's t == 0 -> 0.01 substitution for the heading; a time
+ * outside every knot interval yields zeros (the reference returns a default-constructed pose).  Host side. */
+int tp_poly_eval(int32_t K, const double* coef, const double* times, int32_t nt, const double* t, double* out);
+
+/* ------------------------------------------------------------------------------------ pwlTraj (fallback trajectory)
+ * piecewiseLinearTraj.cpp: what polyTrajOctomap / polyTrajOccMap return when no valid polynomial trajectory was found
+ * (polyTrajOctomap.cpp:309-317).  Host side (serial, a handful of waypoints), no engine needed.
+ * tp_pwl_plan = pwlTraj::updatePath + avgTimeAllocation (:31-46, :82-119): yaw_in NULL (useYaw = false) -> headings from
+ * the segments; yaw_out[K]; times_out (room for 2 (K-1) + 1 knots: rotation and forward periods alternate); returns the
+ * number of knots or a negative error.  tp_pwl_eval = pwlTraj::getPose (:199-268): out[4 nt] = x, y, z, yaw. */
+int tp_pwl_plan(int32_t K, const double* path, const double* yaw_in, double desired_vel, double desired_ang_vel, double* yaw_out,
+                double* times_out);
+int tp_pwl_eval(int32_t K, const double* path, const double* yaw, int32_t n_times, const double* times, int32_t nt, const double* t,
+                double* out);
 
 #ifdef __cplusplus
 }

@@ -407,6 +407,47 @@ def test_bspline_traj_class_drop_in(tp, engine, orc, sq_omap, problems):
         assert np.array_equal([x, y, z], ref)
 
 
+def test_batched_pose_sampling_matches_host_and_oracle(tp, engine, orc, problems):
+    """tp_vigo_sample_batch (bsplineTraj::getPose / evalTraj / evalTrajToMsg for a whole batch): position, velocity and
+    acceleration bit-identical to the host de Boor (tp_bspline_eval) and to the oracle's bspline::at; yaw within 4 ulp
+    of libm's atan2; ragged and empty sample lists, out-of-range times (clamped as bspline.cpp:33-35)."""
+    off, ctrl = problems["offsets"], problems["ctrl"]
+    B = 24
+    ts = 0.2
+    rng = np.random.default_rng(7)
+    times = []
+    for b in range(B):
+        dur = (off[b + 1] - off[b] - 3) * ts
+        k = int(rng.integers(0, 40)) if b % 5 else 0   # some trajectories have no samples at all
+        tt = rng.uniform(-0.5, dur + 0.5, k)            # some before 0 / after the end
+        if k >= 3:
+            tt[0], tt[1], tt[2] = 0.0, dur, 3 * ts     # end points and a knot
+        times.append(tt)
+    out = engine.sample_batch(off[:B + 1], ctrl[:off[B]], times=times, ts=ts, vel=True, acc=True, yaw=True)
+    n = 0
+    for b in range(B):
+        c = ctrl[off[b]:off[b + 1]]
+        sl = slice(out["t_offsets"][b], out["t_offsets"][b + 1])
+        if len(times[b]) == 0:
+            assert sl.start == sl.stop
+            continue
+        assert np.array_equal(out["pos"][sl], tp.bspline_eval(c, times[b], ts, 0))
+        assert np.array_equal(out["vel"][sl], tp.bspline_eval(c, times[b], ts, 1))
+        assert np.array_equal(out["acc"][sl], tp.bspline_eval(c, times[b], ts, 2))
+        assert np.array_equal(out["pos"][sl], orc.bspline_at(c, times[b], 3, ts))
+        assert np.array_equal(out["vel"][sl], orc.bspline_deriv_at(c, times[b], 1, ts))
+        v = out["vel"][sl]
+        ref = np.arctan2(v[:, 1], v[:, 0])
+        assert np.all(np.abs(out["yaw"][sl] - ref) <= 4 * np.spacing(np.abs(ref)) + 1e-300)
+        n += len(times[b])
+    # evalTraj's accumulated grid for every trajectory of the batch, positions only
+    g = engine.sample_batch(off, ctrl, dt=0.05, ts=ts, vel=False, yaw=False)
+    b = len(off) - 2
+    sl = slice(g["t_offsets"][b], g["t_offsets"][b + 1])
+    assert np.array_equal(g["pos"][sl], tp.bspline_eval(ctrl[off[b]:off[b + 1]], g["t"][sl], ts, 0))
+    print(f"batched sampling: {n} ragged samples + {len(g['t'])} grid samples bit-identical to the host de Boor")
+
+
 # ------------------------------------------------------------------------------------ committed golden vectors
 # tests/golden/vigo_golden.npz was generated by tools/make_golden.py through oracle/_ref, i.e. with the
 # REFERENCE'S OWN solver/lbfgs.hpp as the L-BFGS iterate.  The CUDA path is compared with the fixtures

@@ -95,6 +95,29 @@ def test_minsnap_solve_parity(tp, field):
     assert st3[0] == -3 and st3[1] == 0
 
 
+def test_minsnap_kernel_against_reference_osqp_golden(tp, field):
+    """k_minsnap_solve against the solutions of the REFERENCE's own libosqp.so (tests/golden/minsnap_osqp_golden.npz,
+    tools/make_minsnap_golden.py) at that solver's accuracy (eps 1e-3: 2e-3 x path length on sampled positions)."""
+    from oracle import polytraj_np as PN
+    from test_oracle_cpu import minsnap_golden_cases, MS_TOL_REL
+    m, g, e = field
+    cases = list(minsnap_golden_cases())
+    pt = tp.PolyTraj(e)
+    bc = np.array([c[1].reshape(12) for c in cases])
+    sols, status = pt.solve_batch([c[0] for c in cases], bc)
+    assert np.all(status == 0)
+    diffs = []
+    for (path, _, times, coef, _, _), (cg, tg) in zip(cases, sols):
+        assert np.max(np.abs(tg - times)) <= 1e-12
+        a, _ = PN.get_trajectory(coef, times, path[-1], 0.05)
+        b, _ = PN.get_trajectory(cg, tg, path[-1], 0.05)
+        d = float(np.max(np.abs(a - b)))
+        assert d <= MS_TOL_REL * times[-1], (len(path), d)
+        diffs.append(d)
+    print("k_minsnap_solve vs reference OSQP: %d cases, median %.2e m, worst %.2e m" % (len(diffs), np.median(diffs), max(diffs)))
+    assert np.median(diffs) <= 1e-3
+
+
 def test_box_collision_bit_exact_and_samples(tp, field):
     from oracle import polytraj_np as PT
     m, g, e = field
@@ -143,3 +166,84 @@ def test_make_plan_adding_waypoint_loop(tp, field):
         assert np.max(np.abs(res[b]["coef"] - o["coef"])) <= 1e-9 * np.max(np.abs(o["coef"])), b
         nvalid += res[b]["valid"]
     assert nvalid >= 1
+
+
+def test_corridor_qp_against_oracle_and_reference_osqp(tp, field):
+    """tp_corridor_solve_batch (corridor-constrained min-snap, polyTrajSolver.cpp:555-579, 813-840, 960-1012) on the golden
+    corridor cases: against the oracle's interior-point solution (same algorithm, both stopped at mu < 1e-10: sampled positions within 2e-5 m, objective
+    within 1e-8 relative, inside the corridor to 1e-9 m), and against the reference's own libosqp.so answers at OSQP's accuracy."""
+    from oracle import frontend_np as F
+    from oracle import polytraj_np as PN
+    from test_oracle_cpu import minsnap_golden_cases
+    m, g, e = field
+    cases = list(minsnap_golden_cases(corridor=True))
+    pt = tp.PolyTraj(e)
+    bc = np.array([c[1].reshape(12) for c in cases])
+    sols, status = pt.corridor_solve_batch([c[0] for c in cases], [c[5] for c in cases], 8.0, bc)
+    assert np.all(status == 0), status
+    worst, worst_osqp = 0.0, 0.0
+    for (path, bcv, times, coef, st_osqp, r), (cg, tg) in zip(cases, sols):
+        K = len(path) - 1
+        co, to, so, _ = PN.corridor_solve(path, r, 8.0, bc=bcv)
+        assert np.all(so == 0) and np.max(np.abs(tg - to)) <= 1e-12
+        a, _ = PN.get_trajectory(cg, tg, path[-1], 0.05)
+        b, _ = PN.get_trajectory(co, to, path[-1], 0.05)
+        worst = max(worst, float(np.max(np.abs(a - b))))
+        P = F.minsnap_P(K)
+        Ac, lo, hi = PN.corridor_rows(path, times, r, 8.0)
+        ref, _ = PN.get_trajectory(coef, times, path[-1], 0.05)
+        for ax in range(3):
+            x, xo = cg[ax].copy(), co[ax].copy()
+            for s in range(K):
+                sc = (times[s + 1] - times[s]) ** np.arange(8)
+                x[s * 8:(s + 1) * 8] *= sc
+                xo[s * 8:(s + 1) * 8] *= sc
+            w = Ac @ x
+            assert np.max(w - hi[:, ax]) <= 1e-9 and np.max(lo[:, ax] - w) <= 1e-9
+            assert abs(x @ P @ x - xo @ P @ xo) <= 1e-8 * max(xo @ P @ xo, 1.0)
+            if st_osqp[ax] == 1:
+                worst_osqp = max(worst_osqp, float(np.max(np.abs(a[:, ax] - ref[:, ax]))))
+    print("corridor QP: worst |pos| vs the oracle %.2e m, vs the reference OSQP (solved axes) %.2e m" % (worst, worst_osqp))
+    assert worst <= 2e-5 and worst_osqp <= 5e-2
+    # an infeasible corridor (2 mm around a sharp corner) is reported, not returned as a solution
+    path = np.array([[0, 0, 1.0], [2, 0, 1.0], [2, 2, 1.0], [0, 2, 1.0]])
+    _, st = pt.corridor_solve_batch([path], [np.full(3, 0.002)], 8.0)
+    co, to, so, _ = PN.corridor_solve(path, np.full(3, 0.002), 8.0)
+    assert np.array_equal(st[0] != 0, so != 0)
+
+
+def test_make_plan_corridor_constraint_loop(tp, field):
+    """polyTrajOctomap::makePlanCorridorConstraint (polyTrajOctomap.cpp:388-530) on field.bt: valid flags, iteration counts and
+    final corridor radii identical to the oracle's loop; trajectories within 2e-5 m; valid ones re-checked collision free."""
+    from oracle import polytraj_np as PT
+    m, g, e = field
+    rng = np.random.default_rng(11)
+    paths = _random_paths(g, m.info(), rng, [3, 4, 5, 6, 8, 10, 4, 5], clear=False)
+    p = tp.default_poly_params()
+    p.max_iter = 6
+    pt = tp.PolyTraj(e, p)
+    out = pt.make_plan_corridor_batch(paths, 0.5, 0.8, 8.0)
+    n_valid = n_strict = 0
+    for q, r in zip(paths, out):
+        o = PT.make_plan_corridor(q, g, 0.5, 0.8, 8.0, max_iter=6)
+        assert r["valid"] == o["valid"]
+        if np.any(r["status"] != 0) or np.any(o["status"] != 0):
+            # a corridor shrunk to the edge of feasibility: whether the last QP still converges within 60 interior-point
+            # iterations is decided in the last bits, on either side; such a path is invalid in both
+            assert not r["valid"]
+            continue
+        n_strict += 1
+        assert r["iters"] == o["iters"], (r["iters"], o["iters"])
+        assert np.allclose(r["r"], o["r"], rtol=0, atol=1e-15)
+        a, _ = PT.get_trajectory(r["coef"], r["times"], q[-1], 0.1)
+        b, _ = PT.get_trajectory(o["coef"], o["times"], q[-1], 0.1)
+        assert np.max(np.abs(a - b)) <= 2e-5
+        if r["valid"]:
+            n_valid += 1
+            has, _, _ = PT.check_collision_traj(g, a, r["times"], 0.1, (0.4, 0.4, 0.2), 0.2)
+            assert not has
+    assert n_strict >= len(paths) // 2
+    print(f"corridor loop: {n_valid}/{len(paths)} valid, {n_strict} compared iteration by iteration, iterations {[r['iters'] for r in out]}")
+    # single-waypoint path (polyTrajOctomap.cpp:390-395)
+    one = pt.make_plan_corridor_batch([paths[0][:1]])
+    assert one[0]["valid"]

@@ -250,3 +250,42 @@ def test_update_path_host_entry(tp, sq_map, sq_omap):
     inp = frontend_np.adjust_path_length_direct(list(path), sq_omap, p.max_path_length)
     want = frontend_np.parameterize_to_bspline(p.ctrl_pt_ts, np.array(inp), np.zeros((4, 3)))
     assert want.shape[0] == n and np.max(np.abs(out[:n] - want)) <= 1e-8
+
+
+def test_pwl_fallback_and_poly_pose_match_the_restatement(tp):
+    """pwlTraj (piecewiseLinearTraj.cpp) and polyTrajSolver::getPose through the C ABI (host side) against the Python
+    restatement: knots, headings and poses, with and without caller-supplied yaw, large turns (> PI_const) included."""
+    import ctypes as C
+    from oracle import pwl_np as PW
+    L = tp.load()
+    rng = np.random.default_rng(3)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    worst = 0.0
+    for trial in range(12):
+        K = int(rng.integers(2, 9))
+        path = np.ascontiguousarray(np.cumsum(rng.uniform(-3, 3, (K, 3)), 0))
+        if trial == 3:
+            path[2] = path[1]   # a zero-length segment (forward period shorter than 1e-3 s)
+        yaw_in = np.ascontiguousarray(rng.uniform(-3.1, 3.1, K)) if trial % 2 else None
+        yaw = np.zeros(K)
+        knots = np.zeros(2 * K + 1)
+        n = L.tp_pwl_plan(K, P(path), P(yaw_in) if yaw_in is not None else None, 1.0, 0.5, P(yaw), P(knots))
+        yo, ko = PW.plan(path, yaw_in)
+        assert n == len(ko) and np.array_equal(yaw, yo) and np.array_equal(knots[:n], ko)
+        t = np.ascontiguousarray(np.concatenate([np.linspace(-0.1, ko[-1] + 0.2, 57), ko]))
+        out = np.zeros((len(t), 4))
+        assert L.tp_pwl_eval(K, P(path), P(yaw), n, P(knots), len(t), P(t), P(out)) == 0
+        ref = np.array([PW.get_pose(path, yo, ko, float(x)) for x in t])
+        worst = max(worst, float(np.max(np.abs(out - ref))))
+    assert worst == 0.0
+    # polyTrajSolver::getPose on an exact min-snap solution
+    from oracle import frontend_np as F
+    path = np.array([[0, 0, 1.0], [1, 1, 1.0], [2, 0, 1.0], [4, 10, 1.0]])   # src/test/waypoint.yaml:2-5
+    coef, times = F.minsnap_solve(path, 1.0)
+    cf = np.ascontiguousarray(coef.reshape(-1))
+    t = np.ascontiguousarray(np.concatenate([np.linspace(0, times[-1], 41), times, [times[-1] + 1.0]]))
+    out = np.zeros((len(t), 4))
+    assert L.tp_poly_eval(len(times) - 1, P(cf), P(np.ascontiguousarray(times)), len(t), P(t), P(out)) == 0
+    ref = np.array([PW.poly_get_pose(coef, times, float(x)) for x in t])
+    assert np.max(np.abs(out - ref)) <= 1e-12
+    assert np.all(out[-1] == 0)   # outside every knot interval: the default pose

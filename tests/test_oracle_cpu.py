@@ -305,3 +305,92 @@ def test_fast_order_vs_reference_order_study(orc, sq_map, sq_omap, tp):
         pl.set_ctrl(out_f[off[b]:off[b + 1]])
         hit += pl.has_collision()
     assert hit == 0
+
+
+MS_GOLD = os.path.join(ROOT, "tests", "golden", "minsnap_osqp_golden.npz")
+
+
+def minsnap_golden_cases(corridor=False):
+    """(path, bc[4,3], times, coef[3, 8K], status[3], corridor sizes) of tests/golden/minsnap_osqp_golden.npz: solutions of the
+    REFERENCE's own libosqp.so with the reference's settings (tools/make_minsnap_golden.py, oracle/osqp_ref.c)."""
+    g = np.load(MS_GOLD)
+    for k in range(int(g["count"])):
+        r = g[f"corridor_{k}"]
+        if (len(r) > 0) != corridor:
+            continue
+        yield g[f"path_{k}"], g[f"bc_{k}"], g[f"times_{k}"], g[f"coef_{k}"], g[f"status_{k}"], r
+
+
+# OSQP stops at eps_abs = eps_rel = 1e-3 on its (scaled) residuals: its coefficients reproduce the exact minimiser's
+# trajectory to about 1e-3 of the path's extent.  Tolerance of the pin: 2e-3 x path length, median over the cases 1e-3 m.
+MS_TOL_REL = 2e-3
+
+
+def test_minsnap_kkt_oracle_is_pinned_to_the_reference_osqp():
+    """The exact KKT oracle (oracle/frontend_np.minsnap_solve) against the solutions the reference's own prebuilt
+    libosqp.so returns for the same QPs (polyTrajSolver.cpp:162-223, 870-879), at that solver's accuracy."""
+    from oracle import frontend_np as F
+    from oracle import polytraj_np as PN
+    diffs = []
+    for path, bc, times, coef, status, _ in minsnap_golden_cases():
+        assert np.all(status == 1)   # OSQP_SOLVED
+        c2, t2 = F.minsnap_solve(path, 1.0, bc[0], bc[1], bc[2], bc[3])
+        assert np.max(np.abs(t2 - times)) <= 1e-12
+        a, _ = PN.get_trajectory(coef, times, path[-1], 0.05)
+        b, _ = PN.get_trajectory(c2, t2, path[-1], 0.05)
+        d = float(np.max(np.abs(a - b)))
+        assert d <= MS_TOL_REL * times[-1], (len(path), d)
+        diffs.append(d)
+        # the objectives agree (OSQP's point is only approximately feasible, so its objective may sit slightly BELOW the minimum)
+        K = len(path) - 1
+        P = F.minsnap_P(K)
+
+        def obj(c):
+            x = c.copy()
+            for s in range(K):
+                x[s * 8:(s + 1) * 8] *= (times[s + 1] - times[s]) ** np.arange(8)
+            return 0.5 * x @ P @ x
+        for ax in range(3):
+            assert abs(obj(c2[ax]) - obj(coef[ax])) <= 5e-2 * obj(coef[ax]) + 1e-9
+    print("KKT oracle vs reference OSQP: %d cases, median %.2e m, worst %.2e m" % (len(diffs), np.median(diffs), max(diffs)))
+    assert np.median(diffs) <= 1e-3
+
+
+def test_corridor_qp_oracle_certificate_and_reference_osqp():
+    """The corridor-constrained min-snap QP (polyTrajSolver.cpp:555-579, 813-840, 960-1012) solved by the oracle's
+    interior-point method: (1) optimality CERTIFICATE — stationarity, primal feasibility, sign and complementarity of the
+    multipliers — so the solution is the unique minimiser independently of the algorithm; (2) against the REFERENCE's
+    own libosqp.so on the same QPs (golden): OSQP (eps 1e-3) violates the corridor by millimetres and sits within
+    centimetres of the exact minimiser, with an objective that is not above it."""
+    from oracle import frontend_np as F
+    from oracle import polytraj_np as PN
+    n_cases = 0
+    for path, bc, times, coef, status, r in minsnap_golden_cases(corridor=True):
+        K = len(path) - 1
+        c2, t2, st, raw = PN.corridor_solve(path, r, 8.0, bc=bc)
+        assert np.all(st == 0) and np.max(np.abs(t2 - times)) <= 1e-12
+        P = F.minsnap_P(K)
+        Aeq, b = F.minsnap_Ab(path, times, bc[0], bc[1], bc[2], bc[3])
+        Ac, lo, hi = PN.corridor_rows(path, times, r, 8.0)
+        a, _ = PN.get_trajectory(coef, times, path[-1], 0.05)
+        bb, _ = PN.get_trajectory(c2, t2, path[-1], 0.05)
+        for ax in range(3):
+            c, y, mu = raw[ax]["c"], raw[ax]["y"], raw[ax]["mu"]
+            w = Ac @ c
+            scale = 1.0 + np.max(np.abs(P @ c))
+            assert np.max(np.abs(P @ c + Aeq.T @ y + Ac.T @ mu)) <= 1e-6 * scale          # stationarity
+            assert np.max(np.abs(Aeq @ c - b[:, ax])) <= 1e-8                                # equality rows
+            assert np.max(w - hi[:, ax]) <= 1e-9 and np.max(lo[:, ax] - w) <= 1e-9           # inside the corridor
+            assert np.all((mu <= 1e-5) | (hi[:, ax] - w <= 1e-4)) and np.all((mu >= -1e-5) | (w - lo[:, ax] <= 1e-4))   # signs
+            assert np.max(np.abs(mu) * np.minimum(hi[:, ax] - w, w - lo[:, ax])) <= 1e-6     # complementarity
+            # the reference's OSQP answer for this axis
+            x = coef[ax].copy()
+            for s in range(K):
+                x[s * 8:(s + 1) * 8] *= (times[s + 1] - times[s]) ** np.arange(8)
+            wo = Ac @ x
+            viol = max(np.max(wo - hi[:, ax]), np.max(lo[:, ax] - wo), 0.0)
+            if status[ax] == 1:   # OSQP_SOLVED (2 = its iteration limit)
+                assert viol <= 2e-2 and np.max(np.abs(a[:, ax] - bb[:, ax])) <= 5e-2
+                assert 0.5 * x @ P @ x <= 0.5 * c @ P @ c * (1 + 1e-9)   # an infeasible point can only be cheaper
+        n_cases += 1
+    assert n_cases >= 6

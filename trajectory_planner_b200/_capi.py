@@ -76,11 +76,11 @@ SYMBOLS = [
     "tp_map_get_grid", "tp_bt_bbox", "tp_engine_default_cfg", "tp_engine_create", "tp_engine_destroy",
     "tp_engine_set_map", "tp_engine_synchronize", "tp_engine_launch_count", "tp_engine_stream",
     "tp_vigo_default_params", "tp_query_points", "tp_query_unknown", "tp_query_lines", "tp_vigo_cost_batch", "tp_vigo_cost_batch_dyn", "tp_vigo_optimize_batch_dyn",
-    "tp_vigo_optimize_batch", "tp_vigo_has_collision_batch", "tp_vigo_find_collision_seg_batch", "tp_astar_batch",
+    "tp_vigo_optimize_batch", "tp_vigo_has_collision_batch", "tp_vigo_sample_batch", "tp_vigo_find_collision_seg_batch", "tp_astar_batch",
     "tp_vigo_init_guides_batch", "tp_vigo_make_plan_batch", "tp_vigo_make_plan_batch_multi", "tp_vigo_frontend_batch", "tp_vigo_frontend_batch_device", "tp_vigo_input_path_check", "tp_vigo_update_path", "tp_bspline_fit",
     "tp_bspline_eval", "tp_engine_profile_enable", "tp_engine_profile_get", "tp_microbench_fp64",
     "tp_microbench_gather", "tp_poly_default_params", "tp_minsnap_solve_batch", "tp_poly_check_batch",
-    "tp_poly_box_collision", "tp_polytraj_make_plan_batch", "tp_polytraj_make_plan_batch_bc",
+    "tp_poly_box_collision", "tp_polytraj_make_plan_batch", "tp_polytraj_make_plan_batch_bc", "tp_poly_eval", "tp_corridor_solve_batch", "tp_polytraj_corridor_plan_batch", "tp_pwl_plan", "tp_pwl_eval",
 ]
 
 
@@ -140,6 +140,7 @@ def load():
     L.tp_vigo_make_plan_batch_multi.argtypes = [vp, C.c_int32, PP, C.c_int32, vp, vp, vp, vp, C.c_int32, vp, vp, vp, C.c_int32, vp]
     L.tp_vigo_cost_batch_dyn.argtypes = [vp, PP, C.c_int32, vp, vp, vp, vp, vp, vp, vp, C.c_int32, vp, vp, vp, vp, vp, C.c_int, vp]
     L.tp_vigo_optimize_batch_dyn.argtypes = [vp, PP, C.c_int32, vp, vp, vp, vp, vp, vp, vp, C.c_int32, vp, vp, vp, vp, vp, C.c_int, vp]
+    L.tp_vigo_sample_batch.argtypes = [vp, C.c_double, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp]
     L.tp_vigo_has_collision_batch.argtypes = [vp, PP, C.c_int32, vp, vp, vp, C.c_int, vp]
     L.tp_vigo_find_collision_seg_batch.argtypes = [vp, PP, C.c_int32, vp, vp, vp, vp, C.c_int, vp]
     L.tp_astar_batch.argtypes = [vp, PP, C.c_int32, vp, vp, vp, vp, vp, C.c_int, vp]
@@ -160,6 +161,11 @@ def load():
     L.tp_poly_box_collision.argtypes = [vp, QP, C.c_int64, vp, vp]
     L.tp_polytraj_make_plan_batch.argtypes = [vp, QP, C.c_int32, vp, vp, vp, vp, C.c_int64, vp, vp, vp, vp]
     L.tp_polytraj_make_plan_batch_bc.argtypes = [vp, QP, C.c_int32, vp, vp, vp, vp, vp, C.c_int64, vp, vp, vp, vp]
+    L.tp_corridor_solve_batch.argtypes = [vp, QP, C.c_int32, vp, vp, vp, vp, C.c_double, vp, vp, vp]
+    L.tp_polytraj_corridor_plan_batch.argtypes = [vp, QP, C.c_int32, vp, vp, vp, C.c_double, C.c_double, C.c_double, vp, vp, vp, vp, vp, vp]
+    L.tp_poly_eval.argtypes = [C.c_int32, vp, vp, C.c_int32, vp, vp]
+    L.tp_pwl_plan.argtypes = [C.c_int32, vp, vp, C.c_double, C.c_double, vp, vp]
+    L.tp_pwl_eval.argtypes = [C.c_int32, vp, vp, C.c_int32, vp, C.c_int32, vp, vp]
     L.tp_engine_profile_enable.argtypes = [vp, C.c_int]
     L.tp_engine_profile_get.argtypes = [vp, C.POINTER(Profile)]
     L.tp_microbench_fp64.argtypes = [vp, _dp]

@@ -290,6 +290,33 @@ class Engine:
                                                 TP_MEM_HOST, None), "tp_vigo_optimize_batch_dyn")
         return ctrl, res, xf
 
+    def sample_batch(self, offsets, ctrl, times=None, dt=None, ts=0.2, vel=True, acc=False, yaw=True):
+        """Batched pose-at-time queries (tp_vigo_sample_batch): `times` = list of per-trajectory time arrays, or `dt` for
+        evalTraj's accumulated grid t = 0; t <= duration; t += dt (bsplineTraj.cpp:1438-1447) per trajectory.
+        -> dict(t_offsets, t, pos [T,3], vel, acc, yaw) (None for the outputs not asked for)."""
+        offsets, ctrl = _i32(offsets), _f64(ctrl).reshape(-1, 3)
+        B = len(offsets) - 1
+        if times is None:
+            times = []
+            for b in range(B):
+                dur = (float(offsets[b + 1] - offsets[b]) - 3.0) * ts
+                tt, t = [], 0.0
+                while t <= dur:
+                    tt.append(t)
+                    t += dt
+                times.append(tt)
+        t_off = np.zeros(B + 1, np.int32)
+        t_off[1:] = np.cumsum([len(x) for x in times])
+        t = _f64(np.concatenate([np.asarray(x, float).ravel() for x in times]) if B else np.zeros(0))
+        T = len(t)
+        pos = np.zeros((T, 3))
+        v = np.zeros((T, 3)) if vel else None
+        a = np.zeros((T, 3)) if acc else None
+        y = np.zeros(T) if yaw else None
+        check(self.L.tp_vigo_sample_batch(self.h, float(ts), B, ptr(offsets), ptr(ctrl), ptr(t_off), ptr(t), ptr(pos), ptr(v), ptr(a),
+                                          ptr(y), TP_MEM_HOST, None), "tp_vigo_sample_batch")
+        return dict(t_offsets=t_off, t=t, pos=pos, vel=v, acc=a, yaw=y)
+
     def has_collision_batch(self, params, offsets, ctrl):
         offsets, ctrl = _i32(offsets), _f64(ctrl).reshape(-1, 3)
         B = len(offsets) - 1
@@ -461,6 +488,40 @@ class PolyTraj:
         out = np.zeros(len(xyz), np.uint8)
         check(self.engine.L.tp_poly_box_collision(self.engine.h, C.byref(self.params), len(xyz), ptr(xyz), ptr(out)), "tp_poly_box_collision")
         return out
+
+    def corridor_solve_batch(self, paths, corridor_size, corridor_res=8.0, bc=None):
+        """polyTrajSolver::solve with corridor constraints (tp_corridor_solve_batch): corridor_size = list of per-segment radii.
+        -> ([(coef [3, 8K], times)], status [B, 3])."""
+        off, wp = self._flat(paths)
+        B = len(paths)
+        r = _f64(np.concatenate([np.asarray(x, float).ravel() for x in corridor_size]))
+        bcv = None if bc is None else _f64(bc).reshape(B, 12)
+        coef = np.zeros(max(len(wp) - B, 1) * 24)
+        times = np.zeros(len(wp))
+        status = np.zeros((B, 3), np.int32)
+        check(self.engine.L.tp_corridor_solve_batch(self.engine.h, C.byref(self.params), B, ptr(off), ptr(wp), ptr(bcv), ptr(r),
+                                                    float(corridor_res), ptr(coef), ptr(times), ptr(status)), "tp_corridor_solve_batch")
+        return _poly_split(off, coef, times), status
+
+    def make_plan_corridor_batch(self, paths, init_r=0.5, fs=0.8, corridor_res=8.0, bc=None):
+        """polyTrajOctomap::makePlanCorridorConstraint for a list of waypoint arrays ->
+        list of dict(valid, iters, coef, times, r, status)."""
+        off, wp = self._flat(paths)
+        B = len(paths)
+        bcv = None if bc is None else _f64(bc).reshape(B, 12)
+        nseg = max(len(wp) - B, 1)
+        coef = np.zeros(nseg * 24)
+        times = np.zeros(len(wp))
+        valid = np.zeros(B, np.uint8)
+        iters = np.zeros(B, np.int32)
+        r = np.zeros(nseg)
+        status = np.zeros((B, 3), np.int32)
+        check(self.engine.L.tp_polytraj_corridor_plan_batch(self.engine.h, C.byref(self.params), B, ptr(off), ptr(wp), ptr(bcv), float(init_r),
+                                                            float(fs), float(corridor_res), ptr(coef), ptr(times), ptr(valid), ptr(iters),
+                                                            ptr(r), ptr(status)), "tp_polytraj_corridor_plan_batch")
+        sols = _poly_split(off, coef, times)
+        return [dict(valid=bool(valid[b]), iters=int(iters[b]), coef=sols[b][0], times=sols[b][1], r=r[off[b] - b:off[b + 1] - b - 1].copy(),
+                     status=status[b].copy()) for b in range(B)]
 
     def make_plan_batch(self, paths, bc=None):
         """polyTrajOctomap::makePlanAddingWaypoint for a list of waypoint arrays (bc: optional [B, 12] v0, v1, a0, a1) ->

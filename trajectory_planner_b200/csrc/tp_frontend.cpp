@@ -299,6 +299,129 @@ int tp_bspline_eval(int32_t N, const double* ctrl, double ts, int32_t deriv, int
   return TP_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// pwlTraj (piecewiseLinearTraj.cpp): the fallback polyTrajOctomap / polyTrajOccMap return when no valid polynomial
+// trajectory was found (polyTrajOctomap.cpp:309-317).  Serial host logic in the reference and here (a handful of
+// waypoints); the yaw that the reference carries through a quaternion is carried as the angle, with
+// quaternion_from_rpy's wrap (utils.h:45-47: yaw > PI_const -> yaw - 2 PI_const) applied where the reference converts.
+static const double kPIc = 3.1415926;   // utils.h:19
+static double pwl_yaw_distance(double y1, double y2) {   // utils.h:74-82
+  double delta = std::fabs(y2 - y1);
+  if (delta > kPIc) delta = 2 * kPIc - delta;
+  return delta;
+}
+static double pwl_wrap(double yaw) { return yaw > kPIc ? yaw - 2 * kPIc : yaw; }
+
+int tp_pwl_plan(int32_t K, const double* path, const double* yaw_in, double desired_vel, double desired_ang_vel, double* yaw_out,
+                double* times_out) {
+  if (K < 2 || !path || !yaw_out || !times_out || !(desired_vel > 0) || !(desired_ang_vel > 0)) {
+    tp_set_error("tp_pwl_plan: need >= 2 waypoints and positive velocities");
+    return TP_ERR_INVALID_ARG;
+  }
+  const bool use_yaw = yaw_in != nullptr;
+  if (use_yaw) {
+    for (int i = 0; i < K; ++i) yaw_out[i] = yaw_in[i];
+  } else {   // pwlTraj::updatePath (:31-46): heading of each segment, the last point repeats the previous heading
+    double yaw = 0.0;
+    for (int i = 0; i < K - 1; ++i) {
+      yaw = std::atan2(path[3 * (i + 1) + 1] - path[3 * i + 1], path[3 * (i + 1)] - path[3 * i]);
+      yaw_out[i] = yaw;
+    }
+    yaw_out[K - 1] = yaw;
+  }
+  // avgTimeAllocation (:82-119): per waypoint a rotation period (zero for the first) then a forward period
+  double total = 0.0;
+  int n = 0;
+  for (int i = 0; i < K - 1; ++i) {
+    if (i != 0) total += pwl_yaw_distance(yaw_out[i - 1], yaw_out[i]) / desired_ang_vel;
+    else total += 0.0;
+    times_out[n++] = total;
+    const double dx = path[3 * i] - path[3 * (i + 1)], dy = path[3 * i + 1] - path[3 * (i + 1) + 1], dz = path[3 * i + 2] - path[3 * (i + 1) + 2];
+    total += std::sqrt(std::pow(dx, 2) + std::pow(dy, 2) + std::pow(dz, 2)) / desired_vel;
+    times_out[n++] = total;
+  }
+  if (use_yaw) {
+    total += pwl_yaw_distance(yaw_out[K - 2], yaw_out[K - 1]) / desired_ang_vel;
+    times_out[n++] = total;
+  }
+  return n;
+}
+
+int tp_pwl_eval(int32_t K, const double* path, const double* yaw, int32_t n_times, const double* times, int32_t nt, const double* t,
+                double* out) {
+  if (K < 2 || !path || !yaw || n_times < 2 || !times || nt < 0 || (nt > 0 && (!t || !out))) return TP_ERR_INVALID_ARG;
+  for (int q = 0; q < nt; ++q) {   // pwlTraj::getPose (:199-268)
+    const double tq = t[q];
+    double* o = out + 4 * q;
+    o[0] = o[1] = o[2] = o[3] = 0.0;
+    if (tq >= times[n_times - 1]) {
+      o[0] = path[3 * (K - 1)]; o[1] = path[3 * (K - 1) + 1]; o[2] = path[3 * (K - 1) + 2];
+      o[3] = pwl_wrap(yaw[K - 1]);
+      continue;
+    }
+    for (int i = 0; i < n_times - 1; ++i) {
+      const double t0 = times[i], t1 = times[i + 1];
+      if (!(tq >= t0 && tq <= t1)) continue;
+      if (i % 2 == 1) {   // rotation period: at waypoint pointIdx + 1, turning from yaw[pointIdx] to yaw[pointIdx + 1]
+        const int pi = (i - 1) / 2;
+        const double yd = yaw[pi + 1] - yaw[pi];
+        double dir = 1.0, yda = std::fabs(yd);
+        if (yda <= kPIc && yd >= 0) dir = 1.0;
+        else if (yda <= kPIc && yd < 0) dir = -1.0;
+        else if (yda > kPIc && yd >= 0) { dir = -1.0; yda = 2 * kPIc - yda; }
+        else if (yda > kPIc && yd < 0) { dir = 1.0; yda = 2 * kPIc - yda; }
+        o[0] = path[3 * (pi + 1)]; o[1] = path[3 * (pi + 1) + 1]; o[2] = path[3 * (pi + 1) + 2];
+        o[3] = pwl_wrap(yaw[pi] + dir * (tq - t0) / (t1 - t0) * yda);
+      } else {            // forward period from waypoint pointIdx to pointIdx + 1
+        const int pi = i / 2;
+        const double* a = path + 3 * pi;
+        const double* b = path + 3 * (pi + 1);
+        if (t1 - t0 < 1e-3) {
+          o[0] = a[0]; o[1] = a[1]; o[2] = a[2];
+        } else {
+          o[0] = a[0] + (tq - t0) * (b[0] - a[0]) / (t1 - t0);
+          o[1] = a[1] + (tq - t0) * (b[1] - a[1]) / (t1 - t0);
+          o[2] = a[2] + (tq - t0) * (b[2] - a[2]) / (t1 - t0);
+        }
+        o[3] = pwl_wrap(yaw[pi]);
+      }
+      break;
+    }
+  }
+  return TP_OK;
+}
+
+int tp_poly_eval(int32_t K, const double* coef, const double* times, int32_t nt, const double* t, double* out) {
+  if (K < 1 || !coef || !times || nt < 0 || (nt > 0 && (!t || !out))) return TP_ERR_INVALID_ARG;
+  for (int q = 0; q < nt; ++q) {   // polyTrajSolver::getPose (polyTrajSolver.cpp:1026-1049)
+    double tq = t[q];
+    double* o = out + 4 * q;
+    o[0] = o[1] = o[2] = o[3] = 0.0;
+    for (int i = 0; i < K; ++i) {
+      if (!(tq >= times[i] && tq <= times[i + 1])) continue;
+      tq = tq - times[i];
+      const double* cx = coef + 8 * i;
+      const double* cy = coef + 8 * (size_t)K + 8 * i;
+      const double* cz = coef + 16 * (size_t)K + 8 * i;
+      double x = 0, y = 0, z = 0;
+      for (int d = 0; d < 8; ++d) {
+        const double pw = std::pow(tq, d);
+        x += cx[d] * pw; y += cy[d] * pw; z += cz[d] * pw;
+      }
+      if (tq == 0) tq = 0.01;
+      double dx = 0, dy = 0;
+      for (int d = 0; d < 8; ++d) {
+        const double pw = std::pow(tq, d - 1);
+        dx += d * cx[d] * pw; dy += d * cy[d] * pw;
+      }
+      o[0] = x; o[1] = y; o[2] = z; o[3] = std::atan2(dy, dx);
+      break;
+    }
+  }
+  return TP_OK;
+}
+
 int64_t tp_vigo_frontend_batch(const tp_map_t* m, const tp_vigo_params* p, int32_t B, const double* starts,
                                const double* goals, int32_t* offsets_out, double* ctrl_out, int64_t ctrl_cap,
                                uint8_t* valid) {

@@ -75,6 +75,90 @@ struct PolySolveArgs {
   int* queue;
 };
 
+// Time allocation + assembly of the equality-constrained KKT system of one path by the whole block:
+// M (n x n, n = 8 K + constraints) = [P A^T; A 0], R (n x 3) = [0; b] for the three axes, s_dt[K] = segment durations
+// (shared), times[nwp] = knots.  Returns (to every thread) 0, -2 too many segments, -3 fewer than two waypoints; *n_out = n.
+__device__ int poly_build_kkt(const double* wp, int nwp, const double* bc, double desired_vel, int cont, double* times, double* M,
+                              double* R, double* s_dt, int* n_out) {
+  const int tid = threadIdx.x;
+  const int K = nwp - 1;
+  if (K < 1 || K > PL_MAX_SEG) return K < 1 ? -3 : -2;
+  const int nvar = PL_NC * K;
+  const int ncon = (2 + 2 * (K - 1)) + 2 * (2 + (K - 1)) + (K - 1) * (cont - 2);
+  const int n = nvar + ncon;
+  *n_out = n;
+  // ---- time allocation (avgTimeAllocation): knots accumulate distance / desiredVel
+  if (tid == 0) {
+    double tt = 0.0;
+    times[0] = 0.0;
+    for (int i = 1; i < nwp; ++i) {
+      const double dx = wp[3 * i] - wp[3 * i - 3], dy = wp[3 * i + 1] - wp[3 * i - 2], dz = wp[3 * i + 2] - wp[3 * i - 1];
+      const double dur = sqrt(dx * dx + dy * dy + dz * dz) / desired_vel;
+      s_dt[i - 1] = dur;
+      tt += dur;
+      times[i] = tt;
+    }
+  }
+  __syncthreads();
+  for (size_t e = tid; e < (size_t)n * n; e += PL_THREADS) M[e] = 0.0;
+  for (int e = tid; e < 3 * n; e += PL_THREADS) R[e] = 0.0;
+  __syncthreads();
+  // ---- P: snap Gram matrix on normalised time (constructP)
+  for (int e = tid; e < K * 16; e += PL_THREADS) {
+    const int s = e / 16, i = 4 + (e % 16) / 4, j = 4 + (e % 4);
+    double f = 1.0;
+    for (int d = 0; d < 4; ++d) f *= (double)((i - d) * (j - d));
+    f /= (double)(i + j - 7);
+    M[(size_t)(s * PL_NC + i) * n + (s * PL_NC + j)] = f;
+  }
+  // ---- A (and A^T) + b: rows in the reference's order (constructA / constructBound)
+  if (tid == 0) {
+    int r = nvar;
+    auto put = [&](int row, int seg, double t1, int order, double scale, double sign) {
+      // derivative row of segment `seg` at normalised time 0 (t1 = 0) or 1: c_d * t^(d-order)
+      for (int d = order; d < PL_NC; ++d) {
+        double c = 1.0;
+        for (int k = 0; k < order; ++k) c *= (double)(d - k);
+        if (t1 == 0.0 && d != order) continue;
+        const double v = sign * c * scale;
+        const int col = seg * PL_NC + d;
+        M[(size_t)row * n + col] += v;
+        M[(size_t)col * n + row] += v;
+      }
+    };
+    auto rhs = [&](int row, double x, double y, double z) { R[3 * row] = x; R[3 * row + 1] = y; R[3 * row + 2] = z; };
+    put(r, 0, 0.0, 0, 1.0, 1.0); rhs(r, wp[0], wp[1], wp[2]); ++r;
+    put(r, K - 1, 1.0, 0, 1.0, 1.0); rhs(r, wp[3 * K], wp[3 * K + 1], wp[3 * K + 2]); ++r;
+    for (int i = 0; i < K - 1; ++i) { put(r, i, 1.0, 0, 1.0, 1.0); rhs(r, wp[3 * i + 3], wp[3 * i + 4], wp[3 * i + 5]); ++r; }
+    for (int i = 0; i < K - 1; ++i) { put(r, i, 1.0, 0, 1.0, 1.0); put(r, i + 1, 0.0, 0, 1.0, -1.0); ++r; }
+    for (int order = 1; order <= 2; ++order) {
+      put(r, 0, 0.0, order, 1.0, 1.0);
+      if (bc) rhs(r, bc[(order == 1 ? 0 : 6)], bc[(order == 1 ? 1 : 7)], bc[(order == 1 ? 2 : 8)]);
+      ++r;
+      put(r, K - 1, 1.0, order, 1.0, 1.0);
+      if (bc) rhs(r, bc[(order == 1 ? 3 : 9)], bc[(order == 1 ? 4 : 10)], bc[(order == 1 ? 5 : 11)]);
+      ++r;
+      for (int i = 0; i < K - 1; ++i) {
+        double sl = 1.0, sr = 1.0;
+        for (int k = 0; k < order; ++k) { sl *= s_dt[i + 1]; sr *= s_dt[i]; }
+        put(r, i, 1.0, order, sl, 1.0);
+        put(r, i + 1, 0.0, order, sr, -1.0);
+        ++r;
+      }
+    }
+    for (int order = 3; order <= cont; ++order)
+      for (int i = 0; i < K - 1; ++i) {
+        double sl = 1.0, sr = 1.0;
+        for (int k = 0; k < order; ++k) { sl *= s_dt[i + 1]; sr *= s_dt[i]; }
+        put(r, i, 1.0, order, sl, 1.0);
+        put(r, i + 1, 0.0, order, sr, -1.0);
+        ++r;
+      }
+  }
+  __syncthreads();
+  return 0;
+}
+
 // One min-snap solve by the whole block: waypoints wp[nwp] (+ boundary conditions bc[12] = v0, v1, a0, a1 or null) ->
 // knots times[nwp], coefficients coef[3][8 K] (axis-major).  M (n x n) and R (n x 3) are the block's scratch, n = 14 K.
 // Returns (to every thread) 0 ok, -1 singular KKT, -2 too many segments, -3 fewer than two waypoints.
@@ -86,81 +170,12 @@ __device__ int poly_solve_one(const double* wp, int nwp, const double* bc, doubl
   __shared__ double s_dt[PL_MAX_SEG + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   {
+    int n = 0;
+    const int brc = poly_build_kkt(wp, nwp, bc, desired_vel, cont, times, M, R, s_dt, &n);
+    if (brc != 0) return brc;
     const int K = nwp - 1;
-    if (K < 1 || K > PL_MAX_SEG) return K < 1 ? -3 : -2;
     const int nvar = PL_NC * K;
-    const int ncon = (2 + 2 * (K - 1)) + 2 * (2 + (K - 1)) + (K - 1) * (cont - 2);
-    const int n = nvar + ncon;
-    // ---- time allocation (avgTimeAllocation): knots accumulate distance / desiredVel
-    if (tid == 0) {
-      double tt = 0.0;
-      times[0] = 0.0;
-      for (int i = 1; i < nwp; ++i) {
-        const double dx = wp[3 * i] - wp[3 * i - 3], dy = wp[3 * i + 1] - wp[3 * i - 2], dz = wp[3 * i + 2] - wp[3 * i - 1];
-        const double dur = sqrt(dx * dx + dy * dy + dz * dz) / desired_vel;
-        s_dt[i - 1] = dur;
-        tt += dur;
-        times[i] = tt;
-      }
-      s_bad = 0;
-    }
-    __syncthreads();
-    for (size_t e = tid; e < (size_t)n * n; e += PL_THREADS) M[e] = 0.0;
-    for (int e = tid; e < 3 * n; e += PL_THREADS) R[e] = 0.0;
-    __syncthreads();
-    // ---- P: snap Gram matrix on normalised time (constructP)
-    for (int e = tid; e < K * 16; e += PL_THREADS) {
-      const int s = e / 16, i = 4 + (e % 16) / 4, j = 4 + (e % 4);
-      double f = 1.0;
-      for (int d = 0; d < 4; ++d) f *= (double)((i - d) * (j - d));
-      f /= (double)(i + j - 7);
-      M[(size_t)(s * PL_NC + i) * n + (s * PL_NC + j)] = f;
-    }
-    // ---- A (and A^T) + b: rows in the reference's order (constructA / constructBound)
-    if (tid == 0) {
-      
-      int r = nvar;
-      auto put = [&](int row, int seg, double t1, int order, double scale, double sign) {
-        // derivative row of segment `seg` at normalised time 0 (t1 = 0) or 1: c_d * t^(d-order)
-        for (int d = order; d < PL_NC; ++d) {
-          double c = 1.0;
-          for (int k = 0; k < order; ++k) c *= (double)(d - k);
-          if (t1 == 0.0 && d != order) continue;
-          const double v = sign * c * scale;
-          const int col = seg * PL_NC + d;
-          M[(size_t)row * n + col] += v;
-          M[(size_t)col * n + row] += v;
-        }
-      };
-      auto rhs = [&](int row, double x, double y, double z) { R[3 * row] = x; R[3 * row + 1] = y; R[3 * row + 2] = z; };
-      put(r, 0, 0.0, 0, 1.0, 1.0); rhs(r, wp[0], wp[1], wp[2]); ++r;
-      put(r, K - 1, 1.0, 0, 1.0, 1.0); rhs(r, wp[3 * K], wp[3 * K + 1], wp[3 * K + 2]); ++r;
-      for (int i = 0; i < K - 1; ++i) { put(r, i, 1.0, 0, 1.0, 1.0); rhs(r, wp[3 * i + 3], wp[3 * i + 4], wp[3 * i + 5]); ++r; }
-      for (int i = 0; i < K - 1; ++i) { put(r, i, 1.0, 0, 1.0, 1.0); put(r, i + 1, 0.0, 0, 1.0, -1.0); ++r; }
-      for (int order = 1; order <= 2; ++order) {
-        put(r, 0, 0.0, order, 1.0, 1.0);
-        if (bc) rhs(r, bc[(order == 1 ? 0 : 6)], bc[(order == 1 ? 1 : 7)], bc[(order == 1 ? 2 : 8)]);
-        ++r;
-        put(r, K - 1, 1.0, order, 1.0, 1.0);
-        if (bc) rhs(r, bc[(order == 1 ? 3 : 9)], bc[(order == 1 ? 4 : 10)], bc[(order == 1 ? 5 : 11)]);
-        ++r;
-        for (int i = 0; i < K - 1; ++i) {
-          double sl = 1.0, sr = 1.0;
-          for (int k = 0; k < order; ++k) { sl *= s_dt[i + 1]; sr *= s_dt[i]; }
-          put(r, i, 1.0, order, sl, 1.0);
-          put(r, i + 1, 0.0, order, sr, -1.0);
-          ++r;
-        }
-      }
-      for (int order = 3; order <= cont; ++order)
-        for (int i = 0; i < K - 1; ++i) {
-          double sl = 1.0, sr = 1.0;
-          for (int k = 0; k < order; ++k) { sl *= s_dt[i + 1]; sr *= s_dt[i]; }
-          put(r, i, 1.0, order, sl, 1.0);
-          put(r, i + 1, 0.0, order, sr, -1.0);
-          ++r;
-        }
-    }
+    if (tid == 0) s_bad = 0;
     __syncthreads();
     // ---- LU with partial pivoting, right-looking; rows with a zero multiplier are skipped
     for (int k = 0; k < n; ++k) {

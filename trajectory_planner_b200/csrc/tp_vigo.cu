@@ -917,6 +917,8 @@ __global__ void k_collect_results(BatchView bv, tp_vigo_result* out) {
 }
 
 #include "tp_poly.cuh"
+#include "tp_corridor.cuh"
+#include "tp_sample.cuh"
 
 // =========================================================================== engine
 struct DevBuf {
@@ -1659,6 +1661,57 @@ int tp_vigo_has_collision_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t
   e->launches += 1;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(hit, e->scratch_c.p, (size_t)B, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return TP_OK;
+}
+
+int tp_vigo_sample_batch(tp_engine_t* e, double ctrl_pt_ts, int32_t B, const int32_t* offsets, const double* ctrl,
+                         const int32_t* t_offsets, const double* t, double* pos, double* vel, double* acc, double* yaw,
+                         int mem, void* stream) {
+  if (!e || B < 0 || !(ctrl_pt_ts > 0)) return TP_ERR_INVALID_ARG;
+  if (B == 0) return TP_OK;
+  if (!offsets || !ctrl || !t_offsets || !t || !pos) return TP_ERR_INVALID_ARG;
+  CK(cudaSetDevice(e->device));
+  cudaStream_t s = pick_stream(e, stream);
+  const int blocks_cap = e->sm_count * 8;
+  if (mem == TP_MEM_DEVICE) {
+    // sample count unknown on the host: a grid-stride launch sized for the machine
+    k_sample_traj<<<blocks_cap, 256, 0, s>>>(B, offsets, ctrl, t_offsets, t, ctrl_pt_ts, pos, vel, acc, yaw);
+    e->launches += 1;
+    CK(cudaGetLastError());
+    return TP_OK;
+  }
+  if (mem != TP_MEM_HOST) return TP_ERR_INVALID_ARG;
+  if (offsets[0] != 0 || t_offsets[0] != 0) { tp_set_error("tp_vigo_sample_batch: offsets[0] and t_offsets[0] must be 0"); return TP_ERR_INVALID_ARG; }
+  for (int b = 0; b < B; ++b)
+    if (offsets[b + 1] < offsets[b] || t_offsets[b + 1] < t_offsets[b]) { tp_set_error("tp_vigo_sample_batch: offsets must be non-decreasing"); return TP_ERR_INVALID_ARG; }
+  const size_t np = (size_t)offsets[B], nt = (size_t)t_offsets[B];
+  if (nt == 0) return TP_OK;
+  const size_t ob = ((size_t)(B + 1) * 4 + 15) & ~(size_t)15;
+  // scratch_a: offsets | t_offsets | ctrl | t      scratch_b: pos | vel | acc | yaw
+  if (e->scratch_a.ensure(2 * ob + (3 * np + nt) * 8) != TP_OK || e->scratch_b.ensure(10 * nt * 8) != TP_OK) return TP_ERR_CUDA;
+  char* a = e->scratch_a.as<char>();
+  int* d_off = (int*)a;
+  int* d_toff = (int*)(a + ob);
+  double* d_ctrl = (double*)(a + 2 * ob);
+  double* d_t = d_ctrl + 3 * np;
+  double* d_pos = e->scratch_b.as<double>();
+  double* d_vel = d_pos + 3 * nt;
+  double* d_acc = d_vel + 3 * nt;
+  double* d_yaw = d_acc + 3 * nt;
+  CK(cudaMemcpyAsync(d_off, offsets, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_toff, t_offsets, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_ctrl, ctrl, 3 * np * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_t, t, nt * 8, cudaMemcpyHostToDevice, s));
+  const int blocks = (int)std::min<size_t>((nt + 255) / 256, (size_t)blocks_cap);
+  k_sample_traj<<<blocks, 256, 0, s>>>(B, d_off, d_ctrl, d_toff, d_t, ctrl_pt_ts, d_pos, vel ? d_vel : nullptr, acc ? d_acc : nullptr,
+                                       yaw ? d_yaw : nullptr);
+  e->launches += 1;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(pos, d_pos, 3 * nt * 8, cudaMemcpyDeviceToHost, s));
+  if (vel) CK(cudaMemcpyAsync(vel, d_vel, 3 * nt * 8, cudaMemcpyDeviceToHost, s));
+  if (acc) CK(cudaMemcpyAsync(acc, d_acc, 3 * nt * 8, cudaMemcpyDeviceToHost, s));
+  if (yaw) CK(cudaMemcpyAsync(yaw, d_yaw, nt * 8, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   return TP_OK;
 }
@@ -2557,3 +2610,92 @@ int tp_polytraj_make_plan_batch_bc(tp_engine_t* e, const tp_poly_params* p, int3
 }
 
 }  // extern "C"
+
+// corridor-constrained min-snap: one QP solve with caller-supplied radii (solve_only) or the whole
+// makePlanCorridorConstraint loop
+static int corridor_run(tp_engine_t* e, const tp_poly_params* p, int32_t B, const int32_t* wp_offsets, const double* waypoints,
+                        const double* bc, const double* r_in, int solve_only, double init_r, double fs, double corridor_res,
+                        double* coef_out, double* times_out, uint8_t* valid_out, int32_t* iters_out, double* r_out, int32_t* status_out) {
+  int rc = poly_check_params(e, p, !solve_only);
+  if (rc != TP_OK) return rc;
+  if (B <= 0 || !wp_offsets || !waypoints || !coef_out || !times_out) return TP_ERR_INVALID_ARG;
+  if (!(corridor_res > 0) || (!solve_only && (!(init_r > 0) || !(fs > 0) || !(fs < 1)))) {
+    tp_set_error("corridor: need corridor_res > 0, initial radius > 0 and a shrinking factor in (0, 1)");
+    return TP_ERR_INVALID_ARG;
+  }
+  if (wp_offsets[0] != 0) { tp_set_error("corridor: wp_offsets[0] must be 0"); return TP_ERR_INVALID_ARG; }
+  int kmax = 1;
+  for (int b = 0; b < B; ++b) {
+    const int nw = wp_offsets[b + 1] - wp_offsets[b];
+    if (nw < 1 || nw > PL_MAX_SEG + 1) { tp_set_error("path %d has %d waypoints (1..%d supported)", b, nw, PL_MAX_SEG + 1); return TP_ERR_CAPACITY; }
+    kmax = std::max(kmax, nw - 1);
+  }
+  CK(cudaSetDevice(e->device));
+  cudaStream_t s = e->stream;
+  if (!solve_only) {
+    rc = poly_ensure_tacc(e, p->delT, s);
+    if (rc != TP_OK) return rc;
+  }
+  const int total = wp_offsets[B], nseg = total - B;
+  const int nmax = 14 * kmax;
+  const size_t stride = corridor_scratch_doubles(nmax);
+  const int grid = std::min(B, e->sm_count * 4);
+  // scratch_b: coef | times | radii in | radii out      scratch_c: iters | status | valid
+  const size_t nb = (size_t)24 * std::max(nseg, 1) + (size_t)total + 2 * (size_t)std::max(nseg, 1);
+  if (e->off.ensure((size_t)(B + 1) * 4) != TP_OK || e->ctrl.ensure((size_t)total * 24) != TP_OK ||
+      e->poly_scratch.ensure((size_t)grid * stride * 8) != TP_OK || e->scratch_b.ensure(nb * 8) != TP_OK ||
+      e->scratch_c.ensure((size_t)B * 17 + 64) != TP_OK || e->counters.ensure(64 * 4) != TP_OK || (bc && e->dyn.ensure((size_t)B * 96) != TP_OK))
+    return TP_ERR_CUDA;
+  CK(cudaMemcpyAsync(e->off.p, wp_offsets, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(e->ctrl.p, waypoints, (size_t)total * 24, cudaMemcpyHostToDevice, s));
+  if (bc) CK(cudaMemcpyAsync(e->dyn.p, bc, (size_t)B * 96, cudaMemcpyHostToDevice, s));
+  CK(cudaMemsetAsync(e->counters.p, 0, 64 * 4, s));
+  CorridorArgs A;
+  A.B = B; A.wp_off = e->off.as<int>(); A.wp = e->ctrl.as<double>(); A.bc = bc ? e->dyn.as<double>() : nullptr;
+  A.desired_vel = p->desired_vel; A.cont = p->cont; A.max_iter = p->max_iter;
+  A.init_r = init_r; A.fs = fs; A.corridor_res = corridor_res; A.solve_only = solve_only;
+  A.t_acc = e->poly_tacc.as<double>(); A.n_t_acc = e->poly_tacc_n;
+  for (int a = 0; a < 3; ++a) A.box[a] = p->box[a];
+  A.map_res = p->map_res;
+  A.coef = e->scratch_b.as<double>(); A.times = A.coef + (size_t)24 * std::max(nseg, 1);
+  double* d_rin = A.times + total;
+  A.r_out = d_rin + std::max(nseg, 1);
+  A.r_in = nullptr;
+  if (r_in && nseg > 0) {
+    CK(cudaMemcpyAsync(d_rin, r_in, (size_t)nseg * 8, cudaMemcpyHostToDevice, s));
+    A.r_in = d_rin;
+  }
+  A.iters = e->scratch_c.as<int>(); A.status = A.iters + B; A.valid = reinterpret_cast<uint8_t*>(A.status + 3 * B);
+  A.scratch = e->poly_scratch.as<double>(); A.stride = stride; A.nmax = nmax; A.queue = e->counters.as<int>();
+  CK(cudaMemsetAsync(A.coef, 0, (size_t)24 * std::max(nseg, 1) * 8, s));
+  {
+    ProfScope ps(e, 6, s, B);
+    k_corridor_loop<<<grid, PL_THREADS, 0, s>>>(A, solve_only && !e->has_map ? PolyMap{} : make_polymap(e));
+  }
+  e->launches += 1;
+  CK(cudaGetLastError());
+  if (nseg > 0) CK(cudaMemcpyAsync(coef_out, A.coef, (size_t)24 * nseg * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(times_out, A.times, (size_t)total * 8, cudaMemcpyDeviceToHost, s));
+  if (valid_out) CK(cudaMemcpyAsync(valid_out, A.valid, (size_t)B, cudaMemcpyDeviceToHost, s));
+  if (iters_out) CK(cudaMemcpyAsync(iters_out, A.iters, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+  if (status_out) CK(cudaMemcpyAsync(status_out, A.status, (size_t)B * 12, cudaMemcpyDeviceToHost, s));
+  if (r_out && nseg > 0) CK(cudaMemcpyAsync(r_out, A.r_out, (size_t)nseg * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return TP_OK;
+}
+
+extern "C" int tp_corridor_solve_batch(tp_engine_t* e, const tp_poly_params* p, int32_t B, const int32_t* wp_offsets, const double* waypoints,
+                                       const double* bc, const double* corridor_size, double corridor_res, double* coef, double* times,
+                                       int32_t* status) {
+  if (!corridor_size || !status) return TP_ERR_INVALID_ARG;
+  return corridor_run(e, p, B, wp_offsets, waypoints, bc, corridor_size, 1, 0.0, 0.0, corridor_res, coef, times, nullptr, nullptr, nullptr, status);
+}
+
+extern "C" int tp_polytraj_corridor_plan_batch(tp_engine_t* e, const tp_poly_params* p, int32_t B, const int32_t* wp_offsets,
+                                               const double* waypoints, const double* bc, double init_r, double fs, double corridor_res,
+                                               double* coef_out, double* times_out, uint8_t* valid_out, int32_t* iters_out,
+                                               double* r_out, int32_t* status_out) {
+  if (!valid_out || !iters_out) return TP_ERR_INVALID_ARG;
+  return corridor_run(e, p, B, wp_offsets, waypoints, bc, nullptr, 0, init_r, fs, corridor_res, coef_out, times_out, valid_out, iters_out,
+                      r_out, status_out);
+}
