@@ -707,6 +707,16 @@ def main():
     h2d = int(total_pts * 24 + (B + 1) * 4)
     d2h = int(total_pts * 24 + B * tp.RESULT_DTYPE.itemsize)
 
+    # ---- N > 1: BASELINE.json configs[2] as well — the 65,536-solve maze.bt + tunnel.bt batch STRONG-scaled over the ranks
+    # (contiguous shards from sharding.shard_bounds, no collective on the solve path), every rank takes part
+    oct_line = None
+    if world > 1 and not args.no_extras:
+        try:
+            oct_line = run_octomap(args, tp, torch, dist, rank, world, local, quiet=True, total=args.octomap_total, K=2, W=1)
+        except Exception as ex:   # a secondary workload must not take the headline line down
+            oct_line = dict(error=repr(ex))
+        torch.cuda.set_stream(tstream)
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -838,6 +848,9 @@ def main():
         except Exception as ex:
             extras["collision_sweep"] = dict(error=repr(ex))
         line["extras"] = extras
+    if oct_line is not None:
+        keys = ("value", "unit", "n_gpus", "ms_per_step", "scaling", "config", "e2e", "roofline", "gpu_launches", "error")
+        line["extras"] = {"octomap65536": {k: oct_line[k] for k in keys if k in oct_line}}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

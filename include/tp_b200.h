@@ -380,6 +380,14 @@ int tp_polytraj_corridor_plan_batch(tp_engine_t* e, const tp_poly_params* p, int
                                     const double* waypoints, const double* bc, double init_r, double fs, double corridor_res,
                                     double* coef_out, double* times_out, uint8_t* valid_out, int32_t* iters_out, double* r_out,
                                     int32_t* status_out);
+/* polyTrajOccMap::makePlan(trajectory, corridorConstraint) (polyTrajOccMap.cpp:326-399): the same loop on the ViGO
+ * occupancy map (mapManager::occMap): a trajectory sample collides when it is inflated-occupied AND unknown
+ * (checkCollisionTraj, :523-546 — the reference's conjunction, preserved); bc = initVel, endVel, initAcc, endAcc are honoured
+ * (:336-341).  corridor_constraint = 0: one equality-only solve, valid = 1 without a collision check (:370-374). */
+int tp_polytraj_occmap_plan_batch(tp_engine_t* e, const tp_poly_params* p, int32_t B, const int32_t* wp_offsets,
+                                  const double* waypoints, const double* bc, int32_t corridor_constraint, double init_r, double fs,
+                                  double corridor_res, double* coef_out, double* times_out, uint8_t* valid_out, int32_t* iters_out,
+                                  double* r_out, int32_t* status_out);
 
 /* polyTrajSolver::getPose (polyTrajSolver.cpp:1026-1049) on one solution in the coef / times layout above (K segments):
  * out[4 nt] = x, y, z, yaw = atan2(dy, dx), with the reference's t == 0 -> 0.01 substitution for the heading; a time

@@ -122,7 +122,11 @@ def corridor_qp_ipm(P, Aeq, b, Ac, lo, hi):
 
         def step(rcu, rcl):
             g = (-rcu + lu * ru) / su + (rcl + ll * rl) / sl
-            s = np.linalg.solve(Kmat, np.concatenate([-rd - Ac.T @ g, -rp]))
+            rhs = np.concatenate([-rd - Ac.T @ g, -rp])
+            try:
+                s = np.linalg.solve(Kmat, rhs)
+            except np.linalg.LinAlgError:   # barrier terms of 1e19 next to entries of order 1: numerically singular in the last
+                s = np.linalg.lstsq(Kmat, rhs, rcond=None)[0]   # iterations (the device guards the vanished pivot instead)
             dc, dy = s[:n], s[n:]
             Adc = Ac @ dc
             dsu, dsl = -ru - Adc, rl + Adc
@@ -172,8 +176,25 @@ def corridor_solve(path, corridor_size, corridor_res=8.0, desired_vel=1.0, cont=
     return coef, times, status, raw
 
 
+def check_collision_traj_occmap(omap, traj, times, delT):
+    """polyTrajOccMap::checkCollisionTraj (polyTrajOccMap.cpp:523-546) on the oracle's occMap: a sample collides when it is
+    inflated-occupied AND unknown (the reference's conjunction)."""
+    traj = np.asarray(traj, float)
+    flags = (omap.query(traj) != 0) & (omap.query_unknown(traj) != 0)
+    seg = set()
+    t = 0.0
+    for c in flags:
+        if c:
+            for i in range(len(times) - 1):
+                if times[i] <= t <= times[i + 1]:
+                    seg.add(i)
+                    break
+        t += delT
+    return bool(flags.any()), sorted(seg), flags
+
+
 def make_plan_corridor(path, grid, init_r=0.5, fs=0.8, corridor_res=8.0, desired_vel=1.0, delT=0.1, box=(0.4, 0.4, 0.2),
-                       map_res=0.2, max_iter=100, cont=4):
+                       map_res=0.2, max_iter=100, cont=4, occmap=None, bc=None):
     """polyTrajOctomap::makePlanCorridorConstraint (polyTrajOctomap.cpp:388-459): corridors of radius init_r around every
     path segment, the radius of a colliding segment shrunk by fs, until collision free or maxIter.  An infeasible
     (or unconverged) QP ends the loop with valid = False: the reference keeps its previous solution in that case
@@ -184,7 +205,7 @@ def make_plan_corridor(path, grid, init_r=0.5, fs=0.8, corridor_res=8.0, desired
     valid = False
     coef = times = None
     while not valid:
-        c2, times, status, _ = corridor_solve(path, r, corridor_res, desired_vel, cont)
+        c2, times, status, _ = corridor_solve(path, r, corridor_res, desired_vel, cont, bc)
         if np.any(status != 0):
             if coef is None:
                 coef = c2
@@ -192,7 +213,10 @@ def make_plan_corridor(path, grid, init_r=0.5, fs=0.8, corridor_res=8.0, desired
             break
         coef = c2
         traj, _ = get_trajectory(coef, times, path[-1], delT)
-        has, segs, _ = check_collision_traj(grid, traj, times, delT, box, map_res)
+        if occmap is not None:   # polyTrajOccMap::makePlan (polyTrajOccMap.cpp:326-399) on the ViGO occupancy map
+            has, segs, _ = check_collision_traj_occmap(occmap, traj, times, delT)
+        else:
+            has, segs, _ = check_collision_traj(grid, traj, times, delT, box, map_res)
         valid = not has
         if not valid:
             for s in segs:

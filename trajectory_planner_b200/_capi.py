@@ -80,7 +80,7 @@ SYMBOLS = [
     "tp_vigo_init_guides_batch", "tp_vigo_make_plan_batch", "tp_vigo_make_plan_batch_multi", "tp_vigo_frontend_batch", "tp_vigo_frontend_batch_device", "tp_vigo_input_path_check", "tp_vigo_update_path", "tp_bspline_fit",
     "tp_bspline_eval", "tp_engine_profile_enable", "tp_engine_profile_get", "tp_microbench_fp64",
     "tp_microbench_gather", "tp_poly_default_params", "tp_minsnap_solve_batch", "tp_poly_check_batch",
-    "tp_poly_box_collision", "tp_polytraj_make_plan_batch", "tp_polytraj_make_plan_batch_bc", "tp_poly_eval", "tp_corridor_solve_batch", "tp_polytraj_corridor_plan_batch", "tp_pwl_plan", "tp_pwl_eval",
+    "tp_poly_box_collision", "tp_polytraj_make_plan_batch", "tp_polytraj_make_plan_batch_bc", "tp_poly_eval", "tp_corridor_solve_batch", "tp_polytraj_corridor_plan_batch", "tp_polytraj_occmap_plan_batch", "tp_pwl_plan", "tp_pwl_eval",
 ]
 
 
@@ -163,6 +163,7 @@ def load():
     L.tp_polytraj_make_plan_batch_bc.argtypes = [vp, QP, C.c_int32, vp, vp, vp, vp, vp, C.c_int64, vp, vp, vp, vp]
     L.tp_corridor_solve_batch.argtypes = [vp, QP, C.c_int32, vp, vp, vp, vp, C.c_double, vp, vp, vp]
     L.tp_polytraj_corridor_plan_batch.argtypes = [vp, QP, C.c_int32, vp, vp, vp, C.c_double, C.c_double, C.c_double, vp, vp, vp, vp, vp, vp]
+    L.tp_polytraj_occmap_plan_batch.argtypes = [vp, QP, C.c_int32, vp, vp, vp, C.c_int32, C.c_double, C.c_double, C.c_double, vp, vp, vp, vp, vp, vp]
     L.tp_poly_eval.argtypes = [C.c_int32, vp, vp, C.c_int32, vp, vp]
     L.tp_pwl_plan.argtypes = [C.c_int32, vp, vp, C.c_double, C.c_double, vp, vp]
     L.tp_pwl_eval.argtypes = [C.c_int32, vp, vp, C.c_int32, vp, C.c_int32, vp, vp]

@@ -503,9 +503,9 @@ class PolyTraj:
                                                     float(corridor_res), ptr(coef), ptr(times), ptr(status)), "tp_corridor_solve_batch")
         return _poly_split(off, coef, times), status
 
-    def make_plan_corridor_batch(self, paths, init_r=0.5, fs=0.8, corridor_res=8.0, bc=None):
-        """polyTrajOctomap::makePlanCorridorConstraint for a list of waypoint arrays ->
-        list of dict(valid, iters, coef, times, r, status)."""
+    def make_plan_corridor_batch(self, paths, init_r=0.5, fs=0.8, corridor_res=8.0, bc=None, occmap=False, corridor_constraint=True):
+        """polyTrajOctomap::makePlanCorridorConstraint for a list of waypoint arrays (occmap=True: polyTrajOccMap::makePlan on
+        the ViGO occupancy map, optionally without corridor constraints) -> list of dict(valid, iters, coef, times, r, status)."""
         off, wp = self._flat(paths)
         B = len(paths)
         bcv = None if bc is None else _f64(bc).reshape(B, 12)
@@ -516,9 +516,15 @@ class PolyTraj:
         iters = np.zeros(B, np.int32)
         r = np.zeros(nseg)
         status = np.zeros((B, 3), np.int32)
-        check(self.engine.L.tp_polytraj_corridor_plan_batch(self.engine.h, C.byref(self.params), B, ptr(off), ptr(wp), ptr(bcv), float(init_r),
-                                                            float(fs), float(corridor_res), ptr(coef), ptr(times), ptr(valid), ptr(iters),
-                                                            ptr(r), ptr(status)), "tp_polytraj_corridor_plan_batch")
+        if occmap:
+            check(self.engine.L.tp_polytraj_occmap_plan_batch(self.engine.h, C.byref(self.params), B, ptr(off), ptr(wp), ptr(bcv),
+                                                              1 if corridor_constraint else 0, float(init_r), float(fs), float(corridor_res),
+                                                              ptr(coef), ptr(times), ptr(valid), ptr(iters), ptr(r), ptr(status)),
+                  "tp_polytraj_occmap_plan_batch")
+        else:
+            check(self.engine.L.tp_polytraj_corridor_plan_batch(self.engine.h, C.byref(self.params), B, ptr(off), ptr(wp), ptr(bcv), float(init_r),
+                                                                float(fs), float(corridor_res), ptr(coef), ptr(times), ptr(valid), ptr(iters),
+                                                                ptr(r), ptr(status)), "tp_polytraj_corridor_plan_batch")
         sols = _poly_split(off, coef, times)
         return [dict(valid=bool(valid[b]), iters=int(iters[b]), coef=sols[b][0], times=sols[b][1], r=r[off[b] - b:off[b + 1] - b - 1].copy(),
                      status=status[b].copy()) for b in range(B)]

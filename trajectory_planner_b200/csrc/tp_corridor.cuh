@@ -9,8 +9,9 @@
 // millimetres, tests/golden/minsnap_osqp_golden.npz); here it is solved to convergence by a Mehrotra predictor-corrector
 // interior-point method — the algorithm, start point and update formulas of oracle/polytraj_np.corridor_qp_ipm, which the
 // tests compare against.  Each Newton system (P + Ac' S Ac) dc + Aeq' dy = ..., Aeq dc = ... has the sparsity of the
-// equality-only KKT system (Ac' S Ac is block diagonal, 8 x 8 per segment) and is factorised by the block's LU
-// (PA = LU, multipliers kept: one factorisation serves the predictor and the corrector).
+// equality-only KKT system (Ac' S Ac is block diagonal, 8 x 8 per segment): the same BAND matrix (tp_band.cuh), factorised
+// by warp 0 of the block (one factorisation serves the predictor and the corrector); the per-row vector work runs on all
+// four warps.
 // One thread block per path runs the whole loop: solve -> sample -> box collision check -> shrink the corridors of the
 // colliding segments by fs -> re-solve, until collision free, an infeasible QP, or maxIter.
 #pragma once
@@ -31,6 +32,8 @@ struct CorridorArgs {
   double init_r, fs, corridor_res;
   const double* r_in;      // solve-only mode: per-segment radii at wp_off[b] - b + s; else null
   int solve_only;          // 1: one QP solve with r_in, no collision loop
+  int occmap;              // 1: polyTrajOccMap's collision test on the ViGO occupancy map instead of the octomap box check
+  int no_corridor;         // 1: polyTrajOccMap::makePlan(corridorConstraint = false): the equality-only solve, always valid
   const double* t_acc;
   int n_t_acc;
   double box[3];
@@ -42,14 +45,16 @@ struct CorridorArgs {
   int* status;             // out [3 B] per axis: 0 converged, 1 infeasible / not converged, < 0 the solver's error
   double* r_out;           // out: final radii per segment (may be null)
   double* scratch;
-  size_t stride;           // doubles per resident block
-  int nmax;
+  size_t stride;           // doubles per resident block: corridor_scratch_doubles(kmax)
+  int kmax;                // segments of the longest path
   int* queue;
 };
 
-__host__ __device__ inline size_t corridor_scratch_doubles(int nmax) {
-  return 2 * (size_t)nmax * nmax + 3 * (size_t)nmax      // M0, M, R
-         + 3 * (size_t)nmax + 4 * (size_t)nmax           // X[3], RHS, DX, RD, piv
+__host__ __device__ inline size_t corridor_scratch_doubles(int kmax) {
+  const size_t n = (size_t)band_order(kmax, 4);
+  return 2 * n * BD_W + 3 * n           // A0, A, R
+         + 3 * n + 2 * n + 2 * n        // X[3], DX, RD, piv + kind (ints)
+         + (size_t)kmax + 8             // dt
          + (size_t)CR_MAX_ROWS * (8 + 1 + 3 + 2 + CR_NVEC);   // Arow, seg, mid, lo / hi, work vectors
 }
 
@@ -72,104 +77,35 @@ struct BlkRed {   // block-wide reductions (128 threads), result to every thread
   __device__ __forceinline__ double min(double v) { return -max(-v); }
 };
 
-// PA = LU in place (partial pivoting, whole rows swapped, multipliers kept below the diagonal, rows with a zero multiplier
-// skipped).  Returns (to every thread) 0 or -1 (singular).
-__device__ int kkt_factor(double* M, int n, int* piv) {
-  __shared__ int f_piv, f_bad;
-  __shared__ double f_red[PL_THREADS / 32];
-  __shared__ int f_redi[PL_THREADS / 32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) f_bad = 0;
-  __syncthreads();
-  for (int k = 0; k < n; ++k) {
-    double best = -1.0;
-    int bi = k;
-    for (int i = k + tid; i < n; i += PL_THREADS) {
-      const double v = fabs(M[(size_t)i * n + k]);
-      if (v > best) { best = v; bi = i; }
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-    }
-    if (lane == 0) { f_red[warp] = best; f_redi[warp] = bi; }
-    __syncthreads();
-    if (tid == 0) {
-      double bb = f_red[0];
-      int ii = f_redi[0];
-      for (int w = 1; w < PL_THREADS / 32; ++w)
-        if (f_red[w] > bb || (f_red[w] == bb && f_redi[w] < ii)) { bb = f_red[w]; ii = f_redi[w]; }
-      f_piv = ii;
-      piv[k] = ii;
-      if (!(bb > 1e-300)) f_bad = 1;
-    }
-    __syncthreads();
-    if (f_bad) break;
-    const int p = f_piv;
-    if (p != k) {
-      for (int j = tid; j < n; j += PL_THREADS) {
-        const double a = M[(size_t)k * n + j];
-        M[(size_t)k * n + j] = M[(size_t)p * n + j];
-        M[(size_t)p * n + j] = a;
-      }
-      __syncthreads();
-    }
-    const double inv = 1.0 / M[(size_t)k * n + k];
-    for (int i = k + 1 + warp; i < n; i += PL_THREADS / 32) {
-      const double mik = M[(size_t)i * n + k];
-      if (mik == 0.0) continue;   // uniform per warp
-      const double l = mik * inv;
-      for (int j = k + 1 + lane; j < n; j += 32) M[(size_t)i * n + j] -= l * M[(size_t)k * n + j];
-      __syncwarp();
-      if (lane == 0) M[(size_t)i * n + k] = l;
-    }
-    __syncthreads();
-  }
-  const int bad = f_bad;
-  __syncthreads();
-  return bad ? -1 : 0;
-}
-
-// x <- (LU)^-1 P x by warp 0 (row-oriented triangular solves, one shuffle reduction per row); every thread calls it
-__device__ void kkt_solve(const double* M, int n, const int* piv, double* x) {
+// band_factor / band_solve (one warp) inside a block: warp 0 works, the block waits
+__device__ int blk_band_factor(double* A, int n, int* piv, bool guard) {
+  __shared__ int f_rc;
   if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    if (lane == 0)
-      for (int k = 0; k < n; ++k) {
-        const int p = piv[k];
-        if (p != k) { const double a = x[k]; x[k] = x[p]; x[p] = a; }
-      }
-    __syncwarp();
-    for (int i = 1; i < n; ++i) {
-      double acc = 0.0;
-      for (int j = lane; j < i; j += 32) acc += M[(size_t)i * n + j] * x[j];
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) x[i] -= acc;
-      __syncwarp();
-    }
-    for (int i = n - 1; i >= 0; --i) {
-      double acc = 0.0;
-      for (int j = i + 1 + lane; j < n; j += 32) acc += M[(size_t)i * n + j] * x[j];
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) x[i] = (x[i] - acc) / M[(size_t)i * n + i];
-      __syncwarp();
-    }
+    const int rc = band_factor(A, n, piv, threadIdx.x, guard);
+    if (threadIdx.x == 0) f_rc = rc;
   }
+  __syncthreads();
+  const int rc = f_rc;
+  __syncthreads();
+  return rc;
+}
+__device__ void blk_band_solve(const double* A, int n, const int* piv, double* x) {
+  if (threadIdx.x < 32) band_solve(A, n, piv, x, 1, threadIdx.x);
   __syncthreads();
 }
 
 struct CorridorWork {   // one path's scratch, carved from the resident block's slice
-  double *M0, *M, *R, *X, *RHS, *DX, *RD, *Arow, *mid, *lo, *hi, *V;
-  int *piv, *seg;
-  int n, nvar, mc;
+  double *A0, *A, *R, *X, *DX, *RD, *T1, *dt, *Arow, *mid, *lo, *hi, *V;
+  int *piv, *kind, *seg;   // kind[i]: coefficient index 8 s + d of band row i, or -1 for a constraint row
+  int n, nvar, mc, K, cont;
 };
 
 // One axis of the corridor QP by the whole block (see the header comment).  X (n) holds the equality-only solution [c; y]
 // on entry and the minimiser on return.  Returns (to every thread) 0 converged / 1 infeasible or not converged.
 __device__ int corridor_ipm(const CorridorWork& W, int ax, const int* rs /*shared: first row of each segment, [K+1]*/, double* s_red) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n = W.n, nvar = W.nvar, mc = W.mc, K = nvar / PL_NC;
+  const int n = W.n, mc = W.mc, K = W.K;
+  const BandLayout L(K, W.cont);
   double* x = W.X + (size_t)ax * n;
   double *su = W.V, *sl = su + CR_MAX_ROWS, *lu = sl + CR_MAX_ROWS, *ll = lu + CR_MAX_ROWS, *ru = ll + CR_MAX_ROWS,
          *rl = ru + CR_MAX_ROWS, *dsu = rl + CR_MAX_ROWS, *dsl = dsu + CR_MAX_ROWS, *dlu = dsl + CR_MAX_ROWS,
@@ -179,7 +115,7 @@ __device__ int corridor_ipm(const CorridorWork& W, int ax, const int* rs /*share
   BlkRed red{s_red};
   auto row_dot = [&](int j, const double* v) {   // [1 t .. t^7] . v_segment
     const double* a = W.Arow + 8 * (size_t)j;
-    const double* c = v + PL_NC * W.seg[j];
+    const double* c = v + L.var(W.seg[j], 0);   // a segment's coefficients are contiguous in band order
     double acc = 0.0;
     for (int d = 0; d < PL_NC; ++d) acc += a[d] * c[d];
     return acc;
@@ -199,8 +135,9 @@ __device__ int corridor_ipm(const CorridorWork& W, int ax, const int* rs /*share
     __syncthreads();
     for (int i = tid; i < n; i += PL_THREADS) {
       double v = -W.RD[i];
-      if (i < nvar) {
-        const int s = i / PL_NC, d = i - s * PL_NC;
+      const int q = W.kind[i];
+      if (q >= 0) {
+        const int s = q / PL_NC, d = q - s * PL_NC;
         double acc = 0.0;
         for (int j = rs[s]; j < rs[s + 1]; ++j) acc += W.Arow[8 * (size_t)j + d] * gv[j];
         v -= acc;
@@ -208,7 +145,7 @@ __device__ int corridor_ipm(const CorridorWork& W, int ax, const int* rs /*share
       W.DX[i] = v;
     }
     __syncthreads();
-    kkt_solve(W.M, n, W.piv, W.DX);
+    blk_band_solve(W.A, n, W.piv, W.DX);
     for (int j = tid; j < mc; j += PL_THREADS) {
       const double adc = row_dot(j, W.DX);
       const double a = -ru[j] - adc, b = rl[j] + adc;
@@ -233,33 +170,25 @@ __device__ int corridor_ipm(const CorridorWork& W, int ax, const int* rs /*share
   int status = 1;
   for (int it = 0; it < CR_IPM_MAX_IT; ++it) {
     // RD = K0 x - [0; b] (+ Ac'(lu - ll) on the coefficient rows): dual residual rd and primal residual rp; |Pc|_inf
-    double pcmax = 0.0;
-    for (int i = warp; i < n; i += PL_THREADS / 32) {
-      const double* row = W.M0 + (size_t)i * n;
-      double acc = 0.0, pc = 0.0;
-      for (int j = lane; j < n; j += 32) {
-        const double t = row[j] * x[j];
-        acc += t;
-        if (j < nvar) pc += t;
-      }
-      for (int o = 16; o > 0; o >>= 1) {
-        acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        pc += __shfl_xor_sync(0xffffffffu, pc, o);
-      }
-      if (i < nvar) pcmax = fmax(pcmax, fabs(pc));
-      if (lane == 0) W.RD[i] = i < nvar ? acc : acc - W.R[3 * i + ax];
-    }
-    __syncthreads();
-    double resmax = 0.0, comp = 0.0;
+    double pcmax = 0.0, resmax = 0.0, comp = 0.0;
     for (int i = tid; i < n; i += PL_THREADS) {
-      double v = W.RD[i];
-      if (i < nvar) {
-        const int s = i / PL_NC, d = i - s * PL_NC;
-        double acc = 0.0;
-        for (int j = rs[s]; j < rs[s + 1]; ++j) acc += W.Arow[8 * (size_t)j + d] * (lu[j] - ll[j]);
-        v += acc;
-        W.RD[i] = v;
+      const int j0 = i - BD_KL > 0 ? i - BD_KL : 0, j1 = i + BD_KL < n - 1 ? i + BD_KL : n - 1;   // K0 itself has bandwidth 13
+      double acc = 0.0;
+      for (int j = j0; j <= j1; ++j) acc += W.A0[bd_idx(i, j)] * x[j];
+      const int q = W.kind[i];
+      double v;
+      if (q >= 0) {
+        const int s = q / PL_NC, d = q - s * PL_NC, v0 = L.var(s, 0);
+        double pc = 0.0;
+        for (int e = 0; e < PL_NC; ++e) pc += W.A0[bd_idx(i, v0 + e)] * x[v0 + e];
+        pcmax = fmax(pcmax, fabs(pc));
+        double g = 0.0;
+        for (int j = rs[s]; j < rs[s + 1]; ++j) g += W.Arow[8 * (size_t)j + d] * (lu[j] - ll[j]);
+        v = acc + g;
+      } else {
+        v = acc - W.R[3 * i + ax];
       }
+      W.RD[i] = v;
       resmax = fmax(resmax, fabs(v));
     }
     for (int j = tid; j < mc; j += PL_THREADS) {
@@ -274,19 +203,30 @@ __device__ int corridor_ipm(const CorridorWork& W, int ax, const int* rs /*share
     const double mu = red.sum(comp) / (2.0 * mc);
     const double res = red.max(resmax);
     const double pcm = red.max(pcmax);
+#ifdef CR_DEBUG
+    if (tid == 0) printf("[ipm] ax %d it %d mu %.3e res %.3e pcm %.3e\n", ax, it, mu, res, pcm);
+#endif
     if (!(mu < 1e30) || !isfinite(res)) break;
     if (mu < CR_IPM_MU_TOL && res < CR_IPM_RES_TOL * (1.0 + pcm)) { status = 0; break; }
     // Newton matrix: K0 with Ac' S Ac added to the segments' 8 x 8 diagonal blocks
-    for (size_t e = tid; e < (size_t)n * n; e += PL_THREADS) W.M[e] = W.M0[e];
+    for (size_t e = tid; e < (size_t)n * BD_W; e += PL_THREADS) W.A[e] = W.A0[e];
     __syncthreads();
     for (int e = tid; e < K * PL_NC * PL_NC; e += PL_THREADS) {
       const int s = e / (PL_NC * PL_NC), q = e - s * PL_NC * PL_NC, d1 = q / PL_NC, d2 = q - d1 * PL_NC;
       double acc = 0.0;
       for (int j = rs[s]; j < rs[s + 1]; ++j) acc += sig[j] * W.Arow[8 * (size_t)j + d1] * W.Arow[8 * (size_t)j + d2];
-      W.M[(size_t)(s * PL_NC + d1) * n + (s * PL_NC + d2)] += acc;
+      W.A[bd_idx(L.var(s, d1), L.var(s, d2))] += acc;
     }
     __syncthreads();
-    if (kkt_factor(W.M, n, W.piv) != 0) break;
+#ifdef CR_DEBUG
+    {
+      double sm_ = 0.0;
+      for (int j = tid; j < mc; j += PL_THREADS) sm_ = fmax(sm_, sig[j]);
+      sm_ = red.max(sm_);
+      if (tid == 0) printf("      max sig %.3e\n", sm_);
+    }
+#endif
+    if (blk_band_factor(W.A, n, W.piv, true) != 0) break;
     // predictor
     for (int j = tid; j < mc; j += PL_THREADS) { rcu[j] = su[j] * lu[j]; rcl[j] = sl[j] * ll[j]; }
     __syncthreads();
@@ -306,9 +246,12 @@ __device__ int corridor_ipm(const CorridorWork& W, int ax, const int* rs /*share
     __syncthreads();
     newton();
     max_steps(ap, ad);
+#ifdef CR_DEBUG
+    if (tid == 0) printf("      sigma %.3e ap %.4f ad %.4f\n", sigma, ap, ad);
+#endif
     ap = fmin(0.995 * ap, 1.0);
     ad = fmin(0.995 * ad, 1.0);
-    for (int i = tid; i < n; i += PL_THREADS) x[i] += (i < nvar ? ap : ad) * W.DX[i];
+    for (int i = tid; i < n; i += PL_THREADS) x[i] += (W.kind[i] >= 0 ? ap : ad) * W.DX[i];
     for (int j = tid; j < mc; j += PL_THREADS) {
       su[j] += ap * dsu[j];
       sl[j] += ap * dsl[j];
@@ -321,18 +264,18 @@ __device__ int corridor_ipm(const CorridorWork& W, int ax, const int* rs /*share
   return status;
 }
 
-__global__ void __launch_bounds__(PL_THREADS) k_corridor_loop(CorridorArgs A, PolyMap map) {
+__global__ void __launch_bounds__(PL_THREADS) k_corridor_loop(CorridorArgs A, PolyMap map, DevMap dmap) {
   __shared__ int s_b, s_go;
   __shared__ double s_dt[PL_MAX_SEG + 1], s_r[PL_MAX_SEG + 1], s_red[PL_THREADS / 32];
   __shared__ int s_rs[PL_MAX_SEG + 2];
   __shared__ uint8_t s_seg[PL_MAX_SEG + 1];
   const int tid = threadIdx.x;
   double* base = A.scratch + (size_t)blockIdx.x * A.stride;
-  const size_t nm = (size_t)A.nmax;
+  const size_t nm = (size_t)band_order(A.kmax, 4);
   CorridorWork W;
-  W.M0 = base; W.M = W.M0 + nm * nm; W.R = W.M + nm * nm; W.X = W.R + 3 * nm; W.RHS = W.X + 3 * nm; W.DX = W.RHS + nm;
-  W.RD = W.DX + nm; W.piv = reinterpret_cast<int*>(W.RD + nm);
-  W.Arow = W.RD + 2 * nm; W.seg = reinterpret_cast<int*>(W.Arow + 8 * (size_t)CR_MAX_ROWS); W.mid = W.Arow + 9 * (size_t)CR_MAX_ROWS;
+  W.A0 = base; W.A = W.A0 + nm * BD_W; W.R = W.A + nm * BD_W; W.X = W.R + 3 * nm; W.DX = W.X + 3 * nm; W.RD = W.DX + nm;
+  W.piv = reinterpret_cast<int*>(W.RD + nm); W.kind = W.piv + nm; W.T1 = W.RD + 2 * nm; W.dt = W.RD + 3 * nm;
+  W.Arow = W.dt + A.kmax + 8; W.seg = reinterpret_cast<int*>(W.Arow + 8 * (size_t)CR_MAX_ROWS); W.mid = W.Arow + 9 * (size_t)CR_MAX_ROWS;
   W.lo = W.mid + 3 * (size_t)CR_MAX_ROWS; W.hi = W.lo + CR_MAX_ROWS; W.V = W.hi + CR_MAX_ROWS;
   for (;;) {
     __syncthreads();
@@ -349,14 +292,19 @@ __global__ void __launch_bounds__(PL_THREADS) k_corridor_loop(CorridorArgs A, Po
       if (tid == 0) A.valid[b] = 1;
       continue;
     }
-    int n = 0;
-    const int brc = poly_build_kkt(wp, nwp, A.bc ? A.bc + 12 * (size_t)b : nullptr, A.desired_vel, A.cont, times, W.M0, W.R, s_dt, &n);
-    if (brc != 0) {
-      if (tid == 0) A.status[3 * b] = A.status[3 * b + 1] = A.status[3 * b + 2] = brc;
+    if (K > PL_MAX_SEG) {
+      if (tid == 0) A.status[3 * b] = A.status[3 * b + 1] = A.status[3 * b + 2] = -2;
       continue;
     }
-    const int nvar = PL_NC * K;
-    W.n = n; W.nvar = nvar;
+    const BandLayout L(K, A.cont);
+    const int n = L.n, nvar = PL_NC * K;
+    W.n = n; W.nvar = nvar; W.K = K; W.cont = A.cont;
+    if (tid < 32) band_build(wp, nwp, A.bc ? A.bc + 12 * (size_t)b : nullptr, A.desired_vel, A.cont, times, W.A0, W.R, W.dt, tid);
+    for (int i = tid; i < n; i += PL_THREADS) W.kind[i] = -1;
+    __syncthreads();
+    for (int q = tid; q < nvar; q += PL_THREADS) W.kind[L.var(q / PL_NC, q % PL_NC)] = q;
+    for (int s = tid; s < K; s += PL_THREADS) s_dt[s] = W.dt[s];
+    __syncthreads();
     // ---- corridor rows (updateCorridorParam): per segment t = 0; t <= 1; t += 1 / ceil(duration * corridorRes)
     if (tid == 0) {
       int m = 0;
@@ -388,34 +336,39 @@ __global__ void __launch_bounds__(PL_THREADS) k_corridor_loop(CorridorArgs A, Po
       int bad = 0;
       for (int ax = 0; ax < 3; ++ax) {
         double* x = W.X + (size_t)ax * n;
-        // start point: K0^-1 [0; b]  (K0 is re-factorised per axis: the interior-point iterations overwrite M)
-        for (size_t e = tid; e < (size_t)n * n; e += PL_THREADS) W.M[e] = W.M0[e];
+        // start point: K0^-1 [0; b]  (K0 is re-factorised per axis: the interior-point iterations overwrite A)
+        for (size_t e = tid; e < (size_t)n * BD_W; e += PL_THREADS) W.A[e] = W.A0[e];
         for (int i = tid; i < n; i += PL_THREADS) x[i] = W.R[3 * i + ax];
         __syncthreads();
-        int st = kkt_factor(W.M, n, W.piv) != 0 ? -1 : 0;
+        int st = blk_band_factor(W.A, n, W.piv, false) != 0 ? -1 : 0;
         if (st == 0) {
-          kkt_solve(W.M, n, W.piv, x);
+          blk_band_solve(W.A, n, W.piv, x);
           for (int j = tid; j < mc; j += PL_THREADS) {
             const double r = s_r[W.seg[j]], m = W.mid[3 * (size_t)j + ax];
             W.lo[j] = m - r;
             W.hi[j] = m + r;
           }
           __syncthreads();
-          st = mc > 0 ? corridor_ipm(W, ax, s_rs, s_red) : 0;
+          st = (mc > 0 && !A.no_corridor) ? corridor_ipm(W, ax, s_rs, s_red) : 0;
         }
         if (tid == 0) A.status[3 * b + ax] = st;
         if (st != 0) bad = 1;
         // de-normalise: c_d /= dt^d (solveX..Z, polyTrajSolver.cpp:874-878)
         for (int q = tid; q < nvar; q += PL_THREADS) {
           const int s = q / PL_NC, d = q - s * PL_NC;
-          coef[(size_t)ax * nvar + q] = x[q] / pow(s_dt[s], (double)d);
+          coef[(size_t)ax * nvar + q] = x[L.var(s, d)] / pow(s_dt[s], (double)d);
         }
         __syncthreads();
       }
       ++it;
       if (A.solve_only || bad) break;
+      if (A.no_corridor) {   // polyTrajOccMap.cpp:370-374: no collision check in this mode
+        if (tid == 0) A.valid[b] = 1;
+        break;
+      }
       int ntraj = 0;
-      const int any = poly_check_one(map, wp, K, coef, times, A.t_acc, A.n_t_acc, A.box, A.map_res, s_seg, &ntraj, nullptr, nullptr, 0);
+      const int any = poly_check_one(map, wp, K, coef, times, A.t_acc, A.n_t_acc, A.box, A.map_res, s_seg, &ntraj, nullptr, nullptr, 0,
+                                     A.occmap ? &dmap : nullptr);
       if (tid == 0) {
         int go = 0;
         if (!any) A.valid[b] = 1;

@@ -5,15 +5,15 @@
 //
 //  k_minsnap_solve : the QP of polyTrajSolver (P: polyTrajSolver.cpp:241-271, equality rows :314-584, bounds
 //                    :587-813, time allocation :125-138, de-normalisation :870-879) solved EXACTLY through its
-//                    KKT system [P A^T; A 0][x; lambda] = [0; b] (the reference hands it to OSQP, eps 1e-3) by an
-//                    in-place LU with partial pivoting, one thread block per problem, the three axes share the
-//                    factorisation.  The matrix (<= 14K x 14K, K <= 63 segments) lives in HBM scratch owned by the
-//                    resident block; rows whose multiplier is exactly zero are skipped (the KKT is sparse).
+//                    KKT system [P A^T; A 0][x; lambda] = [0; b] (the reference hands it to OSQP, eps 1e-3): ordered
+//                    segment by segment the system is banded (half-bandwidth 13), and ONE WARP per problem runs a band
+//                    LU with partial pivoting (tp_band.cuh); the three axes share the factorisation.
 //  k_poly_check    : polyTrajSolver::getTrajectory (:1125-1137, accumulated t += delT, position = sum c_d pow(t,d))
 //                    + polyTrajOctomap::checkCollisionTraj / checkCollision / checkCollisionPoint
 //                    (polyTrajOctomap.cpp:634-656, 547-590): per sample a box of points, each "collision" when
 //                    outside the known bounding box, unknown, or occupied; colliding samples mark their segment.
 #pragma once
+#include "tp_band.cuh"
 
 #define PL_THREADS 128
 #define PL_DEG 7
@@ -70,199 +70,48 @@ struct PolySolveArgs {
   double* coef;           // out: problem b, axis a, segment s, power d at 24*(wp_off[b]-b) + a*8*K + 8*s + d
   double* times;          // out: [total waypoints] time knots
   int* status;            // out: 0 ok, -1 singular, -2 too many segments
-  double* scratch;        // [grid * (nmax*nmax + 3*nmax)]
-  int nmax;
+  double* scratch;        // [workers * stride]
+  size_t stride;          // doubles per worker: poly_scratch_doubles(longest path)
   int* queue;
 };
 
-// Time allocation + assembly of the equality-constrained KKT system of one path by the whole block:
-// M (n x n, n = 8 K + constraints) = [P A^T; A 0], R (n x 3) = [0; b] for the three axes, s_dt[K] = segment durations
-// (shared), times[nwp] = knots.  Returns (to every thread) 0, -2 too many segments, -3 fewer than two waypoints; *n_out = n.
-__device__ int poly_build_kkt(const double* wp, int nwp, const double* bc, double desired_vel, int cont, double* times, double* M,
-                              double* R, double* s_dt, int* n_out) {
-  const int tid = threadIdx.x;
-  const int K = nwp - 1;
-  if (K < 1 || K > PL_MAX_SEG) return K < 1 ? -3 : -2;
-  const int nvar = PL_NC * K;
-  const int ncon = (2 + 2 * (K - 1)) + 2 * (2 + (K - 1)) + (K - 1) * (cont - 2);
-  const int n = nvar + ncon;
-  *n_out = n;
-  // ---- time allocation (avgTimeAllocation): knots accumulate distance / desiredVel
-  if (tid == 0) {
-    double tt = 0.0;
-    times[0] = 0.0;
-    for (int i = 1; i < nwp; ++i) {
-      const double dx = wp[3 * i] - wp[3 * i - 3], dy = wp[3 * i + 1] - wp[3 * i - 2], dz = wp[3 * i + 2] - wp[3 * i - 1];
-      const double dur = sqrt(dx * dx + dy * dy + dz * dz) / desired_vel;
-      s_dt[i - 1] = dur;
-      tt += dur;
-      times[i] = tt;
-    }
-  }
-  __syncthreads();
-  for (size_t e = tid; e < (size_t)n * n; e += PL_THREADS) M[e] = 0.0;
-  for (int e = tid; e < 3 * n; e += PL_THREADS) R[e] = 0.0;
-  __syncthreads();
-  // ---- P: snap Gram matrix on normalised time (constructP)
-  for (int e = tid; e < K * 16; e += PL_THREADS) {
-    const int s = e / 16, i = 4 + (e % 16) / 4, j = 4 + (e % 4);
-    double f = 1.0;
-    for (int d = 0; d < 4; ++d) f *= (double)((i - d) * (j - d));
-    f /= (double)(i + j - 7);
-    M[(size_t)(s * PL_NC + i) * n + (s * PL_NC + j)] = f;
-  }
-  // ---- A (and A^T) + b: rows in the reference's order (constructA / constructBound)
-  if (tid == 0) {
-    int r = nvar;
-    auto put = [&](int row, int seg, double t1, int order, double scale, double sign) {
-      // derivative row of segment `seg` at normalised time 0 (t1 = 0) or 1: c_d * t^(d-order)
-      for (int d = order; d < PL_NC; ++d) {
-        double c = 1.0;
-        for (int k = 0; k < order; ++k) c *= (double)(d - k);
-        if (t1 == 0.0 && d != order) continue;
-        const double v = sign * c * scale;
-        const int col = seg * PL_NC + d;
-        M[(size_t)row * n + col] += v;
-        M[(size_t)col * n + row] += v;
-      }
-    };
-    auto rhs = [&](int row, double x, double y, double z) { R[3 * row] = x; R[3 * row + 1] = y; R[3 * row + 2] = z; };
-    put(r, 0, 0.0, 0, 1.0, 1.0); rhs(r, wp[0], wp[1], wp[2]); ++r;
-    put(r, K - 1, 1.0, 0, 1.0, 1.0); rhs(r, wp[3 * K], wp[3 * K + 1], wp[3 * K + 2]); ++r;
-    for (int i = 0; i < K - 1; ++i) { put(r, i, 1.0, 0, 1.0, 1.0); rhs(r, wp[3 * i + 3], wp[3 * i + 4], wp[3 * i + 5]); ++r; }
-    for (int i = 0; i < K - 1; ++i) { put(r, i, 1.0, 0, 1.0, 1.0); put(r, i + 1, 0.0, 0, 1.0, -1.0); ++r; }
-    for (int order = 1; order <= 2; ++order) {
-      put(r, 0, 0.0, order, 1.0, 1.0);
-      if (bc) rhs(r, bc[(order == 1 ? 0 : 6)], bc[(order == 1 ? 1 : 7)], bc[(order == 1 ? 2 : 8)]);
-      ++r;
-      put(r, K - 1, 1.0, order, 1.0, 1.0);
-      if (bc) rhs(r, bc[(order == 1 ? 3 : 9)], bc[(order == 1 ? 4 : 10)], bc[(order == 1 ? 5 : 11)]);
-      ++r;
-      for (int i = 0; i < K - 1; ++i) {
-        double sl = 1.0, sr = 1.0;
-        for (int k = 0; k < order; ++k) { sl *= s_dt[i + 1]; sr *= s_dt[i]; }
-        put(r, i, 1.0, order, sl, 1.0);
-        put(r, i + 1, 0.0, order, sr, -1.0);
-        ++r;
-      }
-    }
-    for (int order = 3; order <= cont; ++order)
-      for (int i = 0; i < K - 1; ++i) {
-        double sl = 1.0, sr = 1.0;
-        for (int k = 0; k < order; ++k) { sl *= s_dt[i + 1]; sr *= s_dt[i]; }
-        put(r, i, 1.0, order, sl, 1.0);
-        put(r, i + 1, 0.0, order, sr, -1.0);
-        ++r;
-      }
-  }
-  __syncthreads();
-  return 0;
-}
+// doubles of scratch one min-snap solve needs for paths of up to kmax segments (band matrix, right-hand sides, pivots, dt)
+__host__ __device__ inline size_t poly_scratch_doubles(int kmax) { return band_scratch_doubles(kmax, 4) + (size_t)kmax + 8; }
 
-// One min-snap solve by the whole block: waypoints wp[nwp] (+ boundary conditions bc[12] = v0, v1, a0, a1 or null) ->
-// knots times[nwp], coefficients coef[3][8 K] (axis-major).  M (n x n) and R (n x 3) are the block's scratch, n = 14 K.
-// Returns (to every thread) 0 ok, -1 singular KKT, -2 too many segments, -3 fewer than two waypoints.
+// One min-snap solve inside a block-per-path kernel: warp 0 runs the banded solver (tp_band.cuh), the block waits.
+// waypoints wp[nwp] (+ boundary conditions bc[12] = v0, v1, a0, a1 or null) -> knots times[nwp], coefficients coef[3][8 K]
+// (axis-major).  `scratch` = poly_scratch_doubles(K) doubles.  Returns (to every thread) 0 ok, -1 singular KKT, -2 too many
+// segments, -3 fewer than two waypoints.
 __device__ int poly_solve_one(const double* wp, int nwp, const double* bc, double desired_vel, int cont, double* coef,
-                              double* times, double* M, double* R) {
-  __shared__ int s_piv, s_bad;
-  __shared__ double s_red[PL_THREADS / 32];
-  __shared__ int s_redi[PL_THREADS / 32];
-  __shared__ double s_dt[PL_MAX_SEG + 1];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  {
-    int n = 0;
-    const int brc = poly_build_kkt(wp, nwp, bc, desired_vel, cont, times, M, R, s_dt, &n);
-    if (brc != 0) return brc;
+                              double* times, double* scratch) {
+  __shared__ int s_rc;
+  if (threadIdx.x < 32) {
     const int K = nwp - 1;
-    const int nvar = PL_NC * K;
-    if (tid == 0) s_bad = 0;
-    __syncthreads();
-    // ---- LU with partial pivoting, right-looking; rows with a zero multiplier are skipped
-    for (int k = 0; k < n; ++k) {
-      double best = -1.0;
-      int bi = k;
-      for (int i = k + tid; i < n; i += PL_THREADS) {
-        const double v = fabs(M[(size_t)i * n + k]);
-        if (v > best) { best = v; bi = i; }
-      }
-      for (int o = 16; o > 0; o >>= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-      }
-      if (lane == 0) { s_red[warp] = best; s_redi[warp] = bi; }
-      __syncthreads();
-      if (tid == 0) {
-        double bb = s_red[0];
-        int ii = s_redi[0];
-        for (int w = 1; w < PL_THREADS / 32; ++w)
-          if (s_red[w] > bb || (s_red[w] == bb && s_redi[w] < ii)) { bb = s_red[w]; ii = s_redi[w]; }
-        s_piv = ii;
-        if (!(bb > 1e-300)) s_bad = 1;
-      }
-      __syncthreads();
-      if (s_bad) break;
-      const int p = s_piv;
-      if (p != k) {
-        for (int j = k + tid; j < n; j += PL_THREADS) {
-          const double a = M[(size_t)k * n + j];
-          M[(size_t)k * n + j] = M[(size_t)p * n + j];
-          M[(size_t)p * n + j] = a;
-        }
-        if (tid < 3) { const double a = R[3 * k + tid]; R[3 * k + tid] = R[3 * p + tid]; R[3 * p + tid] = a; }
-        __syncthreads();
-      }
-      const double inv = 1.0 / M[(size_t)k * n + k];
-      for (int i = k + 1 + warp; i < n; i += PL_THREADS / 32) {
-        const double mik = M[(size_t)i * n + k];
-        if (mik == 0.0) continue;   // uniform per warp
-        const double l = mik * inv;
-        for (int j = k + 1 + lane; j < n; j += 32) M[(size_t)i * n + j] -= l * M[(size_t)k * n + j];
-        if (lane < 3) R[3 * i + lane] -= l * R[3 * k + lane];
-        if (lane == 0) M[(size_t)i * n + k] = 0.0;
-      }
-      __syncthreads();
-    }
-    if (s_bad) {
-      __syncthreads();
-      return -1;
-    }
-    // ---- back substitution, one warp per axis
-    if (warp < 3) {
-      for (int i = n - 1; i >= 0; --i) {
-        double acc = 0.0;
-        for (int j = i + 1 + lane; j < n; j += 32) acc += M[(size_t)i * n + j] * R[3 * j + warp];
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) R[3 * i + warp] = (R[3 * i + warp] - acc) / M[(size_t)i * n + i];
-        __syncwarp();
-      }
-    }
-    __syncthreads();
-    // ---- de-normalise: c_d /= dt^d (solveX..Z, :874-878)
-    for (int e = tid; e < 3 * nvar; e += PL_THREADS) {
-      const int a = e / nvar, q = e - a * nvar, s = q / PL_NC, d = q - s * PL_NC;
-      coef[(size_t)a * nvar + q] = R[3 * q + a] / pow(s_dt[s], (double)d);
-    }
-    __syncthreads();
+    double* dt = scratch + ((K >= 1 && K <= PL_MAX_SEG) ? band_scratch_doubles(K, cont) : 0);
+    const int rc = band_minsnap_solve(wp, nwp, bc, desired_vel, cont, coef, times, scratch, dt, PL_MAX_SEG, threadIdx.x);
+    if (threadIdx.x == 0) s_rc = rc;
   }
-  return 0;
+  __syncthreads();
+  const int rc = s_rc;
+  __syncthreads();
+  return rc;
 }
 
 __global__ void __launch_bounds__(PL_THREADS) k_minsnap_solve(PolySolveArgs A) {
-  __shared__ int s_b;
-  const int tid = threadIdx.x;
-  double* M = A.scratch + (size_t)blockIdx.x * ((size_t)A.nmax * A.nmax + 3 * (size_t)A.nmax);
-  double* R = M + (size_t)A.nmax * A.nmax;   // rhs, [n][3]
+  // ONE WARP per problem: four independent workers per block, problems from a shared queue, no block barrier
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* scratch = A.scratch + ((size_t)blockIdx.x * (PL_THREADS / 32) + warp) * A.stride;
   for (;;) {
-    __syncthreads();
-    if (tid == 0) s_b = atomicAdd(A.queue, 1);
-    __syncthreads();
-    const int b = s_b;
+    int b = 0;
+    if (lane == 0) b = atomicAdd(A.queue, 1);
+    b = __shfl_sync(0xffffffffu, b, 0);
     if (b >= A.B) break;
-    const int w0 = A.wp_off[b], nwp = A.wp_off[b + 1] - w0;
-    const int st = poly_solve_one(A.wp + 3 * (size_t)w0, nwp, A.bc ? A.bc + 12 * (size_t)b : nullptr, A.desired_vel, A.cont,
-                                  A.coef + (size_t)3 * PL_NC * (w0 - b), A.times + w0, M, R);
-    if (tid == 0) A.status[b] = st;
+    const int w0 = A.wp_off[b], nwp = A.wp_off[b + 1] - w0, K = nwp - 1;
+    double* dt = scratch + ((K >= 1 && K <= PL_MAX_SEG) ? band_scratch_doubles(K, A.cont) : 0);
+    const int st = band_minsnap_solve(A.wp + 3 * (size_t)w0, nwp, A.bc ? A.bc + 12 * (size_t)b : nullptr, A.desired_vel, A.cont,
+                                      A.coef + (size_t)3 * PL_NC * (w0 - b), A.times + w0, scratch, dt, PL_MAX_SEG, lane);
+    if (lane == 0) A.status[b] = st;
+    __syncwarp();
   }
 }
 
@@ -306,7 +155,7 @@ __device__ __forceinline__ void poly_eval(const double* coef, const double* knot
 // waypoint; marks seg_hit[K]; returns (to every thread) whether any sample collides; *n_traj = trajectory entries.
 __device__ int poly_check_one(const PolyMap& map, const double* wp, int K, const double* coef, const double* knots,
                               const double* t_acc, int n_t_acc, const double box[3], double map_res, uint8_t* seg_hit,
-                              int* n_traj, double* samples, uint8_t* sample_hit, int samp_cap) {
+                              int* n_traj, double* samples, uint8_t* sample_hit, int samp_cap, const DevMap* occmap = nullptr) {
   const int tid = threadIdx.x;
   const double T = knots[K];
   for (int i = tid; i < K; i += PL_THREADS) seg_hit[i] = 0;
@@ -323,7 +172,10 @@ __device__ int poly_check_one(const PolyMap& map, const double* wp, int K, const
     double p[3];
     if (s < npoly) poly_eval(coef, knots, K, t_acc[s], p);
     else { p[0] = wp[3 * (size_t)K]; p[1] = wp[3 * (size_t)K + 1]; p[2] = wp[3 * (size_t)K + 2]; }
-    const bool hit = pm_collision_box(map, p[0], p[1], p[2], box, map_res);
+    // polyTrajOctomap: the collision box on the 3-state grid; polyTrajOccMap (occmap != null): the sample itself, colliding when
+    // it is inflated-occupied AND unknown (polyTrajOccMap.cpp:531 — the reference's conjunction, preserved)
+    const bool hit = occmap ? (dm_inflated(*occmap, d3(p[0], p[1], p[2])) && dm_unknown(*occmap, d3(p[0], p[1], p[2])))
+                            : pm_collision_box(map, p[0], p[1], p[2], box, map_res);
     if (samples && s < samp_cap) {
       double* o = samples + (size_t)s * 3;
       o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
@@ -378,8 +230,8 @@ struct PolyLoopArgs {
   int* n_wp;               // [B]
   uint8_t* valid;          // [B]
   int* iters;              // [B]
-  double* scratch;         // [grid * (nmax*nmax + 3*nmax)]
-  int nmax;
+  double* scratch;         // [grid * stride]
+  size_t stride;           // doubles per block: poly_scratch_doubles(cap - 1)
   int* queue;
 };
 
@@ -387,8 +239,7 @@ __global__ void __launch_bounds__(PL_THREADS) k_polytraj_loop(PolyLoopArgs A, Po
   __shared__ int s_b, s_n, s_go, s_it;
   __shared__ uint8_t s_seg[PL_MAX_SEG + 1];
   const int tid = threadIdx.x;
-  double* M = A.scratch + (size_t)blockIdx.x * ((size_t)A.nmax * A.nmax + 3 * (size_t)A.nmax);
-  double* R = M + (size_t)A.nmax * A.nmax;
+  double* scratch = A.scratch + (size_t)blockIdx.x * A.stride;
   for (;;) {
     __syncthreads();
     if (tid == 0) s_b = atomicAdd(A.queue, 1);
@@ -409,7 +260,7 @@ __global__ void __launch_bounds__(PL_THREADS) k_polytraj_loop(PolyLoopArgs A, Po
     int it = 0;
     for (;;) {
       const int nwp = s_n, K = nwp - 1;
-      const int st = poly_solve_one(wp, nwp, A.bc ? A.bc + 12 * (size_t)b : nullptr, A.desired_vel, A.cont, coef, times, M, R);
+      const int st = poly_solve_one(wp, nwp, A.bc ? A.bc + 12 * (size_t)b : nullptr, A.desired_vel, A.cont, coef, times, scratch);
       ++it;
       int any = 1, ntraj = 0;
       if (st == 0) any = poly_check_one(map, wp, K, coef, times, A.t_acc, A.n_t_acc, A.box, A.map_res, s_seg, &ntraj, nullptr, nullptr, 0);

@@ -770,7 +770,39 @@ __global__ void __launch_bounds__(TP_LB_THREADS, MODE == 3 ? 4 : (MODE == 4 ? TP
   for (;;) {
     if (tid == 0) {
       int b = -1, cc = 0, res = resume;
-      if (pb_class < 0) {
+      if (resume == 2) {
+        // k_phase_a runs beside this kernel: prefer parked trajectories (phase B); with none ready, help with phase A (so
+        // the batch drains whoever is resident); leave once every class served is through phase A and its lists are empty
+        for (;;) {
+          bool all_final = true;
+          for (int c = my_class; c < 4 && b < 0; ++c) {
+            const int csize = cls_begin[c + 1] - cls_begin[c];
+            if (csize == 0) continue;
+            const bool final_pass = *((volatile int*)&park.started[c]) >= csize;   // read BEFORE the scan
+            for (int k = 0; k < TP_PARK_BUCKETS && b < 0; ++k) {
+              const int q = c * TP_PARK_BUCKETS + k;
+              for (;;) {
+                const int h = *((volatile int*)&park.head[q]);
+                if (h >= *((volatile int*)&park.tail[q])) break;
+                if (atomicCAS(&park.head[q], h, h + 1) != h) continue;
+                while ((b = *((volatile int*)&park.list[(size_t)q * park.stride + h])) < 0) __nanosleep(100);
+                break;
+              }
+            }
+            if (b >= 0) cc = c;
+            else if (!final_pass) all_final = false;
+          }
+          if (b >= 0) { __threadfence(); res = 1; break; }
+          for (int c = my_class; c < 4 && b < 0; ++c) {
+            if (cls_begin[c + 1] == cls_begin[c] || *((volatile int*)&cls_next[c]) >= cls_begin[c + 1] - cls_begin[c]) continue;
+            const int i = cls_begin[c] + atomicAdd(&cls_next[c], 1);
+            if (i < cls_begin[c + 1]) { b = order[i]; cc = c; }
+          }
+          if (b >= 0) { res = 0; break; }
+          if (all_final) break;
+          __nanosleep(500);
+        }
+      } else if (pb_class < 0) {
         for (int c = my_class; c < 4 && b < 0; ++c) {
           if (cls_begin[c + 1] == cls_begin[c]) continue;
           const int i = cls_begin[c] + atomicAdd(&cls_next[c], 1);
@@ -778,7 +810,7 @@ __global__ void __launch_bounds__(TP_LB_THREADS, MODE == 3 ? 4 : (MODE == 4 ? TP
         }
         if (b < 0 && park.thresh >= 0) pb_class = my_class;
       }
-      while (b < 0 && pb_class >= 0 && pb_class < 4) {
+      while (resume != 2 && b < 0 && pb_class >= 0 && pb_class < 4) {
         const int c = pb_class, csize = cls_begin[c + 1] - cls_begin[c];
         if (csize == 0) { ++pb_class; continue; }
         // buckets of the class, hardest-looking first; only slots that a parker has already reserved are claimed
@@ -829,6 +861,74 @@ __global__ void __launch_bounds__(TP_LB_THREADS, MODE == 3 ? 4 : (MODE == 4 ? TP
     atomicExch(&slot_flags[s_slot], 0);
   }
   if (MODE == 3) tm_block_free(tm_slot, tid);
+}
+
+// Phase A as its own launch (team-form batches): makePlan steps 1-3 (segments, A*, guide points) are serial work for ONE
+// warp, and a team block (128 threads, 45-96 KB of shared memory, 168 registers) keeps three warps at a barrier while its
+// serial warp searches — an SM ran three searches at a time (ncu on maze.bt: 75 % of all samples at that barrier).  This
+// kernel runs the same dev_plan_init with one warp per worker and only the A* scratch in shared memory (30 KB: seven
+// workers per SM), parks every trajectory that is still active into the SAME per-class lists k_solve's phase B drains
+// (k_solve runs beside it with resume = 2: phase B only), and exits as the queues run dry, which hands the SM over to the
+// team blocks.  Results do not depend on who ran phase A (same device functions, same order of operations per trajectory).
+__global__ void __launch_bounds__(32) k_phase_a(const __grid_constant__ BatchView bv, const __grid_constant__ VigoConst C,
+                                                const __grid_constant__ DevMap map, const __grid_constant__ AStarPools P,
+                                                const int* __restrict__ order, const int* __restrict__ cls_begin, int* cls_next,
+                                                int* slot_flags, long long* timeline, ParkQueue park) {
+  __shared__ PlanSmem S;
+  const int lane = threadIdx.x;
+  int s_slot = 0;
+  if (lane == 0) {
+    const int W_ = P.workers;
+    int sidx = (int)(((unsigned)(blockIdx.x + 7919) * 2654435761u) % (unsigned)W_);
+    while (atomicCAS(&slot_flags[sidx], 0, 1) != 0) sidx = sidx + 1 == W_ ? 0 : sidx + 1;
+    s_slot = sidx;
+  }
+  s_slot = __shfl_sync(0xffffffffu, s_slot, 0);
+  Worker W = make_worker(C, P, s_slot, lane, &S.as);
+  for (;;) {
+    int b = -1, cc = 0;
+    if (lane == 0)
+      for (int c = 0; c < 4 && b < 0; ++c) {
+        if (cls_begin[c + 1] == cls_begin[c]) continue;
+        const int i = cls_begin[c] + atomicAdd(&cls_next[c], 1);
+        if (i < cls_begin[c + 1]) { b = order[i]; cc = c; }
+      }
+    b = __shfl_sync(0xffffffffu, b, 0);
+    if (b < 0) break;
+    cc = __shfl_sync(0xffffffffu, cc, 0);
+    long long t_start = 0;
+    if (timeline && lane == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start));
+    TrajState& st = bv.st[b];
+    W.flood_trigger = TP_FLOOD_TRIGGER;
+    W.goal_unreachable = 0;
+    W.flood_wasted = 0;
+    dev_plan_init(bv, C, map, st, W, S, b, lane);
+    if (lane == 0) {
+      if (W.goal_unreachable) st.astar_unreach = 1;
+      if (timeline) timeline[4 * (size_t)b] = t_start;
+      if (st.status == TS_ACTIVE) {
+        const int np = park.score_mode == 0 ? st.n_pairs : (park.score_mode == 1 ? st.n_pairs * st.N / 32 : st.n_pairs * 8 + st.astar_expansions / 64);
+        const int bk = (st.astar_expansions >= 4 * park.thresh || st.astar_unreach) ? 0 : (st.astar_expansions >= park.thresh ? 1 :
+                       (np >= park.b[0] ? 2 : (np >= park.b[1] ? 3 : (np >= park.b[2] ? 4 : 5))));
+        const int q = cc * TP_PARK_BUCKETS + bk;
+        const int pos = atomicAdd(&park.tail[q], 1);
+        __threadfence();                                  // the trajectory's state is in HBM before its id shows up
+        atomicExch(&park.list[(size_t)q * park.stride + pos], b);
+      } else if (timeline) {   // finished in phase A (failed A*, already collision free, ...)
+        long long t_end;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_end));
+        timeline[4 * (size_t)b + 1] = t_end;
+        timeline[4 * (size_t)b + 3] = (long long)st.astar_expansions << 32;
+      }
+      __threadfence();
+      atomicAdd(&park.started[cc], 1);
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    __threadfence();
+    atomicExch(&slot_flags[s_slot], 0);
+  }
 }
 
 #include "tp_solve_warp.cuh"
@@ -2041,6 +2141,27 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
       }
     }
     CK(cudaEventRecord(e->ev_fork, s));
+    // team form: makePlan steps 1-3 as their own launch of light one-warp workers (k_phase_a) beside the team blocks, which
+    // then run phase B only (resume = 2).  Needs the park lists and enough A* node pools for both sets of workers.
+    bool hybrid = false;
+    {
+      static const int phase_a_env = getenv("TP_PHASE_A") ? atoi(getenv("TP_PHASE_A")) : 7;   // light workers per SM; 0 = off
+      int workers_total = 0;
+      for (int c = 0; c < 4; ++c) workers_total += grid_of[c];
+      const int ga = std::min(std::min(M, e->sm_count * phase_a_env), e->pools.workers - workers_total);
+      if (phase_a_env > 0 && mode == 4 && pq.thresh >= 0 && ga >= e->sm_count) {
+        hybrid = true;
+        cudaStream_t as = e->class_stream[7];
+        CK(cudaStreamWaitEvent(as, e->ev_fork, 0));
+        {
+          ProfScope ps(e, 3, as, ga);
+          k_phase_a<<<ga, 32, 0, as>>>(bs.bv, bs.C, e->dmap, e->pools, e->active[0].as<int>(), d_cb, d_cb + 5, e->pool_flags.as<int>(), tl, pq);
+        }
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(e->ev_join[7], as));
+        e->launches += 1;
+      }
+    }
     int used = 0;
     for (int c = 0; c < 4; ++c) {
       if (grid_of[c] == 0) continue;
@@ -2056,7 +2177,7 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
         else if (mode == 1) k_solve<1><<<grid, TP_LB_THREADS, smem[c], cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, d_cb, d_cb + 5, c, nmax[c], e->pool_flags.as<int>(), e->counters_ptr(), tl, resume, rounds, pq);
         else if (mode == 2) k_solve<2><<<grid, TP_LB_THREADS, smem[c], cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, d_cb, d_cb + 5, c, nmax[c], e->pool_flags.as<int>(), e->counters_ptr(), tl, resume, rounds, pq);
         else if (mode == 3) k_solve<3><<<grid, TP_LB_THREADS, smem[c], cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, d_cb, d_cb + 5, c, nmax[c], e->pool_flags.as<int>(), e->counters_ptr(), tl, resume, rounds, pq);
-        else if (mode == 4) k_solve<4><<<grid, TP_LB_THREADS, smem[c], cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, d_cb, d_cb + 5, c, nmax[c], e->pool_flags.as<int>(), e->counters_ptr(), tl, resume, rounds, pq);
+        else if (mode == 4) k_solve<4><<<grid, TP_LB_THREADS, smem[c], cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, d_cb, d_cb + 5, c, nmax[c], e->pool_flags.as<int>(), e->counters_ptr(), tl, hybrid ? 2 : resume, rounds, pq);
         else k_solve<0><<<grid, TP_LB_THREADS, smem[c], cs>>>(bs.bv, bs.C, e->dmap, e->pools, ord, d_cb, d_cb + 5, c, nmax[c], e->pool_flags.as<int>(), e->counters_ptr(), tl, resume, rounds, pq);
       }
       CK(cudaGetLastError());
@@ -2065,6 +2186,7 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
       ++used;
     }
     for (int i = 0; i < used; ++i) CK(cudaStreamWaitEvent(s, e->ev_join[i], 0));
+    if (hybrid) CK(cudaStreamWaitEvent(s, e->ev_join[7], 0));
     if (getenv("TP_PROF_DUMP")) fprintf(stderr, "[tp-mix] grids by class: %d %d %d %d; whole workers/SM by class: %d %d %d %d (smem %zu %zu %zu %zu B), class sizes %d %d %d %d\n",
                                         grid_of[0], grid_of[1], grid_of[2], grid_of[3], best[0], best[1], best[2], best[3], smem[0], smem[1], smem[2], smem[3], cb[1] - cb[0], cb[2] - cb[1],
                                         cb[3] - cb[2], cb[4] - cb[3]);
@@ -2403,14 +2525,15 @@ static int poly_check_params(const tp_engine* e, const tp_poly_params* p, bool n
 static int poly_solve_device(tp_engine* e, const tp_poly_params* p, int B, int max_k, const int* d_off, const double* d_wp,
                              const double* d_bc, double* d_coef, double* d_times, int* d_status, cudaStream_t s) {
   if (max_k > PL_MAX_SEG) { tp_set_error("a path has %d segments (max %d)", max_k, PL_MAX_SEG); return TP_ERR_CAPACITY; }
-  const int nmax = 14 * std::max(max_k, 1);
-  const int grid = std::min(B, e->sm_count * 8);
-  if (e->poly_scratch.ensure((size_t)grid * ((size_t)nmax * nmax + 3 * (size_t)nmax) * 8) != TP_OK || e->counters.ensure(64 * 4) != TP_OK)
+  // one WARP per problem (tp_band.cuh): four workers per block, up to 16 blocks per SM
+  const size_t stride = poly_scratch_doubles(std::max(max_k, 1));
+  const int grid = std::min((B + 3) / 4, e->sm_count * 16);
+  if (e->poly_scratch.ensure((size_t)grid * 4 * stride * 8) != TP_OK || e->counters.ensure(64 * 4) != TP_OK)
     return TP_ERR_CUDA;
   CK(cudaMemsetAsync(e->counters.p, 0, 64 * 4, s));
   PolySolveArgs A;
   A.B = B; A.wp_off = d_off; A.wp = d_wp; A.bc = d_bc; A.desired_vel = p->desired_vel; A.cont = p->cont;
-  A.coef = d_coef; A.times = d_times; A.status = d_status; A.scratch = e->poly_scratch.as<double>(); A.nmax = nmax;
+  A.coef = d_coef; A.times = d_times; A.status = d_status; A.scratch = e->poly_scratch.as<double>(); A.stride = stride;
   A.queue = e->counters.as<int>();
   {
     ProfScope ps(e, 6, s, B);
@@ -2560,13 +2683,13 @@ int tp_polytraj_make_plan_batch_bc(tp_engine_t* e, const tp_poly_params* p, int3
   rc = poly_ensure_tacc(e, p->delT, s);
   if (rc != TP_OK) return rc;
   const int total = wp_offsets[B];
-  const int nmax = 14 * (cap - 1);
+  const size_t pstride = poly_scratch_doubles(cap - 1);
   const int grid = std::min(B, e->sm_count * 8);
   const size_t st_wp = (size_t)B * cap * 3, st_coef = (size_t)B * 24 * (cap - 1), st_t = (size_t)B * cap;
   // staging rows | packed outputs (sized for wp_cap)
   const size_t packed = (size_t)wp_cap * 3 + (size_t)wp_cap * 24 + (size_t)wp_cap;
   if (e->off.ensure((size_t)(B + 1) * 4) != TP_OK || e->ctrl.ensure((size_t)std::max(total, 1) * 24) != TP_OK ||
-      e->poly_scratch.ensure((size_t)grid * ((size_t)nmax * nmax + 3 * (size_t)nmax) * 8) != TP_OK ||
+      e->poly_scratch.ensure((size_t)grid * pstride * 8) != TP_OK ||
       e->scratch_a.ensure((st_wp + st_coef + st_t) * 8) != TP_OK || e->scratch_b.ensure(packed * 8) != TP_OK ||
       e->scratch_c.ensure((size_t)B * 16 + 64) != TP_OK || e->counters.ensure(64 * 4) != TP_OK || (bc && e->dyn.ensure((size_t)B * 96) != TP_OK))
     return TP_ERR_CUDA;
@@ -2584,7 +2707,7 @@ int tp_polytraj_make_plan_batch_bc(tp_engine_t* e, const tp_poly_params* p, int3
   A.n_wp = e->scratch_c.as<int>(); A.iters = A.n_wp + B;
   int* d_off_out = A.iters + B;            // [B + 1]
   A.valid = reinterpret_cast<uint8_t*>(d_off_out + B + 1);
-  A.scratch = e->poly_scratch.as<double>(); A.nmax = nmax; A.queue = e->counters.as<int>();
+  A.scratch = e->poly_scratch.as<double>(); A.stride = pstride; A.queue = e->counters.as<int>();
   {
     ProfScope ps(e, 6, s, B);
     k_polytraj_loop<<<grid, PL_THREADS, 0, s>>>(A, make_polymap(e));
@@ -2614,12 +2737,12 @@ int tp_polytraj_make_plan_batch_bc(tp_engine_t* e, const tp_poly_params* p, int3
 // corridor-constrained min-snap: one QP solve with caller-supplied radii (solve_only) or the whole
 // makePlanCorridorConstraint loop
 static int corridor_run(tp_engine_t* e, const tp_poly_params* p, int32_t B, const int32_t* wp_offsets, const double* waypoints,
-                        const double* bc, const double* r_in, int solve_only, double init_r, double fs, double corridor_res,
+                        const double* bc, const double* r_in, int solve_only, int occmap, int no_corridor, double init_r, double fs, double corridor_res,
                         double* coef_out, double* times_out, uint8_t* valid_out, int32_t* iters_out, double* r_out, int32_t* status_out) {
   int rc = poly_check_params(e, p, !solve_only);
   if (rc != TP_OK) return rc;
   if (B <= 0 || !wp_offsets || !waypoints || !coef_out || !times_out) return TP_ERR_INVALID_ARG;
-  if (!(corridor_res > 0) || (!solve_only && (!(init_r > 0) || !(fs > 0) || !(fs < 1)))) {
+  if ((!no_corridor && !(corridor_res > 0)) || (!solve_only && (!(init_r > 0) || !(fs > 0) || !(fs < 1)))) {
     tp_set_error("corridor: need corridor_res > 0, initial radius > 0 and a shrinking factor in (0, 1)");
     return TP_ERR_INVALID_ARG;
   }
@@ -2637,8 +2760,7 @@ static int corridor_run(tp_engine_t* e, const tp_poly_params* p, int32_t B, cons
     if (rc != TP_OK) return rc;
   }
   const int total = wp_offsets[B], nseg = total - B;
-  const int nmax = 14 * kmax;
-  const size_t stride = corridor_scratch_doubles(nmax);
+  const size_t stride = corridor_scratch_doubles(kmax);
   const int grid = std::min(B, e->sm_count * 4);
   // scratch_b: coef | times | radii in | radii out      scratch_c: iters | status | valid
   const size_t nb = (size_t)24 * std::max(nseg, 1) + (size_t)total + 2 * (size_t)std::max(nseg, 1);
@@ -2653,7 +2775,7 @@ static int corridor_run(tp_engine_t* e, const tp_poly_params* p, int32_t B, cons
   CorridorArgs A;
   A.B = B; A.wp_off = e->off.as<int>(); A.wp = e->ctrl.as<double>(); A.bc = bc ? e->dyn.as<double>() : nullptr;
   A.desired_vel = p->desired_vel; A.cont = p->cont; A.max_iter = p->max_iter;
-  A.init_r = init_r; A.fs = fs; A.corridor_res = corridor_res; A.solve_only = solve_only;
+  A.init_r = init_r; A.fs = fs; A.corridor_res = corridor_res; A.solve_only = solve_only; A.occmap = occmap; A.no_corridor = no_corridor;
   A.t_acc = e->poly_tacc.as<double>(); A.n_t_acc = e->poly_tacc_n;
   for (int a = 0; a < 3; ++a) A.box[a] = p->box[a];
   A.map_res = p->map_res;
@@ -2666,11 +2788,11 @@ static int corridor_run(tp_engine_t* e, const tp_poly_params* p, int32_t B, cons
     A.r_in = d_rin;
   }
   A.iters = e->scratch_c.as<int>(); A.status = A.iters + B; A.valid = reinterpret_cast<uint8_t*>(A.status + 3 * B);
-  A.scratch = e->poly_scratch.as<double>(); A.stride = stride; A.nmax = nmax; A.queue = e->counters.as<int>();
+  A.scratch = e->poly_scratch.as<double>(); A.stride = stride; A.kmax = kmax; A.queue = e->counters.as<int>();
   CK(cudaMemsetAsync(A.coef, 0, (size_t)24 * std::max(nseg, 1) * 8, s));
   {
     ProfScope ps(e, 6, s, B);
-    k_corridor_loop<<<grid, PL_THREADS, 0, s>>>(A, solve_only && !e->has_map ? PolyMap{} : make_polymap(e));
+    k_corridor_loop<<<grid, PL_THREADS, 0, s>>>(A, solve_only && !e->has_map ? PolyMap{} : make_polymap(e), e->dmap);
   }
   e->launches += 1;
   CK(cudaGetLastError());
@@ -2688,7 +2810,7 @@ extern "C" int tp_corridor_solve_batch(tp_engine_t* e, const tp_poly_params* p, 
                                        const double* bc, const double* corridor_size, double corridor_res, double* coef, double* times,
                                        int32_t* status) {
   if (!corridor_size || !status) return TP_ERR_INVALID_ARG;
-  return corridor_run(e, p, B, wp_offsets, waypoints, bc, corridor_size, 1, 0.0, 0.0, corridor_res, coef, times, nullptr, nullptr, nullptr, status);
+  return corridor_run(e, p, B, wp_offsets, waypoints, bc, corridor_size, 1, 0, 0, 0.0, 0.0, corridor_res, coef, times, nullptr, nullptr, nullptr, status);
 }
 
 extern "C" int tp_polytraj_corridor_plan_batch(tp_engine_t* e, const tp_poly_params* p, int32_t B, const int32_t* wp_offsets,
@@ -2696,6 +2818,16 @@ extern "C" int tp_polytraj_corridor_plan_batch(tp_engine_t* e, const tp_poly_par
                                                double* coef_out, double* times_out, uint8_t* valid_out, int32_t* iters_out,
                                                double* r_out, int32_t* status_out) {
   if (!valid_out || !iters_out) return TP_ERR_INVALID_ARG;
-  return corridor_run(e, p, B, wp_offsets, waypoints, bc, nullptr, 0, init_r, fs, corridor_res, coef_out, times_out, valid_out, iters_out,
+  return corridor_run(e, p, B, wp_offsets, waypoints, bc, nullptr, 0, 0, 0, init_r, fs, corridor_res, coef_out, times_out, valid_out, iters_out,
                       r_out, status_out);
+}
+
+extern "C" int tp_polytraj_occmap_plan_batch(tp_engine_t* e, const tp_poly_params* p, int32_t B, const int32_t* wp_offsets,
+                                             const double* waypoints, const double* bc, int32_t corridor_constraint, double init_r, double fs,
+                                             double corridor_res, double* coef_out, double* times_out, uint8_t* valid_out, int32_t* iters_out,
+                                             double* r_out, int32_t* status_out) {
+  if (!valid_out || !iters_out) return TP_ERR_INVALID_ARG;
+  if (!corridor_constraint) { init_r = 1.0; fs = 0.5; }   // unused in that mode
+  return corridor_run(e, p, B, wp_offsets, waypoints, bc, nullptr, 0, 1, corridor_constraint ? 0 : 1, init_r, fs, corridor_res, coef_out, times_out,
+                      valid_out, iters_out, r_out, status_out);
 }
