@@ -253,7 +253,11 @@ int tp_vigo_init_guides_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B
  * and parameters: findCollisionSeg -> A* detours -> guide points -> [L-BFGS -> collision check ->
  * re-guide / weight doubling]* -> linear time re-parameterisation.  ctrl_in / ctrl_out may alias.
  * dyn_* (may be NULL / 0): dynamic obstacles shared by the whole batch
- * (bsplineTraj::updateDynamicObstacles, bsplineTraj.cpp:326-330). */
+ * (bsplineTraj::updateDynamicObstacles, bsplineTraj.cpp:326-330).
+ * mem = TP_MEM_DEVICE: offsets / ctrl_in / ctrl_out / results are device pointers (dyn_* stay host pointers).  NOTED
+ * EXCEPTION to "returns without synchronising": the call synchronises `stream` twice while it sets the batch up (it reads
+ * the offsets back to size the shared-memory classes, and one 4-byte key per trajectory to order the class queues); the
+ * solve kernels themselves are only enqueued, results are complete when `stream` has drained. */
 int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, const int32_t* offsets,
                             const double* ctrl_in, double* ctrl_out, tp_vigo_result* results, int32_t n_dyn,
                             const double* dyn_pos, const double* dyn_vel, const double* dyn_size, int mem, void* stream);

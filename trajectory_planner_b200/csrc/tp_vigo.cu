@@ -37,7 +37,8 @@
 __device__ __forceinline__ unsigned dq_flag(const DevMap& map, const D3& p, int unknown) {
   return unknown ? (dm_unknown(map, p) ? 1u : 0u) : (dm_inflated(map, p) ? 1u : 0u);
 }
-__global__ void __launch_bounds__(256) k_query_points(DevMap map, long n, const double* __restrict__ xyz, uint8_t* __restrict__ out, int unknown) {
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) k_query_points(DevMap map, long n, const double* __restrict__ xyz, uint8_t* __restrict__ out, int unknown) {
   const long stride = (long)gridDim.x * blockDim.x;
   const long nquad = n >> 2;
   const bool aligned = ((reinterpret_cast<uintptr_t>(xyz) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 3) == 0);
@@ -46,9 +47,31 @@ __global__ void __launch_bounds__(256) k_query_points(DevMap map, long n, const 
     for (long j = blockIdx.x * (long)blockDim.x + threadIdx.x; j < nquad; j += stride) {
       const double2 a = __ldcs(v + 6 * j), b = __ldcs(v + 6 * j + 1), c = __ldcs(v + 6 * j + 2), d = __ldcs(v + 6 * j + 3),
                     e = __ldcs(v + 6 * j + 4), f = __ldcs(v + 6 * j + 5);
-      const unsigned h0 = dq_flag(map, d3(a.x, a.y, b.x), unknown), h1 = dq_flag(map, d3(b.y, c.x, c.y), unknown),
-                     h2 = dq_flag(map, d3(d.x, d.y, e.x), unknown), h3 = dq_flag(map, d3(e.y, f.x, f.y), unknown);
-      __stcs(reinterpret_cast<unsigned*>(out) + j, h0 | (h1 << 8) | (h2 << 16) | (h3 << 24));
+      // the four cell addresses first, then the four map gathers back to back (one L2 round trip per iteration instead of
+      // four dependent ones), then the flags; a point outside the grid reads word 0 and is forced to "occupied / unknown"
+      const double px[4] = {a.x, b.y, d.x, e.y}, py[4] = {a.y, c.x, d.y, f.x}, pz[4] = {b.x, c.y, e.x, f.y};
+      size_t w[4];
+      int bit[4];
+      bool in[4];
+      const uint32_t* __restrict__ grid = unknown ? map.known : map.inflated;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        int ix, iy, iz;
+        in[q] = dm_index(map, px[q], py[q], pz[q], ix, iy, iz);
+        w[q] = in[q] ? ((size_t)ix * map.dim[1] + iy) * map.wz + (iz >> 5) : 0;
+        bit[q] = in[q] ? (iz & 31) : 0;
+      }
+      uint32_t word[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) word[q] = __ldg(grid + w[q]);
+      unsigned h = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const unsigned set = (word[q] >> bit[q]) & 1u;
+        const unsigned flag = in[q] ? (unknown ? (set ^ 1u) : set) : 1u;
+        h |= flag << (8 * q);
+      }
+      __stcs(reinterpret_cast<unsigned*>(out) + j, h);
     }
   }
   // the last n % 4 queries, or everything when the buffers are not aligned
@@ -1606,11 +1629,16 @@ static int query_common(tp_engine_t* e, int64_t n, const double* a, const double
   const int threads = 256;
   // point queries: four per thread and iteration, a grid of whole waves (8 blocks of 256 threads fit an SM)
   const long work = kind == 2 ? n : (n + 3) / 4;
-  const long blocks = std::min<long>((work + threads - 1) / threads, (long)e->sm_count * 8);
+  // resident blocks per SM the point-query kernel is compiled for (registers: 4 -> 62, 6 -> 40, 8 -> 32 with a small spill);
+  // the grid is exactly one resident wave of the grid-stride loop
+  static const int minb = getenv("TP_QUERY_MINB") ? atoi(getenv("TP_QUERY_MINB")) : 4;
+  const long blocks = std::min<long>((work + threads - 1) / threads, (long)e->sm_count * (kind == 2 ? 8 : (minb >= 8 ? 8 : (minb >= 6 ? 6 : 4))));
   {
     ProfScope ps(e, 5, s);
     if (kind == 2) k_query_lines<<<(int)blocks, threads, 0, s>>>(e->dmap, (long)n, da, db, dout);
-    else k_query_points<<<(int)blocks, threads, 0, s>>>(e->dmap, (long)n, da, dout, kind);
+    else if (minb >= 8) k_query_points<8><<<(int)blocks, threads, 0, s>>>(e->dmap, (long)n, da, dout, kind);
+    else if (minb >= 6) k_query_points<6><<<(int)blocks, threads, 0, s>>>(e->dmap, (long)n, da, dout, kind);
+    else k_query_points<4><<<(int)blocks, threads, 0, s>>>(e->dmap, (long)n, da, dout, kind);
   }
   e->query_points += (double)n;
   e->launches += 1;
