@@ -560,6 +560,13 @@ struct ParkQueue {
   int thresh;      // A* expansions of makePlan steps 1-3 from which a trajectory counts as a hard start; < 0: parking disabled
   int score_mode;  // difficulty score of a parked trajectory: 0 guide pairs, 1 pairs x N / 32, 2 pairs x 8 + expansions / 64
   int b[3];        // bucket bounds on the score (descending)
+  // time slicing (k_phase_a + k_solve<4>, resume = 2): a trajectory's FIRST turn is `slice` optimise / check / re-guide
+  // rounds; if still active it goes to the back of its class's ring and its next turn runs to the end
+  int* ring;       // [4][stride]  ids waiting for their next turn (-1 = empty slot)
+  int* rtail;      // [4]  ring slots handed out
+  int* rhead;      // [4]  ring slots claimed
+  int* remaining;  // [4]  trajectories of the class that are not finished yet
+  int slice;       // rounds per turn (<= 0: run to the end)
 };
 
 struct SolveLayout {
@@ -639,6 +646,9 @@ __device__ __forceinline__ int solve_one(const BatchView& bv, const VigoConst& C
   }
   double fl = 0.0, its = 0.0, evs = 0.0, smp = 0.0;
   int rounds_done = 0;
+  // time slicing: a NEGATIVE round limit -r means "the first r rounds of this trajectory only" — the first turn is short
+  // (most trajectories finish in it; the survivors reveal themselves early), every later turn runs to the end
+  if (rounds_this_pass < 0) rounds_this_pass = st.lbfgs_runs < -rounds_this_pass ? -rounds_this_pass - st.lbfgs_runs : 0x7fffffff;
 #ifdef TP_LBFGS_TIMING
   long long ph[4] = {0, 0, 0, 0}, pt0 = clock64(), pt1;
   const long long pstart = pinit0;
@@ -747,8 +757,9 @@ __device__ __forceinline__ int solve_one(const BatchView& bv, const VigoConst& C
       timeline[4 * (size_t)b + 3] = (long long)st.lbfgs_iters | ((long long)st.astar_expansions << 32);
     }
   }
+  const int unfinished = st.status == TS_ACTIVE;   // the pass ended at its round limit (time slicing / two-pass scheduling)
   __syncthreads();
-  return 0;
+  return unfinished ? 2 : 0;
 }
 
 // Persistent workers: one launch per size class; a worker of class c owns shared memory for that class's longest
@@ -794,15 +805,16 @@ __global__ void __launch_bounds__(TP_LB_THREADS, MODE == 3 ? 4 : (MODE == 4 ? TP
     if (tid == 0) {
       int b = -1, cc = 0, res = resume;
       if (resume == 2) {
-        // k_phase_a runs beside this kernel: prefer parked trajectories (phase B); with none ready, help with phase A (so
-        // the batch drains whoever is resident); leave once every class served is through phase A and its lists are empty
+        // k_phase_a runs beside this kernel: prefer parked trajectories (phase B: first the ones that have not started,
+        // hardest-looking first, then the ring of those waiting for their next turn); with none ready, help with phase A (so
+        // the batch drains whoever is resident); leave once no trajectory of the classes served is unfinished
         for (;;) {
-          bool all_final = true;
+          bool all_done = true;
           for (int c = my_class; c < 4 && b < 0; ++c) {
             const int csize = cls_begin[c + 1] - cls_begin[c];
             if (csize == 0) continue;
-            const bool final_pass = *((volatile int*)&park.started[c]) >= csize;   // read BEFORE the scan
-            for (int k = 0; k < TP_PARK_BUCKETS && b < 0; ++k) {
+            const int rem = *((volatile int*)&park.remaining[c]);   // read BEFORE the scans: 0 = nothing can show up any more
+            for (int k = 0; k < TP_PARK_BUCKETS && b < 0; ++k) {   // not started yet, hardest-looking first
               const int q = c * TP_PARK_BUCKETS + k;
               for (;;) {
                 const int h = *((volatile int*)&park.head[q]);
@@ -812,8 +824,15 @@ __global__ void __launch_bounds__(TP_LB_THREADS, MODE == 3 ? 4 : (MODE == 4 ? TP
                 break;
               }
             }
+            while (b < 0) {   // next turn of a trajectory that has had one (round robin)
+              const int h = *((volatile int*)&park.rhead[c]);
+              if (h >= *((volatile int*)&park.rtail[c])) break;
+              if (atomicCAS(&park.rhead[c], h, h + 1) != h) continue;
+              int* slot = &park.ring[(size_t)c * park.stride + (h % park.stride)];
+              while ((b = atomicExch(slot, -1)) < 0) __nanosleep(100);
+            }
             if (b >= 0) cc = c;
-            else if (!final_pass) all_final = false;
+            else if (rem > 0) all_done = false;
           }
           if (b >= 0) { __threadfence(); res = 1; break; }
           for (int c = my_class; c < 4 && b < 0; ++c) {
@@ -822,7 +841,7 @@ __global__ void __launch_bounds__(TP_LB_THREADS, MODE == 3 ? 4 : (MODE == 4 ? TP
             if (i < cls_begin[c + 1]) { b = order[i]; cc = c; }
           }
           if (b >= 0) { res = 0; break; }
-          if (all_final) break;
+          if (all_done) break;
           __nanosleep(500);
         }
       } else if (pb_class < 0) {
@@ -859,11 +878,23 @@ __global__ void __launch_bounds__(TP_LB_THREADS, MODE == 3 ? 4 : (MODE == 4 ? TP
     const int b = pick[0];
     if (b < 0) break;
     const int res = pick[3] >> 8;
-    const int parked = solve_one<MODE>(bv, C, map, P, b, class_max_n, s_slot, sw, tbase, counters, timeline, res, rounds_this_pass,
-                                       res ? -1 : park.thresh, sm);
+    const int parked = solve_one<MODE>(bv, C, map, P, b, class_max_n, s_slot, sw, tbase, counters, timeline, res,
+                                       (resume == 2 && res && park.slice > 0) ? -park.slice : rounds_this_pass, res ? -1 : park.thresh, sm);
+    if (resume == 2 && tid == 0 && parked != 1) {
+      const int cc = pick[3] & 255;
+      if (parked == 2) {   // still active after its turn: to the back of the class's ring
+        const int pos = atomicAdd(&park.rtail[cc], 1);
+        int* slot = &park.ring[(size_t)cc * park.stride + (pos % park.stride)];
+        __threadfence();                                  // the trajectory's state is in HBM before its id shows up
+        while (atomicCAS(slot, -1, b) != -1) __nanosleep(100);
+      } else {
+        __threadfence();
+        atomicSub(&park.remaining[cc], 1);
+      }
+    }
     if (park.thresh >= 0 && !res && tid == 0) {
       const int cc = pick[3] & 255;
-      if (parked) {
+      if (parked == 1) {
         // bucket by the guide pairs the first searches produced (the best cheap predictor of the remaining work)
         const TrajState* ps = reinterpret_cast<const TrajState*>(sm + SL.st);
         const int np = park.score_mode == 0 ? ps->n_pairs : (park.score_mode == 1 ? ps->n_pairs * ps->N / 32 : ps->n_pairs * 8 + ps->astar_expansions / 64);
@@ -937,11 +968,15 @@ __global__ void __launch_bounds__(32) k_phase_a(const __grid_constant__ BatchVie
         const int pos = atomicAdd(&park.tail[q], 1);
         __threadfence();                                  // the trajectory's state is in HBM before its id shows up
         atomicExch(&park.list[(size_t)q * park.stride + pos], b);
-      } else if (timeline) {   // finished in phase A (failed A*, already collision free, ...)
-        long long t_end;
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_end));
-        timeline[4 * (size_t)b + 1] = t_end;
-        timeline[4 * (size_t)b + 3] = (long long)st.astar_expansions << 32;
+      } else {   // finished in phase A (failed A*, already collision free, ...)
+        if (timeline) {
+          long long t_end;
+          asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_end));
+          timeline[4 * (size_t)b + 1] = t_end;
+          timeline[4 * (size_t)b + 3] = (long long)st.astar_expansions << 32;
+        }
+        __threadfence();
+        atomicSub(&park.remaining[cc], 1);
       }
       __threadfence();
       atomicAdd(&park.started[cc], 1);
@@ -2135,14 +2170,15 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
       }
     }
     if (e->stage_busy) CK(cudaEventSynchronize(e->ev_stage));   // the previous copy out of the staging buffer
-    if (ensure_stage(e, (size_t)M * 4 + 64) != TP_OK) return TP_ERR_CUDA;
+    if (ensure_stage(e, (size_t)M * 4 + 128) != TP_OK) return TP_ERR_CUDA;
     memcpy(e->h_stage, ids.data(), (size_t)M * 4);
     int* h_cb = reinterpret_cast<int*>(static_cast<char*>(e->h_stage) + (size_t)M * 4);
     for (int c = 0; c < 5; ++c) h_cb[c] = cb[c];
     for (int c = 0; c < 4; ++c) h_cb[5 + c] = 0;
-    int* d_cb = e->counters.as<int>() + 16;   // [16..20] class ranges, [21..24] cursors
+    for (int c = 0; c < 4; ++c) h_cb[9 + c] = cb[c + 1] - cb[c];
+    int* d_cb = e->counters.as<int>() + 16;   // [16..20] class ranges, [21..24] cursors, [25..28] unfinished trajectories per class
     CK(cudaMemcpyAsync(e->active[0].p, e->h_stage, (size_t)M * 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(d_cb, h_cb, 9 * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_cb, h_cb, 13 * 4, cudaMemcpyHostToDevice, s));
     CK(cudaEventRecord(e->ev_stage, s));
     e->stage_busy = true;
     // parking (k_solve phases A / B): only when the batch outnumbers the resident workers — otherwise every trajectory
@@ -2150,17 +2186,22 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
     ParkQueue pq;
     pq.list = nullptr; pq.tail = pq.head = pq.started = nullptr; pq.stride = M; pq.thresh = -1;
     pq.score_mode = 0; pq.b[0] = 16; pq.b[1] = 8; pq.b[2] = 2;
+    pq.ring = nullptr; pq.rtail = pq.rhead = nullptr; pq.remaining = d_cb + 9; pq.slice = 0;
     {
       static const int park_env = getenv("TP_PARK_THRESH") ? atoi(getenv("TP_PARK_THRESH")) : 1500;
       int workers_total = 0;
       for (int c = 0; c < 4; ++c) workers_total += grid_of[c];
       if (park_env >= 0 && !resume && rounds == 0x7fffffff && M > workers_total) {
         const int nq = 4 * TP_PARK_BUCKETS;
-        if (e->parkq.ensure(((size_t)nq * M + 2 * nq + 16) * 4) != TP_OK) return TP_ERR_CUDA;
+        if (e->parkq.ensure(((size_t)(nq + 4) * M + 2 * nq + 16) * 4) != TP_OK) return TP_ERR_CUDA;
         int* base = e->parkq.as<int>();
         CK(cudaMemsetAsync(base, 0, (size_t)(2 * nq + 16) * 4, s));
-        CK(cudaMemsetAsync(base + 2 * nq + 16, 0xFF, (size_t)nq * M * 4, s));
+        CK(cudaMemsetAsync(base + 2 * nq + 16, 0xFF, (size_t)(nq + 4) * M * 4, s));
         pq.tail = base; pq.head = base + nq; pq.started = base + 2 * nq; pq.list = base + 2 * nq + 16;
+        pq.rtail = pq.started + 4; pq.rhead = pq.started + 8; pq.ring = pq.list + (size_t)nq * M;
+        // rounds of a trajectory's first turn (team form with k_phase_a; 0 = every trajectory runs to its end once started)
+        static const int slice_env = getenv("TP_SLICE_ROUNDS") ? atoi(getenv("TP_SLICE_ROUNDS")) : 0;   // measured: 1..3 lengthen the batch by 5-10 % (profiles/r02_summary.md)
+        pq.slice = slice_env;
         pq.thresh = park_env;
         pq.score_mode = getenv("TP_PARK_SCORE") ? atoi(getenv("TP_PARK_SCORE")) : 0;
         pq.b[0] = getenv("TP_PARK_B0") ? atoi(getenv("TP_PARK_B0")) : 16;
