@@ -1,8 +1,8 @@
 import os, sys, numpy as np
-sys.path.insert(0,'/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import trajectory_planner_b200 as tp
 name = os.environ.get("PROBE_MAP", "maze"); B = int(os.environ.get("PROBE_B", "4096"))
-m = tp.OccMap.from_tpm('/root/repo/data/maps/%s.tpm' % name); info = m.info()
+m = tp.OccMap.from_tpm(os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), 'data', 'maps', '%s.tpm' % name)); info = m.info()
 e = tp.Engine(0); e.set_map(m); p = tp.default_params()
 inf = m.grid("inflated"); kz = int(np.floor((1.0 - info["origin"][2]) / info["res"]))
 free = np.argwhere(inf[:, :, kz] == 0); rng = np.random.default_rng(20261018); org, res = np.array(info["origin"]), info["res"]
