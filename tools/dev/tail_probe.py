@@ -10,13 +10,16 @@ os.environ["TP_TIMELINE"] = "/tmp/tl.bin"
 out, r = eng.make_plan_batch(p, offsets, ctrl)
 tl = np.fromfile("/tmp/tl.bin", dtype=np.int64).reshape(-1, 4)
 t0 = tl[:, 0].min(); st = (tl[:, 0] - t0) / 1e6; en = (tl[:, 1] - t0) / 1e6
+sb = np.where(tl[:, 2] > 1000000, (tl[:, 2] - t0) / 1e6, st)   # phase-B start of resumed trajectories
 N = np.diff(offsets)
 print("makespan %.1f ms" % en.max())
 act = [(en > t).sum() for t in np.arange(0, en.max(), 4.0)]
 print("active trajectories (not finished) every 4 ms:", act)
 for i in np.argsort(-en)[:12]:
-    print("traj %d N %d phaseA-start %.1f end %.1f status %d iters %d evals %d exp %d searches %d rounds %d fail %d" % (i, N[i], st[i], en[i], r['status'][i], r['lbfgs_iters'][i], r['lbfgs_evals'][i], r['astar_expansions'][i], r['astar_searches'][i], r['outer_rounds'][i], r['fail_count'][i]))
+    print("traj %d N %d phaseA-start %.1f phaseB-start %.1f busy %.1f end %.1f pairs %d status %d iters %d evals %d exp %d searches %d rounds %d fail %d" % (i, N[i], st[i], sb[i], en[i] - sb[i], en[i], r['n_guide_pairs'][i], r['status'][i], r['lbfgs_iters'][i], r['lbfgs_evals'][i], r['astar_expansions'][i], r['astar_searches'][i], r['outer_rounds'][i], r['fail_count'][i]))
 work = r['lbfgs_evals'] * N
 print("corr(end time, evals*N) among last 5%:", np.corrcoef(en[np.argsort(-en)[:200]], work[np.argsort(-en)[:200]])[0, 1])
 top = np.argsort(-work)[:12]
+long_ = np.argsort(-(en - sb))[:15]
+print("longest phase B turns:", [(int(i), int(N[i]), round(float(sb[i]), 1), round(float(en[i] - sb[i]), 1), int(r['n_guide_pairs'][i]), int(r['status'][i])) for i in long_])
 print("largest evals*N:", [(int(i), int(N[i]), int(r['lbfgs_evals'][i]), round(float(en[i]), 1)) for i in top])

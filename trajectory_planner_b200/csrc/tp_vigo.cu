@@ -566,7 +566,8 @@ struct ParkQueue {
   int* rtail;      // [4]  ring slots handed out
   int* rhead;      // [4]  ring slots claimed
   int* remaining;  // [4]  trajectories of the class that are not finished yet
-  int slice;       // rounds per turn (<= 0: run to the end)
+  int slice;       // rounds of the first turn (<= 0: run to the end)
+  int rev;         // one worker in `rev` scans the buckets easiest-first (0 = none)
 };
 
 struct SolveLayout {
@@ -753,7 +754,7 @@ __device__ __forceinline__ int solve_one(const BatchView& bv, const VigoConst& C
       asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
       if (!resume) timeline[4 * (size_t)b] = t_start;
       timeline[4 * (size_t)b + 1] = t_end;
-      timeline[4 * (size_t)b + 2] = (long long)smid;
+      timeline[4 * (size_t)b + 2] = resume ? t_start : (long long)smid;   // resumed: when its phase B turn began
       timeline[4 * (size_t)b + 3] = (long long)st.lbfgs_iters | ((long long)st.astar_expansions << 32);
     }
   }
@@ -801,6 +802,7 @@ __global__ void __launch_bounds__(TP_LB_THREADS, MODE == 3 ? 4 : (MODE == 4 ? TP
   // ones, hardest bucket first.  Only slots a parker has reserved are claimed; once every trajectory of the class has
   // been through phase A the lists are final and an empty scan ends the class.
   int pb_class = -1;   // thread 0: >= 0 once this worker is in phase B
+  const bool tail_worker = park.rev > 0 && (blockIdx.x % park.rev) == park.rev - 1;
   for (;;) {
     if (tid == 0) {
       int b = -1, cc = 0, res = resume;
@@ -810,11 +812,15 @@ __global__ void __launch_bounds__(TP_LB_THREADS, MODE == 3 ? 4 : (MODE == 4 ? TP
         // the batch drains whoever is resident); leave once no trajectory of the classes served is unfinished
         for (;;) {
           bool all_done = true;
-          for (int c = my_class; c < 4 && b < 0; ++c) {
-            const int csize = cls_begin[c + 1] - cls_begin[c];
-            if (csize == 0) continue;
-            const int rem = *((volatile int*)&park.remaining[c]);   // read BEFORE the scans: 0 = nothing can show up any more
-            for (int k = 0; k < TP_PARK_BUCKETS && b < 0; ++k) {   // not started yet, hardest-looking first
+          for (int c = my_class; c < 4; ++c)   // read BEFORE the scans: 0 = nothing of that class can show up any more
+            if (cls_begin[c + 1] > cls_begin[c] && *((volatile int*)&park.remaining[c]) > 0) all_done = false;
+          // not started yet: BUCKET-major over the classes this worker can serve, so that a worker of a long-trajectory
+          // class takes a hard-looking short trajectory before an easy-looking one of its own class (order within the
+          // buckets: hardest-looking first, or easiest first for one worker in `park.rev`)
+          for (int kk = 0; kk < TP_PARK_BUCKETS && b < 0; ++kk) {
+            const int k = tail_worker ? TP_PARK_BUCKETS - 1 - kk : kk;
+            for (int c = my_class; c < 4 && b < 0; ++c) {
+              if (cls_begin[c + 1] == cls_begin[c]) continue;
               const int q = c * TP_PARK_BUCKETS + k;
               for (;;) {
                 const int h = *((volatile int*)&park.head[q]);
@@ -823,8 +829,12 @@ __global__ void __launch_bounds__(TP_LB_THREADS, MODE == 3 ? 4 : (MODE == 4 ? TP
                 while ((b = *((volatile int*)&park.list[(size_t)q * park.stride + h])) < 0) __nanosleep(100);
                 break;
               }
+              if (b >= 0) cc = c;
             }
-            while (b < 0) {   // next turn of a trajectory that has had one (round robin)
+          }
+          for (int c = my_class; c < 4 && b < 0 && park.slice > 0; ++c) {   // next turn of a trajectory that has had one
+            if (cls_begin[c + 1] == cls_begin[c]) continue;
+            while (b < 0) {
               const int h = *((volatile int*)&park.rhead[c]);
               if (h >= *((volatile int*)&park.rtail[c])) break;
               if (atomicCAS(&park.rhead[c], h, h + 1) != h) continue;
@@ -832,7 +842,6 @@ __global__ void __launch_bounds__(TP_LB_THREADS, MODE == 3 ? 4 : (MODE == 4 ? TP
               while ((b = atomicExch(slot, -1)) < 0) __nanosleep(100);
             }
             if (b >= 0) cc = c;
-            else if (rem > 0) all_done = false;
           }
           if (b >= 0) { __threadfence(); res = 1; break; }
           for (int c = my_class; c < 4 && b < 0; ++c) {
@@ -2186,7 +2195,7 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
     ParkQueue pq;
     pq.list = nullptr; pq.tail = pq.head = pq.started = nullptr; pq.stride = M; pq.thresh = -1;
     pq.score_mode = 0; pq.b[0] = 16; pq.b[1] = 8; pq.b[2] = 2;
-    pq.ring = nullptr; pq.rtail = pq.rhead = nullptr; pq.remaining = d_cb + 9; pq.slice = 0;
+    pq.ring = nullptr; pq.rtail = pq.rhead = nullptr; pq.remaining = d_cb + 9; pq.slice = 0; pq.rev = 0;
     {
       static const int park_env = getenv("TP_PARK_THRESH") ? atoi(getenv("TP_PARK_THRESH")) : 1500;
       int workers_total = 0;
@@ -2202,6 +2211,8 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
         // rounds of a trajectory's first turn (team form with k_phase_a; 0 = every trajectory runs to its end once started)
         static const int slice_env = getenv("TP_SLICE_ROUNDS") ? atoi(getenv("TP_SLICE_ROUNDS")) : 0;   // measured: 1..3 lengthen the batch by 5-10 % (profiles/r02_summary.md)
         pq.slice = slice_env;
+        static const int rev_env = getenv("TP_PARK_REV") ? atoi(getenv("TP_PARK_REV")) : 0;
+        pq.rev = rev_env;
         pq.thresh = park_env;
         pq.score_mode = getenv("TP_PARK_SCORE") ? atoi(getenv("TP_PARK_SCORE")) : 0;
         pq.b[0] = getenv("TP_PARK_B0") ? atoi(getenv("TP_PARK_B0")) : 16;
