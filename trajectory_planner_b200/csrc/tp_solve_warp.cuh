@@ -285,10 +285,7 @@ __global__ void __launch_bounds__(128) k_solve_w(const __grid_constant__ BatchVi
     if (park.thresh >= 0 && !res && lane == 0) {
       if (parked) {
         const TrajState* ps = reinterpret_cast<const TrajState*>(sm + SL.st);
-        const int np = park.score_mode == 0 ? ps->n_pairs : (park.score_mode == 1 ? ps->n_pairs * ps->N / 32 : ps->n_pairs * 8 + ps->astar_expansions / 64);
-        // buckets 0 / 1: long first searches (the batch's potential tail: resumed first); 2..5 by guide pairs
-        const int bk = (ps->astar_expansions >= 4 * park.thresh || ps->astar_unreach) ? 0 : (ps->astar_expansions >= park.thresh ? 1 :
-                       (np >= park.b[0] ? 2 : (np >= park.b[1] ? 3 : (np >= park.b[2] ? 4 : 5))));
+        const int bk = park_bucket(park, *ps);
         const int q = cc * TP_PARK_BUCKETS + bk;
         const int pos = atomicAdd(&park.tail[q], 1);
         __threadfence();                                  // the trajectory's state is in HBM before its id shows up

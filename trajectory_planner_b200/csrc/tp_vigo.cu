@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(32) k_plan_init(BatchView bv, VigoConst C, Dev
 #ifndef TP_TEAM_BLOCKS
 #define TP_TEAM_BLOCKS 3   // resident teams per SM the team-form kernel is compiled for (3: 168 registers, 4: 128)
 #endif
-#define TP_PARK_BUCKETS 6
+#define TP_PARK_BUCKETS 12
 struct ParkQueue {
   int* list;       // [4 classes][TP_PARK_BUCKETS][stride]
   int* tail;       // [4][TP_PARK_BUCKETS]  slots handed out to parkers
@@ -569,6 +569,15 @@ struct ParkQueue {
   int slice;       // rounds of the first turn (<= 0: run to the end)
   int rev;         // one worker in `rev` scans the buckets easiest-first (0 = none)
 };
+// Bucket of a trajectory parked after makePlan steps 1-3, hardest-looking first: 0 / 1 = long first searches or an unreachable
+// goal (the batch's potential tail), then ten by the difficulty score (guide pairs: the best cheap predictor of the remaining
+// work, Spearman 0.8 with it — tools/dev/predict_probe.py)
+__device__ __forceinline__ int park_bucket(const ParkQueue& park, const TrajState& ps) {
+  const int np = park.score_mode == 0 ? ps.n_pairs : (park.score_mode == 1 ? ps.n_pairs * ps.N / 32 : ps.n_pairs * 8 + ps.astar_expansions / 64);
+  if (ps.astar_expansions >= 4 * park.thresh || ps.astar_unreach) return 0;
+  if (ps.astar_expansions >= park.thresh) return 1;
+  return np >= 24 ? 2 : (np >= 16 ? 3 : (np >= 12 ? 4 : (np >= 8 ? 5 : (np >= 6 ? 6 : (np >= 4 ? 7 : (np >= 3 ? 8 : (np >= 2 ? 9 : (np >= 1 ? 10 : 11))))))));
+}
 
 struct SolveLayout {
   int st;      // TrajState (doubles offset)
@@ -906,10 +915,7 @@ __global__ void __launch_bounds__(TP_LB_THREADS, MODE == 3 ? 4 : (MODE == 4 ? TP
       if (parked == 1) {
         // bucket by the guide pairs the first searches produced (the best cheap predictor of the remaining work)
         const TrajState* ps = reinterpret_cast<const TrajState*>(sm + SL.st);
-        const int np = park.score_mode == 0 ? ps->n_pairs : (park.score_mode == 1 ? ps->n_pairs * ps->N / 32 : ps->n_pairs * 8 + ps->astar_expansions / 64);
-        // buckets 0 / 1: long first searches (the batch's potential tail: resumed first); 2..5 by guide pairs
-        const int bk = (ps->astar_expansions >= 4 * park.thresh || ps->astar_unreach) ? 0 : (ps->astar_expansions >= park.thresh ? 1 :
-                       (np >= park.b[0] ? 2 : (np >= park.b[1] ? 3 : (np >= park.b[2] ? 4 : 5))));
+        const int bk = park_bucket(park, *ps);
         const int q = cc * TP_PARK_BUCKETS + bk;
         const int pos = atomicAdd(&park.tail[q], 1);
         __threadfence();                                  // the trajectory's state is in HBM before its id shows up
@@ -970,9 +976,7 @@ __global__ void __launch_bounds__(32) k_phase_a(const __grid_constant__ BatchVie
       if (W.goal_unreachable) st.astar_unreach = 1;
       if (timeline) timeline[4 * (size_t)b] = t_start;
       if (st.status == TS_ACTIVE) {
-        const int np = park.score_mode == 0 ? st.n_pairs : (park.score_mode == 1 ? st.n_pairs * st.N / 32 : st.n_pairs * 8 + st.astar_expansions / 64);
-        const int bk = (st.astar_expansions >= 4 * park.thresh || st.astar_unreach) ? 0 : (st.astar_expansions >= park.thresh ? 1 :
-                       (np >= park.b[0] ? 2 : (np >= park.b[1] ? 3 : (np >= park.b[2] ? 4 : 5))));
+        const int bk = park_bucket(park, st);
         const int q = cc * TP_PARK_BUCKETS + bk;
         const int pos = atomicAdd(&park.tail[q], 1);
         __threadfence();                                  // the trajectory's state is in HBM before its id shows up
