@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(32) k_plan_init(BatchView bv, VigoConst C, Dev
 #ifndef TP_TEAM_BLOCKS
 #define TP_TEAM_BLOCKS 3   // resident teams per SM the team-form kernel is compiled for (3: 168 registers, 4: 128)
 #endif
-#define TP_PARK_BUCKETS 12
+#define TP_PARK_BUCKETS 16
 struct ParkQueue {
   int* list;       // [4 classes][TP_PARK_BUCKETS][stride]
   int* tail;       // [4][TP_PARK_BUCKETS]  slots handed out to parkers
@@ -569,14 +569,21 @@ struct ParkQueue {
   int slice;       // rounds of the first turn (<= 0: run to the end)
   int rev;         // one worker in `rev` scans the buckets easiest-first (0 = none)
 };
-// Bucket of a trajectory parked after makePlan steps 1-3, hardest-looking first: 0 / 1 = long first searches or an unreachable
-// goal (the batch's potential tail), then ten by the difficulty score (guide pairs: the best cheap predictor of the remaining
-// work, Spearman 0.8 with it — tools/dev/predict_probe.py)
+// Bucket of a trajectory parked after makePlan steps 1-3, hardest-looking first.  0-5: by the length of its first A*
+// searches (a trajectory whose first searches were long has long re-guide searches too — on the octomap rasters the
+// longest trajectories are 100 k-expansion ones, 250 ms alone, and must start first), an unreachable goal counts as a
+// long search; 6-15: by the difficulty score (guide pairs: the best cheap predictor of the remaining work, Spearman 0.8
+// with it — tools/dev/predict_probe.py)
 __device__ __forceinline__ int park_bucket(const ParkQueue& park, const TrajState& ps) {
   const int np = park.score_mode == 0 ? ps.n_pairs : (park.score_mode == 1 ? ps.n_pairs * ps.N / 32 : ps.n_pairs * 8 + ps.astar_expansions / 64);
-  if (ps.astar_expansions >= 4 * park.thresh || ps.astar_unreach) return 0;
-  if (ps.astar_expansions >= park.thresh) return 1;
-  return np >= 24 ? 2 : (np >= 16 ? 3 : (np >= 12 ? 4 : (np >= 8 ? 5 : (np >= 6 ? 6 : (np >= 4 ? 7 : (np >= 3 ? 8 : (np >= 2 ? 9 : (np >= 1 ? 10 : 11))))))));
+  const int ex = ps.astar_expansions, t = park.thresh;
+  if (ex >= 32 * t) return 0;
+  if (ex >= 16 * t) return 1;
+  if (ex >= 8 * t) return 2;
+  if (ex >= 4 * t || ps.astar_unreach) return 3;
+  if (ex >= 2 * t) return 4;
+  if (ex >= t) return 5;
+  return np >= 24 ? 6 : (np >= 16 ? 7 : (np >= 12 ? 8 : (np >= 8 ? 9 : (np >= 6 ? 10 : (np >= 4 ? 11 : (np >= 3 ? 12 : (np >= 2 ? 13 : (np >= 1 ? 14 : 15))))))));
 }
 
 struct SolveLayout {
