@@ -93,6 +93,32 @@ def test_minsnap_solve_parity(tp, field):
     # degenerate inputs: too few waypoints
     s3, st3 = pt.solve_batch([np.array([[0, 0, 1.0]]), paths[2]])
     assert st3[0] == -3 and st3[1] == 0
+    # the band solver's limits: the longest path it accepts (63 segments, n = 882), one more (rejected), and the lower
+    # continuity degrees (fewer junction rows: the band layout changes with cont)
+    long_paths = []
+    for K in (40, 63, 64):
+        wp = [np.array([0.0, 0.0, 1.0])]
+        for _ in range(K):
+            ang, st = rng.uniform(0, 2 * np.pi), rng.uniform(1, 3)
+            wp.append(wp[-1] + np.array([st * np.cos(ang), st * np.sin(ang), rng.uniform(-0.1, 0.1)]))
+        long_paths.append(np.array(wp))
+    with pytest.raises(tp.TpError):   # 64 segments: the whole call fails loudly (TP_ERR_CAPACITY), nothing is solved silently
+        pt.solve_batch(long_paths)
+    sl, stl = pt.solve_batch(long_paths[:2])
+    assert list(stl) == [0, 0]
+    for p_, (coef, times) in zip(long_paths[:2], sl[:2]):
+        co, to = F.minsnap_solve(p_, 1.0)
+        # n = 560 / 882 with a KKT condition number beyond 1e10: BOTH solutions carry ~1e-7 of noise (the oracle's lstsq returns
+        # 1e-7 where the rest-to-rest boundary rows force exact zeros), so the comparison is at 1e-6 here, 1e-9 at the benchmark's sizes
+        assert np.max(np.abs(coef - co)) <= 1e-6 * np.max(np.abs(co))
+    for cont in (2, 3):
+        pc = tp.default_poly_params()
+        pc.cont = cont
+        sc, stc = tp.PolyTraj(e, pc).solve_batch(paths[:8])
+        assert np.all(stc == 0)
+        for p_, (coef, times) in zip(paths[:8], sc):
+            co, to = F.minsnap_solve(p_, 1.0, cont=cont)
+            assert np.max(np.abs(coef - co)) <= 1e-9 * np.max(np.abs(co)), cont
 
 
 def test_minsnap_kernel_against_reference_osqp_golden(tp, field):
