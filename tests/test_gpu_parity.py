@@ -405,6 +405,13 @@ def test_bspline_traj_class_drop_in(tp, engine, orc, sq_omap, problems):
         x, y, z, yaw = bt.getPose(0.5 * bt.getDuration())
         ref = orc.bspline_at(bt.getControlPoints().T, [0.5 * bt.getDuration()])[0]
         assert np.array_equal([x, y, z], ref)
+        # a failed replan (here: too few control points) leaves the committed trajectory, its duration and its factor in
+        # place (bspline_ is only replaced by a successful makePlan, bsplineTraj.cpp:376-377)
+        dur, lf, committed = bt.getDuration(), bt.getLinearFactor(), bt.getTrajectoryControlPoints()
+        bt.updateControlPoints(bt.getControlPoints().T[:5])
+        assert not bt.makePlan()
+        assert bt.getDuration() == dur and bt.getLinearFactor() == lf and np.array_equal(bt.getTrajectoryControlPoints(), committed)
+        assert np.array_equal(bt.getPose(0.5 * dur)[:3], [x, y, z])
 
 
 def test_batched_pose_sampling_matches_host_and_oracle(tp, engine, orc, problems):

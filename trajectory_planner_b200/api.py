@@ -557,7 +557,8 @@ class BsplineTraj:
     def __init__(self, engine, params=None):
         self.engine = engine
         self.params = params if params is not None else default_params()
-        self.ctrl = None
+        self.ctrl = None          # optData_.controlPoints: the working points
+        self.traj = None          # bspline_: the committed trajectory, replaced only by a successful makePlan (bsplineTraj.cpp:376-377)
         self.init_ = False
         self.linear_factor = 1.0
         self.dyn = None
@@ -629,6 +630,7 @@ class BsplineTraj:
         self.last_result = res[0]
         self.ctrl = out
         if res[0]["status"] == _capi.TP_STATUS_SUCCESS:
+            self.traj = out.copy()   # a failed replan leaves the previous trajectory (and its factor) in place, as the reference does
             self.linear_factor = float(res[0]["linear_factor"])
             return True
         return False
@@ -636,8 +638,11 @@ class BsplineTraj:
     def getControlPoints(self):
         return self.ctrl.T.copy()  # 3 x N like the reference's Eigen::MatrixXd
 
+    def getTrajectoryControlPoints(self):
+        return None if self.traj is None else self.traj.T.copy()
+
     def getDuration(self):
-        return (len(self.ctrl) - 3) * self.params.ctrl_pt_ts
+        return 0.0 if self.traj is None else (len(self.traj) - 3) * self.params.ctrl_pt_ts
 
     def getTimestep(self):
         return self.params.ts
@@ -649,11 +654,14 @@ class BsplineTraj:
         return self.linear_factor * t
 
     def getPose(self, t, yaw=True):
-        """-> (x, y, z, yaw) — bsplineTraj.cpp:1402-1419 (pose-at-time stays on the host)."""
-        p = bspline_eval(self.ctrl, [t], self.params.ctrl_pt_ts, 0)[0]
+        """-> (x, y, z, yaw) of the COMMITTED trajectory — bsplineTraj.cpp:1402-1419 (one trajectory, one time: on the host;
+        batches go through Engine.sample_batch)."""
+        if self.traj is None:
+            return 0.0, 0.0, 0.0, 0.0
+        p = bspline_eval(self.traj, [t], self.params.ctrl_pt_ts, 0)[0]
         if not yaw:
             return p[0], p[1], p[2], 0.0
-        v = bspline_eval(self.ctrl, [t], self.params.ctrl_pt_ts, 1)[0]
+        v = bspline_eval(self.traj, [t], self.params.ctrl_pt_ts, 1)[0]
         return p[0], p[1], p[2], float(np.arctan2(v[1], v[0]))
 
     def isCurrTrajValid(self):
