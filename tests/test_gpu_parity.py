@@ -744,7 +744,7 @@ import sys, numpy as np
 sys.path.insert(0, sys.argv[1])
 import trajectory_planner_b200 as tp
 z = np.load(sys.argv[2])
-eng = tp.Engine(0); eng.set_map(tp.OccMap.from_tpm(sys.argv[1] + "/data/maps/square_static.tpm"))
+eng = tp.Engine(0); eng.set_map(tp.OccMap.from_tpm(sys.argv[1] + "/data/maps/" + (sys.argv[4] if len(sys.argv) > 4 else "square_static") + ".tpm"))
 outs = {}
 for strict in (0, 1):
     p = tp.default_params(); p.strict_order = strict
@@ -778,6 +778,49 @@ def test_park_and_resume_scheduling_changes_no_result(tp, engine, sq_map, sq_oma
         for f in ("status", "lbfgs_iters", "lbfgs_evals", "astar_expansions", "outer_rounds", "final_cost", "linear_factor"):
             assert np.array_equal(res[f], ref["res%d" % strict][f]), (strict, f)
         print(f"strict={strict}: 1400 trajectories bit-identical with and without parking; success rate {np.mean(res['status'] == 1):.3f}")
+
+
+@pytest.mark.gpu
+def test_phase_a_kernel_and_schedule_change_no_result_on_maze(tp, orc, tmp_path):
+    """The A*-bound raster: 1 200 trajectories on maze.bt (long searches, flood fills, most goals unreachable) through
+    k_phase_a + team blocks with the bucket-ordered phase B, against (a) a child process with parking disabled (everything
+    inside the team kernel) — bit-identical in every field, and (b) the CPU oracle of the default mode on a sample."""
+    import subprocess, sys
+    import bench
+    from helpers import oracle_map_from
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    m = tp.OccMap.from_tpm(os.path.join(root, "data", "maps", "maze.tpm"))
+    e = tp.Engine(0)
+    e.set_map(m)
+    p = tp.default_params()
+    S, G = bench.octomap_pairs(m.grid("inflated"), m.info(), 1700, np.random.default_rng(5))
+    off, ctrl, valid = e.frontend_batch(p, S, G)
+    keep = np.flatnonzero((valid != 0) & (np.diff(off) >= 7))[:1200]
+    chunks = [ctrl[off[b]:off[b + 1]] for b in keep]
+    o2 = np.concatenate([[0], np.cumsum([len(c) for c in chunks])]).astype(np.int32)
+    c2 = np.concatenate(chunks, 0)
+    inp, outp = str(tmp_path / "in.npz"), str(tmp_path / "out.npz")
+    np.savez(inp, offsets=o2, ctrl=c2)
+    r = subprocess.run([sys.executable, "-c", _NOPARK_SCRIPT, root, inp, outp, "maze"], env=dict(os.environ, TP_PARK_THRESH="-1"),
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = np.load(outp)
+    out, res = e.make_plan_batch(p, o2, c2)
+    assert np.array_equal(out, ref["out0"])
+    for f in ("status", "lbfgs_iters", "lbfgs_evals", "astar_searches", "astar_expansions", "outer_rounds", "fail_count", "final_cost"):
+        assert np.array_equal(res[f], ref["res0"][f]), f
+    # the CPU oracle of the default mode on the first 48 trajectories
+    om = oracle_map_from(orc, m)
+    po = om.lib.default_params()
+    po.soft_atan2 = 1
+    po.fast_order = 4
+    n = 48
+    _, out_o, st_o = orc.make_plan_batch(om, po, o2[:n + 1], c2[:o2[n]], nthreads=os.cpu_count() or 4)
+    assert np.array_equal(out[:o2[n]], out_o)
+    assert np.array_equal(res["astar_expansions"][:n], st_o["astar_expansions"]) and np.array_equal(res["lbfgs_iters"][:n], st_o["lbfgs_iters"])
+    print(f"maze, 1200 trajectories: bit-identical with and without k_phase_a / parking; {n} of them bit-identical to the CPU oracle; "
+          f"success {np.mean(res['status'] == 1):.3f}, A* expansions per solve {res['astar_expansions'].mean():.0f}")
+    e.close()
 
 
 @pytest.mark.gpu
