@@ -34,6 +34,7 @@ int main(int argc, char** argv) {
   const std::vector<Vec3> se(4, Vec3{0, 0, 0});
   if (!planner.updatePath(path, se)) return 4;
   print_vec("ctrl_in", planner.getControlPoints());
+  const std::vector<double> ctrl0 = planner.getControlPoints();
   const bool ok = planner.makePlan();
   std::printf("makeplan %d %d %d %d\n", (int)ok, planner.lastResult().lbfgs_iters, planner.lastResult().astar_expansions, planner.lastResult().outer_rounds);
   print_vec("ctrl_out", planner.getControlPoints());
@@ -41,6 +42,30 @@ int main(int argc, char** argv) {
   std::printf("duration %.17g linear_factor %.17g valid %d\n", planner.getDuration(), planner.getLinearFactor(), (int)planner.isCurrTrajValid());
   const Pose q = planner.getPose(0.37 * planner.getDuration());
   std::printf("pose %.17g %.17g %.17g %.17g\n", q.x, q.y, q.z, q.yaw);
+  {   // batched entry points of the engine object: pose sampling and the multi-engine batch (two engines on this GPU)
+    const std::vector<double>& c = planner.getTrajectoryControlPoints();
+    const std::vector<int32_t> off = {0, (int32_t)(c.size() / 3)}, toff = {0, 3};
+    const std::vector<double> tt = {0.0, 0.37 * planner.getDuration(), planner.getDuration()};
+    std::vector<double> pos, vel, yaw;
+    const bool sok = eng->samplePoseBatch(planner.getControlPointTs(), off, c, toff, tt, pos, &vel, &yaw);
+    std::printf("sample %d %.17g %.17g %.17g %.17g\n", (int)sok, pos[3], pos[4], pos[5], yaw[1]);
+    auto eng2 = std::make_shared<engineB200>(0);
+    tp_engine_set_map(eng2->get(), sq);
+    std::vector<int32_t> boff = {0};
+    std::vector<double> bc;
+    for (int r = 0; r < 6; ++r) {   // six copies of the unoptimised control points
+      bc.insert(bc.end(), ctrl0.begin(), ctrl0.end());
+      boff.push_back((int32_t)(bc.size() / 3));
+    }
+    std::vector<tp_vigo_result> br;
+    std::vector<int32_t> who;
+    const bool mok = engineB200::makePlanBatchMulti({eng.get(), eng2.get()}, planner.params(), boff, bc, br, &who);
+    bool same = mok;
+    for (int r = 0; r < 6 && same; ++r)
+      for (size_t i = 0; i < ctrl0.size(); ++i)
+        if (bc[r * ctrl0.size() + i] != planner.getControlPoints()[i]) { same = false; break; }
+    std::printf("multi %d same_as_single %d engines_used %d %d\n", (int)mok, (int)same, (int)who.front(), (int)who.back());
+  }
   // a failed replan (start inside an obstacle column is rejected by updatePath -> the committed trajectory must survive)
   const std::vector<double> committed = planner.getTrajectoryControlPoints();
   Path bad;

@@ -42,6 +42,30 @@ class engineB200 {
     return tp_vigo_make_plan_batch(e_, &p, B, offsets.data(), ctrl.data(), ctrl.data(), results.data(), 0, nullptr,
                                    nullptr, nullptr, TP_MEM_HOST, nullptr) == TP_OK;
   }
+  // Batched pose-at-time queries (getPose / evalTraj for a whole batch on the GPU): trajectory b is sampled at the times
+  // t[tOffsets[b] .. tOffsets[b+1]-1]; pos / vel are 3 doubles per sample, yaw one (vel / yaw may be null pointers).
+  bool samplePoseBatch(double ctrlPtTs, const std::vector<int32_t>& offsets, const std::vector<double>& ctrl,
+                       const std::vector<int32_t>& tOffsets, const std::vector<double>& t, std::vector<double>& pos,
+                       std::vector<double>* vel, std::vector<double>* yaw) {
+    const int32_t B = (int32_t)offsets.size() - 1;
+    pos.assign(3 * t.size(), 0.0);
+    if (vel) vel->assign(3 * t.size(), 0.0);
+    if (yaw) yaw->assign(t.size(), 0.0);
+    return tp_vigo_sample_batch(e_, ctrlPtTs, B, offsets.data(), ctrl.data(), tOffsets.data(), t.data(), pos.data(),
+                                vel ? vel->data() : nullptr, nullptr, yaw ? yaw->data() : nullptr, TP_MEM_HOST, nullptr) == TP_OK;
+  }
+  // One batch on several engines of this host (one per GPU, the map set on each): independent trajectories, no exchange
+  // step; one host thread per engine inside the library.  engineOf (may be null) reports who solved what.
+  static bool makePlanBatchMulti(const std::vector<engineB200*>& engines, const tp_vigo_params& p, const std::vector<int32_t>& offsets,
+                                 std::vector<double>& ctrl, std::vector<tp_vigo_result>& results, std::vector<int32_t>* engineOf = nullptr) {
+    const int32_t B = (int32_t)offsets.size() - 1;
+    results.resize((size_t)B);
+    if (engineOf) engineOf->assign((size_t)B, -1);
+    std::vector<tp_engine_t*> h;
+    for (engineB200* e : engines) h.push_back(e->get());
+    return tp_vigo_make_plan_batch_multi(h.data(), (int32_t)h.size(), &p, B, offsets.data(), ctrl.data(), ctrl.data(), results.data(), 0,
+                                         nullptr, nullptr, nullptr, 0, engineOf ? engineOf->data() : nullptr) == TP_OK;
+  }
  private:
   tp_engine_t* e_;
 };

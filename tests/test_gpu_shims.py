@@ -55,6 +55,10 @@ def test_cpp_shims_run_on_the_gpu_and_match_the_python_api(tp, engine, sq_map, t
         assert float(d[0]) == bt.getDuration() and float(d[2]) == bt.getLinearFactor() and int(d[4]) == 1
         x, y, z, yaw = bt.getPose(0.37 * bt.getDuration())
         assert np.allclose([float(v) for v in o["pose"][0].split()], [x, y, z, yaw], rtol=0, atol=1e-15)
+        sm = [float(v) for v in o["sample"][0].split()]
+        assert sm[0] == 1 and np.allclose(sm[1:4], [x, y, z], rtol=0, atol=0) and abs(sm[4] - yaw) <= 1e-14
+        mu = o["multi"][0].split()
+        assert mu[0] == "1" and mu[2] == "1"   # six copies solved on two engines == the single solve, bit for bit
     rp = o["replan"][0].split()
     assert rp[0] == "0" and rp[1] == "0" and rp[3] == "1"   # rejected path: the committed trajectory survives
     # ---- bspline value type
