@@ -38,6 +38,7 @@ struct Worker {
   int flood_trigger;      // expansions after which astar_search checks reachability (adaptive per trajectory)
   int goal_unreachable;   // set by astar_search when the flood fill proved the goal unreachable
   int flood_wasted;       // consecutive floods of this trajectory that found the goal reachable (nothing gained)
+  int* flood_stats;       // engine-wide outcome counts of FIRST reachability checks (AStarPools::flood_stats)
 };
 
 struct AStarFrame {  // per-search constants (uniform across the warp)
@@ -303,6 +304,17 @@ struct Heap {
 #define TP_FLOOD_TRIGGER 2048       // expansions after which a search checks reachability (a flood costs about as much as 500)
 #endif
 #define TP_FLOOD_TRIGGER_AGAIN 192  // ... once this trajectory has already had an unreachable goal
+#ifndef TP_FLOOD_TRIGGER_EARLY
+#define TP_FLOOD_TRIGGER_EARLY 512  // first check of a search on a map where such checks mostly prove the goal unreachable
+#endif
+// A flood costs about as much as 250 expansions and, when it proves the goal unreachable after 512 instead of 2 048
+// expansions, saves 1 536 of them: checking early pays once one early check in seven succeeds.  The engine counts the
+// outcomes of first checks (maze.bt: most goals are unreachable -> 512; square_static_map: most long searches arrive -> 2 048).
+// Neither the outcome nor the expansion count of a search depends on when it checks.
+__device__ __forceinline__ int flood_first_trigger(const int* stats) {
+  const int unreach = *((volatile const int*)&stats[0]), reach = *((volatile const int*)&stats[1]);
+  return 7 * unreach >= reach ? TP_FLOOD_TRIGGER_EARLY : TP_FLOOD_TRIGGER;
+}
 #define TP_FLOOD_ROUND (32 * 26)    // cells one round can add to the worklist
 // The flood runs on ONE shared-memory bitmap F over the pool's stored cells (bit (i PY + j) KL + kk): first every
 // enterable free cell is marked (one coalesced pass over the map words of the window, lane per (i, j) column — no map
@@ -573,6 +585,9 @@ __device__ __noinline__ int astar_search(const DevMap& map, const VigoConst& C, 
   round = __shfl_sync(0xffffffffu, round, 0);
   F.round = round;
   expansions = 0;
+  // this search's reachability check: the trajectory's own setting when it has history, else the engine-wide choice
+  const bool first_check = W.flood_trigger == TP_FLOOD_TRIGGER;
+  const int flood_at = first_check ? flood_first_trigger(W.flood_stats) : W.flood_trigger;
   {
     // smallest k with (k - CZ)*step + center.z >= min_height, found with the reference's expression
     int k = (int)floor((C.p.min_height - F.center.z) * F.inv_step) + C.pool[2] / 2 - 1;
@@ -786,7 +801,7 @@ __device__ __noinline__ int astar_search(const DevMap& map, const VigoConst& C, 
       break;
     }
     if (C.p.astar_max_expansions > 0 && num_iter >= C.p.astar_max_expansions) break;
-    if (num_iter == W.flood_trigger) {
+    if (num_iter == flood_at) {
       const int hs = __shfl_sync(0xffffffffu, H.size, 0);
 #ifdef TP_ASTAR_TIMING
       const long long tf0 = clock64();
@@ -797,6 +812,10 @@ __device__ __noinline__ int astar_search(const DevMap& map, const VigoConst& C, 
       t0 = clock64();
 #endif
       W.flood_wasted = comp >= 0 ? 0 : W.flood_wasted + 1;
+      if (first_check && lane == 0) {
+        const int idx = comp >= 0 ? 0 : 1;
+        if (atomicAdd(&W.flood_stats[idx], 1) > (1 << 20)) { atomicSub(&W.flood_stats[0], W.flood_stats[0] / 2); atomicSub(&W.flood_stats[1], W.flood_stats[1] / 2); }
+      }
       if (comp >= 0) {  // goal unreachable: the search would pop the whole component and fail
         W.goal_unreachable = 1;
         num_iter = (C.p.astar_max_expansions > 0 && comp > C.p.astar_max_expansions) ? C.p.astar_max_expansions : comp;

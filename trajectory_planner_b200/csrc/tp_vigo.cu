@@ -390,6 +390,7 @@ __device__ __forceinline__ Worker make_worker(const VigoConst& C, const AStarPoo
   W.flood_trigger = TP_FLOOD_TRIGGER;
   W.goal_unreachable = 0;
   W.flood_wasted = 0;
+  W.flood_stats = P.flood_stats;
   return W;
 }
 
@@ -1313,8 +1314,8 @@ static int ensure_pools(tp_engine* e, const VigoConst& C) {
   if (e->pool_sc.ensure((size_t)workers * C.max_seg * TP_SC_CAP * 24) != TP_OK) return TP_ERR_CUDA;
   if (e->pool_sclen.ensure((size_t)workers * C.max_seg * 4) != TP_OK) return TP_ERR_CUDA;
   if (e->pool_rounds.ensure((size_t)workers * 4) != TP_OK) return TP_ERR_CUDA;
-  if (e->pool_flags.ensure(((size_t)workers + 256) * 4) != TP_OK) return TP_ERR_CUDA;   // pool slots + per-SM tickets
-  CK(cudaMemsetAsync(e->pool_flags.p, 0, ((size_t)workers + 256) * 4, e->stream));
+  if (e->pool_flags.ensure(((size_t)workers + 256 + 2) * 4) != TP_OK) return TP_ERR_CUDA;   // pool slots + per-SM tickets + flood statistics
+  CK(cudaMemsetAsync(e->pool_flags.p, 0, ((size_t)workers + 256 + 2) * 4, e->stream));
   CK(cudaMemsetAsync(e->pool_nodes.p, 0, (size_t)workers * (pool_nodes + 1) * sizeof(ANode), e->stream));
   CK(cudaMemsetAsync(e->pool_rounds.p, 0, (size_t)workers * 4, e->stream));
   CK(cudaStreamSynchronize(e->stream));
@@ -1325,6 +1326,7 @@ static int ensure_pools(tp_engine* e, const VigoConst& C) {
   e->pools.sc = e->pool_sc.as<double>();
   e->pools.sc_len = e->pool_sclen.as<int>();
   e->pools.rounds = e->pool_rounds.as<uint32_t>();
+  e->pools.flood_stats = e->pool_flags.as<int>() + workers + 256;
   e->pools.pool_nodes = pool_nodes;
   e->pools.workers = workers;
   memcpy(e->pools_key, key, sizeof(key));
@@ -1619,6 +1621,7 @@ int tp_engine_set_map(tp_engine_t* e, const tp_map_t* m) {
   if (e->map_infl.ensure(wi.size() * 4) != TP_OK || e->map_known.ensure(wk.size() * 4) != TP_OK) return TP_ERR_CUDA;
   CK(cudaMemcpy(e->map_infl.p, wi.data(), wi.size() * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(e->map_known.p, wk.data(), wk.size() * 4, cudaMemcpyHostToDevice));
+  if (e->pools.workers > 0) CK(cudaMemset(e->pools.flood_stats, 0, 2 * sizeof(int)));   // the statistics belong to the map
   {
     std::vector<uint32_t> wo;
     m->pack(0, wo);

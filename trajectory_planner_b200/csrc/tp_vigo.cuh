@@ -112,6 +112,7 @@ struct AStarPools {
   double* sc;          // [workers * max_seg * TP_SC_CAP * 3]   shortcut paths
   int* sc_len;         // [workers * max_seg]
   uint32_t* rounds;    // [workers]
+  int* flood_stats;    // [2] floods that proved the goal unreachable / that found it reachable (first checks only)
   size_t pool_nodes;
   int workers;
 };
