@@ -142,10 +142,12 @@ __device__ int corridor_ipm(const CorridorWork& W, int ax, const int* rs /*share
         for (int j = rs[s]; j < rs[s + 1]; ++j) acc += W.Arow[8 * (size_t)j + d] * gv[j];
         v -= acc;
       }
-      W.DX[i] = v;
+      W.DX[i] = v * W.T1[i];
     }
     __syncthreads();
     blk_band_solve(W.A, n, W.piv, W.DX);
+    for (int i = tid; i < n; i += PL_THREADS) W.DX[i] *= W.T1[i];
+    __syncthreads();
     for (int j = tid; j < mc; j += PL_THREADS) {
       const double adc = row_dot(j, W.DX);
       const double a = -ru[j] - adc, b = rl[j] + adc;
@@ -203,9 +205,6 @@ __device__ int corridor_ipm(const CorridorWork& W, int ax, const int* rs /*share
     const double mu = red.sum(comp) / (2.0 * mc);
     const double res = red.max(resmax);
     const double pcm = red.max(pcmax);
-#ifdef CR_DEBUG
-    if (tid == 0) printf("[ipm] ax %d it %d mu %.3e res %.3e pcm %.3e\n", ax, it, mu, res, pcm);
-#endif
     if (!(mu < 1e30) || !isfinite(res)) break;
     if (mu < CR_IPM_MU_TOL && res < CR_IPM_RES_TOL * (1.0 + pcm)) { status = 0; break; }
     // Newton matrix: K0 with Ac' S Ac added to the segments' 8 x 8 diagonal blocks
@@ -218,14 +217,18 @@ __device__ int corridor_ipm(const CorridorWork& W, int ax, const int* rs /*share
       W.A[bd_idx(L.var(s, d1), L.var(s, d2))] += acc;
     }
     __syncthreads();
-#ifdef CR_DEBUG
-    {
-      double sm_ = 0.0;
-      for (int j = tid; j < mc; j += PL_THREADS) sm_ = fmax(sm_, sig[j]);
-      sm_ = red.max(sm_);
-      if (tid == 0) printf("      max sig %.3e\n", sm_);
+    // symmetric equilibration D K D, D_i = 1 / sqrt(K_ii) on the coefficient rows whose diagonal carries a barrier term
+    // (they reach 1e19 in the last iterations, beside constraint entries of order 1): the factorisation keeps its digits
+    for (int i = tid; i < n; i += PL_THREADS) {
+      const double dii = W.kind[i] >= 0 ? fabs(W.A[bd_idx(i, i)]) : 0.0;
+      W.T1[i] = dii > 1.0 ? 1.0 / sqrt(dii) : 1.0;
     }
-#endif
+    __syncthreads();
+    for (int e = tid; e < n * BD_W; e += PL_THREADS) {
+      const int i = e / BD_W, j = i + (e - i * BD_W) - BD_KL;
+      if (j >= 0 && j < n) W.A[e] *= W.T1[i] * W.T1[j];
+    }
+    __syncthreads();
     if (blk_band_factor(W.A, n, W.piv, true) != 0) break;
     // predictor
     for (int j = tid; j < mc; j += PL_THREADS) { rcu[j] = su[j] * lu[j]; rcl[j] = sl[j] * ll[j]; }
@@ -246,9 +249,6 @@ __device__ int corridor_ipm(const CorridorWork& W, int ax, const int* rs /*share
     __syncthreads();
     newton();
     max_steps(ap, ad);
-#ifdef CR_DEBUG
-    if (tid == 0) printf("      sigma %.3e ap %.4f ad %.4f\n", sigma, ap, ad);
-#endif
     ap = fmin(0.995 * ap, 1.0);
     ad = fmin(0.995 * ad, 1.0);
     for (int i = tid; i < n; i += PL_THREADS) x[i] += (W.kind[i] >= 0 ? ap : ad) * W.DX[i];
