@@ -71,9 +71,9 @@ struct WfShared {
 };
 static_assert(sizeof(WfShared) <= WF_CTX * 8, "WfShared outgrew its shared-memory slot");
 
+#define WF_HS 34           // history: doubles per ELEMENT (32 rows + 2 of padding, see wf_layout)
 struct WfLayout {   // offsets in doubles from the worker's solver base (context, then control points)
-  int ns;           // history row stride
-  int cp, g, xp, gp, d, S, Y, gram, ca, cb, sc, red, gpart, pair, pstart, total;
+  int cp, g, xp, gp, d, H, gram, ca, cb, sc, red, gpart, pair, pstart, total;
 };
 #define WF_NW_MAX 4
 __host__ __device__ inline WfLayout wf_layout(int N) {
@@ -81,16 +81,17 @@ __host__ __device__ inline WfLayout wf_layout(int N) {
   const int n = 3 * (N - 2 * TP_DEGREE);
   const int nn = n > 0 ? n : 0;
   const int ne = (nn + 3) & ~3;   // vectors are zero-padded to a multiple of 4 (the row dot products run 4 elements a step)
-  L.ns = ne + 1;                  // odd row stride: the 16 rows a half-warp reads at one element index hit 16 different bank pairs
   int o = WF_CTX;
   L.cp = o; o += 3 * N + (N & 1);
   L.g = o; o += ne;
   L.xp = o; o += ne;
   L.gp = o; o += ne;
   L.d = o; o += ne;
-  L.S = o; o += WF_M * L.ns;
-  L.Y = o; o += WF_M * L.ns;
-  o += (o & 1);
+  // History, ELEMENT-major: H[i * WF_HS + r], r = 0..15 <-> s_slot, r = 16..31 <-> y_slot.  The Gram dot products (lane
+  // <-> row, serial over the elements) read 32 consecutive doubles per element; the direction (thread <-> element) reads
+  // its element's 32 rows with sixteen 128-bit loads at constant offsets - no per-row address arithmetic - and the
+  // stride of 34 doubles (272 B = 16 mod 128) spreads the eight lanes of a quarter-warp over all 32 banks.
+  L.H = o; o += ne * WF_HS;       // (o is even here: 16-byte aligned rows)
   L.gram = o; o += WF_GRAM;
   L.ca = o; o += WF_M;
   L.cb = o; o += WF_M;
@@ -405,23 +406,23 @@ __device__ __noinline__ void wf_gram_update(double* base, int N_, int slot, int 
   constexpr int P = 32 * NW;
   const int lane = tid & 31, warp = tid >> 5;
   const WfLayout L = wf_layout(N_);
-  const int n = 3 * (N_ - 2 * TP_DEGREE), ns = L.ns;
+  const int n = 3 * (N_ - 2 * TP_DEGREE);
   const double* x = base + L.cp + 3 * TP_DEGREE;
   const double* g = base + L.g;
   const double* xp = base + L.xp;
   double* gp = base + L.gp;
-  double* S = base + L.S;
+  double* H = base + L.H;
   double* G = base + L.gram;
 #pragma unroll 1
   for (int i = tid; i < n; i += P) {
     const double yi = g[i] - gp[i];
-    S[(size_t)slot * ns + i] = x[i] - xp[i];
-    S[(size_t)(WF_M + slot) * ns + i] = yi;   // Y = S + 16 ns
+    H[i * WF_HS + slot] = x[i] - xp[i];
+    H[i * WF_HS + WF_M + slot] = yi;
     gp[i] = yi;
   }
   wf_sync<NW>();
   // this warp's contiguous chunk of the zero-padded elements (a multiple of 4 elements)
-  const double* row = S + (size_t)lane * ns;
+  const double* row = H + lane;
   const int n4 = (n + 3) & ~3;
   const int chunk = ((n4 / 4 + NW - 1) / NW) * 4;
   const int i0 = warp * chunk;
@@ -431,7 +432,7 @@ __device__ __noinline__ void wf_gram_update(double* base, int N_, int slot, int 
   for (int i = i0; i < i1; i += 4) {
     const double2 y01 = *reinterpret_cast<const double2*>(gp + i), y23 = *reinterpret_cast<const double2*>(gp + i + 2);
     const double2 g01 = *reinterpret_cast<const double2*>(g + i), g23 = *reinterpret_cast<const double2*>(g + i + 2);
-    const double r0 = row[i], r1 = row[i + 1], r2 = row[i + 2], r3 = row[i + 3];
+    const double r0 = row[i * WF_HS], r1 = row[(i + 1) * WF_HS], r2 = row[(i + 2) * WF_HS], r3 = row[(i + 3) * WF_HS];
     a0 = fma(r0, y01.x, a0); b0 = fma(r0, g01.x, b0);
     a1 = fma(r1, y01.y, a1); b1 = fma(r1, g01.y, b1);
     a2 = fma(r2, y23.x, a2); b2 = fma(r2, g23.x, b2);
@@ -511,12 +512,40 @@ __device__ __noinline__ void wf_coeffs(double* G, double* ca, double* cb, double
   const double* yyrow = G + WF_G_YY + s * WF_GS;
   // ---- first loop
   double rr = -sg_s * inv_s;
+#ifdef WF_COEFFS_STEPWISE
 #pragma unroll
   for (int t = 0; t < WF_M; ++t) {
     const int st = (newest - t) & (WF_M - 1);
     const double ala = __shfl_sync(WF_FULL, rr, st);
     rr = fma(-ala, arow[st], rr);
   }
+#else
+  // Four steps per round of shuffles: the four rows whose alphas become final in steps 4k..4k+3 are broadcast at once
+  // and every lane redoes their in-block updates (six FMAs, the operands and the order the owning lanes use), so the
+  // dependent chain per four steps is ONE shuffle round trip + 4 FMAs instead of four round trips.  Every row still
+  // receives its 16 FMAs in step order with the same operands: the results are bit-identical to the step-by-step loop.
+  const double* Ab = G + WF_G_A;
+#pragma unroll
+  for (int k = 0; k < WF_M / 4; ++k) {
+    const int s0 = (newest - 4 * k) & (WF_M - 1), s1 = (s0 - 1) & (WF_M - 1), s2 = (s0 - 2) & (WF_M - 1), s3 = (s0 - 3) & (WF_M - 1);
+    const double a0 = __shfl_sync(WF_FULL, rr, s0);
+    double a1 = __shfl_sync(WF_FULL, rr, s1), a2 = __shfl_sync(WF_FULL, rr, s2), a3 = __shfl_sync(WF_FULL, rr, s3);
+    const double m0 = arow[s0], m1 = arow[s1], m2 = arow[s2], m3 = arow[s3];
+    const double e10 = Ab[s1 * WF_GS + s0];
+    const double e20 = Ab[s2 * WF_GS + s0], e21 = Ab[s2 * WF_GS + s1];
+    const double e30 = Ab[s3 * WF_GS + s0], e31 = Ab[s3 * WF_GS + s1], e32 = Ab[s3 * WF_GS + s2];
+    a1 = fma(-a0, e10, a1);
+    a2 = fma(-a0, e20, a2);
+    a3 = fma(-a0, e30, a3);
+    rr = fma(-a0, m0, rr);
+    a2 = fma(-a1, e21, a2);
+    a3 = fma(-a1, e31, a3);
+    rr = fma(-a1, m1, rr);
+    a3 = fma(-a2, e32, a3);
+    rr = fma(-a2, m2, rr);
+    rr = fma(-a3, m3, rr);
+  }
+#endif
   const double al = rr;
   // ---- middle
   __syncwarp();
@@ -534,12 +563,42 @@ __device__ __noinline__ void wf_coeffs(double* G, double* ca, double* cb, double
   }
   // ---- second loop
   double bacc = (-gamma * ((t0 + t1) + (t2 + t3))) * inv_s;
+#ifdef WF_COEFFS_STEPWISE
 #pragma unroll
   for (int t = WF_M - 1; t >= 0; --t) {
     const int st = (newest - t) & (WF_M - 1);
     const double cst = __shfl_sync(WF_FULL, al - bacc, st);
     bacc = fma(cst, brow[st], bacc);
   }
+#else
+  // same four-step blocking, oldest block first: b of the block's four rows by shuffle, their alphas from tb[]
+  const double* Bb = G + WF_G_BT;
+#pragma unroll
+  for (int k = 0; k < WF_M / 4; ++k) {
+    const int s0 = (newest - (WF_M - 1) + 4 * k) & (WF_M - 1), s1 = (s0 + 1) & (WF_M - 1), s2 = (s0 + 2) & (WF_M - 1), s3 = (s0 + 3) & (WF_M - 1);
+    const double b0 = __shfl_sync(WF_FULL, bacc, s0);
+    double b1 = __shfl_sync(WF_FULL, bacc, s1), b2 = __shfl_sync(WF_FULL, bacc, s2), b3 = __shfl_sync(WF_FULL, bacc, s3);
+    const double l0 = tb[s0], l1 = tb[s1], l2 = tb[s2], l3 = tb[s3];
+    const double m0 = brow[s0], m1 = brow[s1], m2 = brow[s2], m3 = brow[s3];
+    const double e10 = Bb[s1 * WF_GS + s0];
+    const double e20 = Bb[s2 * WF_GS + s0], e21 = Bb[s2 * WF_GS + s1];
+    const double e30 = Bb[s3 * WF_GS + s0], e31 = Bb[s3 * WF_GS + s1], e32 = Bb[s3 * WF_GS + s2];
+    const double c0 = l0 - b0;
+    b1 = fma(c0, e10, b1);
+    b2 = fma(c0, e20, b2);
+    b3 = fma(c0, e30, b3);
+    bacc = fma(c0, m0, bacc);
+    const double c1 = l1 - b1;
+    b2 = fma(c1, e21, b2);
+    b3 = fma(c1, e31, b3);
+    bacc = fma(c1, m1, bacc);
+    const double c2 = l2 - b2;
+    b3 = fma(c2, e32, b3);
+    bacc = fma(c2, m2, bacc);
+    const double c3 = l3 - b3;
+    bacc = fma(c3, m3, bacc);
+  }
+#endif
   const double aa = al - bacc;
   const double bb = -gamma * al;
   if (lane < WF_M) {
@@ -564,9 +623,9 @@ __device__ __noinline__ void wf_direction(double* base, int N_, int tid) {
   WF_ASSUME_SHARED(base);
   constexpr int P = 32 * NW;
   const WfLayout L = wf_layout(N_);
-  const int n = 3 * (N_ - 2 * TP_DEGREE), ns = L.ns;
+  const int n = 3 * (N_ - 2 * TP_DEGREE);
   const double* g = base + L.g;
-  const double* S = base + L.S;
+  const double* H = base + L.H;
   double* d = base + L.d;
   double ca[WF_M], cb[WF_M];
 #pragma unroll
@@ -578,13 +637,18 @@ __device__ __noinline__ void wf_direction(double* base, int N_, int tid) {
 #pragma unroll 1
   for (int i = tid; i < n; i += P) {
     double a0 = cg * g[i], a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    const double* sp = S + i;
+    const double2* hp = reinterpret_cast<const double2*>(H + i * WF_HS);
 #pragma unroll
-    for (int j = 0; j < WF_M / 2; ++j) {
-      a0 = fma(ca[j], sp[(size_t)j * ns], a0);
-      a1 = fma(ca[j + 8], sp[(size_t)(j + 8) * ns], a1);
-      a2 = fma(cb[j], sp[(size_t)(j + WF_M) * ns], a2);
-      a3 = fma(cb[j + 8], sp[(size_t)(j + 8 + WF_M) * ns], a3);
+    for (int j = 0; j < WF_M / 4; ++j) {
+      const double2 s0 = hp[j], s1 = hp[j + 4], y0 = hp[j + 8], y1 = hp[j + 12];
+      a0 = fma(ca[2 * j], s0.x, a0);
+      a1 = fma(ca[2 * j + 8], s1.x, a1);
+      a2 = fma(cb[2 * j], y0.x, a2);
+      a3 = fma(cb[2 * j + 8], y1.x, a3);
+      a0 = fma(ca[2 * j + 1], s0.y, a0);
+      a1 = fma(ca[2 * j + 9], s1.y, a1);
+      a2 = fma(cb[2 * j + 1], y0.y, a2);
+      a3 = fma(cb[2 * j + 9], y1.y, a3);
     }
     d[i] = (a0 + a1) + (a2 + a3);
   }
