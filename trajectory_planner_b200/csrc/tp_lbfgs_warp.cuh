@@ -105,6 +105,11 @@ __host__ __device__ inline WfLayout wf_layout(int N) {
 }
 
 #define WF_FULL 0xffffffffu
+#ifdef WF_COEFFS_ROLLED
+#define WF_COEFFS_LOOP _Pragma("unroll 1")
+#else
+#define WF_COEFFS_LOOP _Pragma("unroll")
+#endif
 // the noinline pieces below get plain pointers: tell the compiler they point into shared memory (LDS / STS instead of
 // generic loads and 64-bit address arithmetic)
 #define WF_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
@@ -525,7 +530,7 @@ __device__ __noinline__ void wf_coeffs(double* G, double* ca, double* cb, double
   // dependent chain per four steps is ONE shuffle round trip + 4 FMAs instead of four round trips.  Every row still
   // receives its 16 FMAs in step order with the same operands: the results are bit-identical to the step-by-step loop.
   const double* Ab = G + WF_G_A;
-#pragma unroll
+WF_COEFFS_LOOP
   for (int k = 0; k < WF_M / 4; ++k) {
     const int s0 = (newest - 4 * k) & (WF_M - 1), s1 = (s0 - 1) & (WF_M - 1), s2 = (s0 - 2) & (WF_M - 1), s3 = (s0 - 3) & (WF_M - 1);
     const double a0 = __shfl_sync(WF_FULL, rr, s0);
@@ -573,7 +578,7 @@ __device__ __noinline__ void wf_coeffs(double* G, double* ca, double* cb, double
 #else
   // same four-step blocking, oldest block first: b of the block's four rows by shuffle, their alphas from tb[]
   const double* Bb = G + WF_G_BT;
-#pragma unroll
+WF_COEFFS_LOOP
   for (int k = 0; k < WF_M / 4; ++k) {
     const int s0 = (newest - (WF_M - 1) + 4 * k) & (WF_M - 1), s1 = (s0 + 1) & (WF_M - 1), s2 = (s0 + 2) & (WF_M - 1), s3 = (s0 + 3) & (WF_M - 1);
     const double b0 = __shfl_sync(WF_FULL, bacc, s0);

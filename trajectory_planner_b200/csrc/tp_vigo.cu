@@ -549,7 +549,9 @@ __global__ void __launch_bounds__(32) k_plan_init(BatchView bv, VigoConst C, Dev
 // Parked trajectories of one batch (see k_solve): per size class a list of ids (filled with -1 before the launch),
 // its tail (slots handed out), its head (slots claimed) and the number of trajectories that finished phase A.
 #ifndef TP_TEAM_BLOCKS
-#define TP_TEAM_BLOCKS 3   // resident teams per SM the team-form kernel is compiled for (3: 168 registers, 4: 128)
+// resident teams per SM the team-form kernel is compiled for.  2: 252 registers, no spills; 3: 168 registers (36 local-memory
+// loads per warp and iteration: measured 1.7 % slower on the 4,096 batch, 7 % slower on a single solve); 4: 128 registers
+#define TP_TEAM_BLOCKS 2
 #endif
 #define TP_PARK_BUCKETS 16
 struct ParkQueue {
