@@ -305,9 +305,11 @@ __device__ unsigned long long g_wf_phase[8];   // whole-batch cycle totals: tota
 // owned by exactly one element: element (c, a) owns jerk / velocity / acceleration term c; the elements of the first
 // optimised point c = 3 additionally own the terms 0..2 that reach into the fixed points; terms made of fixed points
 // only are X->f_const.
+struct WfEv { double v[4]; };   // returned BY VALUE (registers); an array by reference would travel through the stack
 template <int NW>
-__device__ __noinline__ void wf_eval(const VigoConst& C, double* base, int with_d, double (&out)[4], int tid) {
+__device__ __noinline__ WfEv wf_eval(const VigoConst& C, double* base, int with_d, int tid) {
   WF_ASSUME_SHARED(base);
+  double out[4];
   constexpr int P = 32 * NW;
   const int lane = tid & 31;
   const WfShared* X = reinterpret_cast<const WfShared*>(base);
@@ -394,7 +396,9 @@ __device__ __noinline__ void wf_eval(const VigoConst& C, double* base, int with_
       out[k] = v;
     }
   }
-  out[0] = out[0] + X->f_const;
+  WfEv r;
+  r.v[0] = out[0] + X->f_const; r.v[1] = out[1]; r.v[2] = out[2]; r.v[3] = out[3];
+  return r;
 }
 
 // New pair (s, y) = (x - xp, g - gp) into slot `slot` (y also into the gp vector, which is dead from here on), then the
@@ -717,7 +721,6 @@ __device__ __noinline__ void lbfgs_run_team(const VigoConst& C, double* base, in
   wf_sync<NW>();
   int evals = 0, k = 0, ret, bsum = 0;
   double fx, gg, xx;
-  double ev[4];
 #ifdef TP_WF_TIMING
   long long tE = 0, tG = 0, tC = 0, tD = 0, tT0 = clock64(), tq0, tq1;
 #define WT0 tq0 = clock64();
@@ -726,8 +729,10 @@ __device__ __noinline__ void lbfgs_run_team(const VigoConst& C, double* base, in
 #define WT0
 #define WT(acc)
 #endif
-  wf_eval<NW>(C, base, 0, ev, tid);
-  fx = ev[0]; gg = ev[2]; xx = ev[3];
+  {
+    const WfEv ev = wf_eval<NW>(C, base, 0, tid);
+    fx = ev.v[0]; gg = ev.v[2]; xx = ev.v[3];
+  }
   ++evals;
   WF_OWNED(i) d[i] = -g[i];
   double xnorm = sqrt(xx), gnorm = sqrt(gg);
@@ -776,8 +781,10 @@ __device__ __noinline__ void lbfgs_run_team(const VigoConst& C, double* base, in
           WF_OWNED(i) x[i] = xp[i] + stp * d[i];
           WT0
           wf_sync<NW>();
-          wf_eval<NW>(C, base, 1, ev, tid);
-          fx = ev[0]; dg = ev[1]; gg = ev[2]; xx = ev[3];
+          {
+            const WfEv ev = wf_eval<NW>(C, base, 1, tid);
+            fx = ev.v[0]; dg = ev.v[1]; gg = ev.v[2]; xx = ev.v[3];
+          }
           WT(tE)
           ++evals;
           const double ftest1 = finit + stp * dgtest;

@@ -357,8 +357,8 @@ __global__ void __launch_bounds__(32) k_cost_w(BatchView bv, VigoConst C, double
   __syncwarp();
   wf_setup<1>(C, sm, N, bv.pairs + (size_t)b * C.gcap, bv.cp_head + st.off, st.n_pairs, st.w_dist, st.w_dyn, bv.n_dyn, bv.dyn_pos,
            bv.dyn_vel, bv.dyn_size, lane);
-  double ev[4];
-  wf_eval<1>(C, sm, 0, ev, lane);
+  const WfEv evr = wf_eval<1>(C, sm, 0, lane);
+  const double* ev = evr.v;
   __syncwarp();
   if (lane == 0) f_out[b] = ev[0];
   double* go = grad_out + 3 * ((size_t)st.off - (size_t)2 * TP_DEGREE * b);

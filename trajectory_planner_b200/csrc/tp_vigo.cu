@@ -185,8 +185,8 @@ __global__ void __launch_bounds__(TP_LB_THREADS) k_cost_t(BatchView bv, VigoCons
   __syncthreads();
   wf_setup<TP_LB_WARPS>(C, sm, N, bv.pairs + (size_t)b * C.gcap, bv.cp_head + st.off, st.n_pairs, st.w_dist, st.w_dyn, bv.n_dyn,
                         bv.dyn_pos, bv.dyn_vel, bv.dyn_size, tid);
-  double ev[4];
-  wf_eval<TP_LB_WARPS>(C, sm, 0, ev, tid);
+  const WfEv evr = wf_eval<TP_LB_WARPS>(C, sm, 0, tid);
+  const double* ev = evr.v;
   __syncthreads();
   if (tid == 0) f_out[b] = ev[0];
   double* go = grad_out + 3 * ((size_t)st.off - (size_t)2 * TP_DEGREE * b);
