@@ -626,7 +626,10 @@ WF_COEFFS_LOOP
 }
 
 // d = cg g + sum_j ca[j] s_j + cb[j] y_j over all 16 slots (coefficients of slots not stored yet are zero), four
-// running sums per element: s_0..7, s_8..15, y_0..7, y_8..15, combined (a0 + a1) + (a2 + a3)
+// running sums per element: s_0..7, s_8..15, y_0..7, y_8..15, combined (a0 + a1) + (a2 + a3).
+// The same pass opens the next iteration for its element (it holds d_i and g_i in registers and owns x_i): xp = x, gp = g
+// and the FIRST trial point of the next line search, x = xp + 1.0 d (lbfgs.hpp:1333 sets step = 1.0; the clamps of
+// line_search_morethuente leave a first trial of 1.0 alone) — the caller skips its own copy and update loops.
 template <int NW>
 __device__ __noinline__ void wf_direction(double* base, int N_, int tid) {
   WF_ASSUME_SHARED(base);
@@ -636,6 +639,9 @@ __device__ __noinline__ void wf_direction(double* base, int N_, int tid) {
   const double* g = base + L.g;
   const double* H = base + L.H;
   double* d = base + L.d;
+  double* x = base + L.cp + 3 * TP_DEGREE;
+  double* xp = base + L.xp;
+  double* gp = base + L.gp;
   double ca[WF_M], cb[WF_M];
 #pragma unroll
   for (int j = 0; j < WF_M; j += 2) {
@@ -645,7 +651,8 @@ __device__ __noinline__ void wf_direction(double* base, int N_, int tid) {
   const double cg = base[L.sc];
 #pragma unroll 1
   for (int i = tid; i < n; i += P) {
-    double a0 = cg * g[i], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    const double gi = g[i], xi = x[i];
+    double a0 = cg * gi, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     const double2* hp = reinterpret_cast<const double2*>(H + i * WF_HS);
 #pragma unroll
     for (int j = 0; j < WF_M / 4; ++j) {
@@ -659,7 +666,11 @@ __device__ __noinline__ void wf_direction(double* base, int N_, int tid) {
       a2 = fma(cb[2 * j + 1], y0.y, a2);
       a3 = fma(cb[2 * j + 9], y1.y, a3);
     }
-    d[i] = (a0 + a1) + (a2 + a3);
+    const double dv = (a0 + a1) + (a2 + a3);
+    d[i] = dv;
+    xp[i] = xi;
+    gp[i] = gi;
+    x[i] = xi + dv;   // = xp + 1.0 * d bit for bit
   }
 }
 
@@ -745,13 +756,14 @@ __device__ __noinline__ void lbfgs_run_team(const VigoConst& C, double* base, in
     int end = 0;
     k = 1;
     for (;;) {
-      WF_OWNED(i) { xp[i] = x[i]; gp[i] = g[i]; }
+      // from the second iteration on wf_direction has already saved xp / gp and advanced x by the unit first trial step
+      const bool pre = k > 1;
+      if (!pre) WF_OWNED(i) { xp[i] = x[i]; gp[i] = g[i]; }
       // ---------------- line_search_morethuente (lbfgs.hpp:716-937), same scalar logic as tp_lbfgs.cuh
       int ls;
-      if (step <= 0.) {
-        ls = LB_INVALIDPARAMS;
-      } else if (0 < dginit) {
-        ls = LB_INCREASEGRADIENT;
+      if (step <= 0. || 0 < dginit) {
+        ls = step <= 0. ? LB_INVALIDPARAMS : LB_INCREASEGRADIENT;
+        if (pre) WF_OWNED(i) x[i] = xp[i];   // no trial is evaluated: the control points stay the last evaluated point
       } else {
         int count = 0, brackt = 0, stage1 = 1, uinfo = 0;
         const double finit = fx;
@@ -778,7 +790,7 @@ __device__ __noinline__ void lbfgs_run_team(const VigoConst& C, double* base, in
             stp = stx;
           if (NW == 1) __syncwarp();   // every lane is done reading the control points of the previous evaluation
                                        // (NW > 1: the barrier inside the evaluation's reduction already says so)
-          WF_OWNED(i) x[i] = xp[i] + stp * d[i];
+          if (!(pre && count == 0 && stp == 1.0)) WF_OWNED(i) x[i] = xp[i] + stp * d[i];
           WT0
           wf_sync<NW>();
           {

@@ -2142,8 +2142,9 @@ int tp_vigo_make_plan_batch(tp_engine_t* e, const tp_vigo_params* p, int32_t B, 
     const size_t smem_sm = 222 * 1024;
     // warp form: a worker is one warp (its own block of 32 threads); registers allow up to 12 per SM
     static const int wf_max = getenv("TP_W_MAX") ? atoi(getenv("TP_W_MAX")) : 12;
-    static const int team_max = getenv("TP_TEAM_MAX") ? atoi(getenv("TP_TEAM_MAX")) : (mode == 4 ? TP_TEAM_BLOCKS : 4);
-    const int maxw = mode == 5 ? wf_max : (mode == 4 ? team_max : 4);
+    static const int team_env = getenv("TP_TEAM_MAX") ? atoi(getenv("TP_TEAM_MAX")) : 0;
+    // resident blocks per SM = the kernels' __launch_bounds__ (team form: TP_TEAM_BLOCKS, tensor-memory form: 4, others: 3)
+    const int maxw = mode == 5 ? wf_max : (mode == 4 ? (team_env > 0 ? team_env : TP_TEAM_BLOCKS) : (mode == 3 ? 4 : 3));
     int a[4];
     for (a[0] = 0; a[0] <= maxw; ++a[0])
       for (a[1] = 0; a[0] + a[1] <= maxw; ++a[1])
