@@ -8,6 +8,10 @@
 // warp order, the Gram dot products are serial per history row over each warp's contiguous chunk with four interleaved
 // partial sums, and fused multiply-adds happen exactly where std::fma is written (build with -ffp-contract=off).  tests/ assert that the CUDA kernel and this file agree BIT FOR BIT on
 // return code, iteration / evaluation counts and control points — that is the pin of the benchmarked mode.
+// What is restated is every VALUE's sequence of operations, not the kernel's schedule or storage: the kernel keeps the
+// history element-major and runs the two triangular recurrences four steps per round of shuffles (each row still gets
+// its 16 FMAs in step order with the same operands), opens the next iteration inside its direction pass (xp = x, gp = g,
+// x = xp + 1.0 d) — this file keeps row-major vectors and the step-by-step loops, and the results must still be equal.
 //
 // What the algorithm is (and how it relates to the reference): the same L-BFGS as solver/lbfgs.hpp:1024-1349 with
 // m = 16 — identical More-Thuente line search (update_trial etc. from lbfgs_port.hpp), identical convergence and
