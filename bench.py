@@ -458,8 +458,8 @@ def extra_minsnap(tp, eng_dev, fp64_peak, B=16384):
     B = len(paths)
     nwp = np.array([len(q) for q in paths])
     pt.solve_batch(paths[:256])
-    # one untimed full-size pass of both entries (as the warm-up steps of the main metric): the engine grows its device
-    # buffers on the first full-size call, and right after the octomap engines were closed that costs ~0.5-1 s of driver time
+    # one untimed full-size pass of both entries (as the warm-up steps of the main metric): the first full-size call after
+    # the octomap engines were closed was measured 0.5-1 s slower than the same call in a fresh process
     pt.solve_batch(paths)
     pt.make_plan_batch(paths)
     e.profile_enable(True)
