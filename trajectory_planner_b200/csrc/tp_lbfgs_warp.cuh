@@ -24,13 +24,15 @@
 // Per iteration only the column of the newest pair and s_i.g / y_i.g change: 4 x 16 dot products of length n.  Lane l
 // owns history ROW l (s_0..s_15, y_0..y_15) for this step and runs its two dot products (with y_new and with g)
 // serially over the elements — 64 dot products, no cross-lane reduction at all — instead of 2 x 16 SEQUENTIAL
-// reductions; the two 16-step triangular recurrences run on register shuffles.
+// reductions; the two 16-step triangular recurrences run on register shuffles, four steps per round (wf_coeffs).
+// The history is stored element-major (wf_layout), and the direction pass also opens the next iteration (wf_direction).
 // WHY A TEAM: one warp issues an instruction every ~4 cycles (dependent FP64 / shared-memory chains), and shared memory
 // (2 x 16 history rows per trajectory) limits an SM to ~5 trajectories — with one warp each, most issue slots idle
 // (measured: 14.5 k cycles per iteration).  Four warps share the element-parallel phases (evaluation, Gram dot
-// products, direction); the serial phases were made cheap enough (coefficients: ~450 instructions) not to dominate.
-// INSTRUCTION COUNT and CODE SIZE are first-class constraints: an iteration costs what it issues; and the SM's instruction cache holds 32 KB (2 048 instructions)
-// that several workers at different phases share.  Hence: constants and the per-solve context live in shared
+// products, direction); the serial phases were made cheap enough not to dominate (~1.1 k of ~7.5 k cycles per iteration).
+// INSTRUCTION COUNT, LATENCY PER INSTRUCTION and REGISTERS are the constraints (measured): a warp
+// issues one instruction per ~9 cycles, so an iteration costs what it issues; compiled for three teams per SM (168
+// registers) the kernel spilled 36 loads per warp and iteration and ran slower than two spill-free teams (TP_TEAM_BLOCKS).  Hence: constants and the per-solve context live in shared
 // memory (a `const VigoConst&` reaching a noinline function turns every access into a generic global load), every
 // rare path is out of line, small vector loops stay rolled.
 #pragma once
