@@ -94,6 +94,8 @@ class Lib:
         L.orc_planner_cost_wform.argtypes = [C.c_void_p, _dp, _dp, C.c_int]
         L.orc_planner_wform_direction_check.restype = C.c_double
         L.orc_planner_wform_direction_check.argtypes = [C.c_void_p, _ip]
+        L.orc_wform_coeffs_schedules_check.restype = C.c_int
+        L.orc_wform_coeffs_schedules_check.argtypes = [C.c_int, C.c_int]
         L.orc_planner_find_collision_seg.argtypes = [C.c_void_p, _ip, C.c_int]
         L.orc_planner_has_collision.argtypes = [C.c_void_p]
         L.orc_planner_init_guides.argtypes = [C.c_void_p]

@@ -1211,6 +1211,65 @@ double orc_planner_cost_wform(void* pl_, const double* x, double* grad, int n) {
   std::memcpy(pl->ctrl.data() + 3 * bsplineDegree, x, n * sizeof(double));
   return pl->costFunctionWform(grad, n);
 }
+// The kernel's schedule of the two triangular recurrences (four steps per round of shuffles, wform::Solver::coeffs_blocked)
+// against the step-by-step form (coeffs) on `cases` random Gram blocks: masked as wf_gram_update leaves them (0..16 stored
+// pairs, random newest slot) or dense, with signed zeros, huge / tiny magnitudes, infinities and NaNs mixed in.  Returns
+// the number of cases whose ca / cb / sc differ in any bit (NaN == NaN).
+int orc_wform_coeffs_schedules_check(int seed, int cases) {
+  using namespace wform;
+  std::vector<double> cpbuf(3 * 8, 0.0);
+  Problem wp;
+  wp.N = 8;
+  wp.cp = cpbuf.data();
+  Solver ws(wp, 4);
+  unsigned long long st = 0x9E3779B97F4A7C15ull * (unsigned long long)(seed + 1);
+  auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return st; };
+  auto uni = [&]() { return (double)(rnd() >> 11) / 9007199254740992.0; };
+  auto val = [&](int special) {
+    double v = (uni() - 0.5) * 2.0 * std::pow(10.0, (int)(rnd() % 7) - 3);
+    if (special) {
+      switch (rnd() % 24) {
+        case 0: v = 0.0; break;
+        case 1: v = -0.0; break;
+        case 2: v = 1e300; break;
+        case 3: v = -1e-300; break;
+        case 4: v = INFINITY; break;
+        case 5: v = NAN; break;
+        default: break;
+      }
+    }
+    return v;
+  };
+  int bad = 0;
+  for (int cs = 0; cs < cases; ++cs) {
+    const int newest = (int)(rnd() % M), count = (int)(rnd() % (M + 1)), dense = (cs % 5) == 4, special = (cs % 3) == 2;
+    std::fill(ws.G.begin(), ws.G.end(), 0.0);
+    auto age = [&](int s_) { return (newest - s_) & (M - 1); };
+    for (int s_ = 0; s_ < M; ++s_) {
+      const bool stored_s = dense || age(s_) < count;
+      if (stored_s) { ws.Sg()[s_] = val(special); ws.Yg()[s_] = val(special); ws.INV()[s_] = val(special); }
+      for (int c = 0; c < M; ++c) {
+        const bool stored_c = dense || age(c) < count;
+        if (!(stored_s && stored_c)) continue;
+        ws.YY()[s_ * GS + c] = val(special);
+        if (dense || age(s_) > age(c)) ws.A()[s_ * GS + c] = val(special);      // pair s older than pair c
+        if (dense || age(c) > age(s_)) ws.Bt()[s_ * GS + c] = val(special);     // Bt[row][col]: pair col older than pair row
+      }
+    }
+    ws.YS()[0] = val(special); ws.YS()[1] = val(special); ws.YS()[2] = val(special);
+    const double gg = std::fabs(val(0));
+    double r1[2 * M + 2], r2[2 * M + 2];
+    ws.coeffs(newest, gg);
+    std::memcpy(r1, ws.ca.data(), M * 8); std::memcpy(r1 + M, ws.cb.data(), M * 8); r1[2 * M] = ws.sc[0]; r1[2 * M + 1] = ws.sc[1];
+    ws.coeffs_blocked(newest, gg);
+    std::memcpy(r2, ws.ca.data(), M * 8); std::memcpy(r2 + M, ws.cb.data(), M * 8); r2[2 * M] = ws.sc[0]; r2[2 * M + 1] = ws.sc[1];
+    bool same = true;   // bit for bit; two NaNs count as equal (IEEE 754 leaves a NaN's sign and payload to the implementation)
+    for (int q = 0; q < 2 * M + 2; ++q)
+      if (std::memcmp(&r1[q], &r2[q], 8) != 0 && !(std::isnan(r1[q]) && std::isnan(r2[q]))) same = false;
+    if (!same) ++bad;
+  }
+  return bad;
+}
 // One warp-form optimize() with a per-iteration direction check: for the (g, S, Y) the warp form had at every iteration,
 // recompute the direction with the reference's two-loop recursion in its serial order (lbfgs.hpp:1293-1316) and return
 // the largest ||d_gram - d_twoloop|| / ||d_twoloop||; out3 = {ret, iters, evals}.

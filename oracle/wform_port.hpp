@@ -390,6 +390,63 @@ struct Solver {
     sc[1] = part[0] - gamma * gg;
   }
 
+  // wf_coeffs AS THE KERNEL SCHEDULES IT (tp_lbfgs_warp.cuh): four steps per round of shuffles — the four rows whose
+  // values become final in steps 4k..4k+3 are broadcast at once, every lane redoes their in-block updates, then each
+  // lane applies the four steps to its own row.  Must equal coeffs() bit for bit (tests/test_oracle_cpu.py).
+  void coeffs_blocked(int newest, double gg) {
+    const double gamma = YS()[0] * YS()[2];
+    double rr[M], al[M], bacc[M];
+    for (int s_ = 0; s_ < M; ++s_) rr[s_] = -Sg()[s_] * INV()[s_];
+    for (int k = 0; k < M / 4; ++k) {
+      int sl[4];
+      for (int j = 0; j < 4; ++j) sl[j] = (newest - 4 * k - j) & (M - 1);
+      double a[4];
+      for (int j = 0; j < 4; ++j) a[j] = rr[sl[j]];                                  // the round of shuffles
+      for (int i = 0; i < 4; ++i)                                                      // in-block updates, every lane
+        for (int j = i + 1; j < 4; ++j) a[j] = std::fma(-a[i], A()[sl[j] * GS + sl[i]], a[j]);
+      for (int s_ = 0; s_ < M; ++s_)                                                   // own row, four steps in order
+        for (int i = 0; i < 4; ++i) rr[s_] = std::fma(-a[i], A()[s_ * GS + sl[i]], rr[s_]);
+    }
+    for (int s_ = 0; s_ < M; ++s_) al[s_] = rr[s_];
+    for (int s_ = 0; s_ < M; ++s_) {
+      double t0 = Yg()[s_], t1 = 0.0, t2 = 0.0, t3 = 0.0;
+      for (int c = 0; c < M; c += 4) {
+        t0 = std::fma(al[c], YY()[s_ * GS + c], t0);
+        t1 = std::fma(al[c + 1], YY()[s_ * GS + c + 1], t1);
+        t2 = std::fma(al[c + 2], YY()[s_ * GS + c + 2], t2);
+        t3 = std::fma(al[c + 3], YY()[s_ * GS + c + 3], t3);
+      }
+      bacc[s_] = (-gamma * ((t0 + t1) + (t2 + t3))) * INV()[s_];
+    }
+    for (int k = 0; k < M / 4; ++k) {
+      int sl[4];
+      for (int j = 0; j < 4; ++j) sl[j] = (newest - (M - 1) + 4 * k + j) & (M - 1);
+      double b[4], c[4];
+      for (int j = 0; j < 4; ++j) b[j] = bacc[sl[j]];
+      for (int i = 0; i < 4; ++i) {
+        c[i] = al[sl[i]] - b[i];
+        for (int j = i + 1; j < 4; ++j) b[j] = std::fma(c[i], Bt()[sl[j] * GS + sl[i]], b[j]);
+      }
+      for (int s_ = 0; s_ < M; ++s_)
+        for (int i = 0; i < 4; ++i) bacc[s_] = std::fma(c[i], Bt()[s_ * GS + sl[i]], bacc[s_]);
+    }
+    double part[M];
+    for (int s_ = 0; s_ < M; ++s_) {
+      const double aa = al[s_] - bacc[s_];
+      const double bb = -gamma * al[s_];
+      ca[s_] = aa;
+      cb[s_] = bb;
+      part[s_] = std::fma(aa, Sg()[s_], bb * Yg()[s_]);
+    }
+    for (int o = 8; o > 0; o >>= 1) {
+      double w[M];
+      for (int i = 0; i < M; ++i) w[i] = part[i] + part[i ^ o];
+      std::memcpy(part, w, sizeof(w));
+    }
+    sc[0] = -gamma;
+    sc[1] = part[0] - gamma * gg;
+  }
+
   // wf_direction
   void direction() {
     const double cg = sc[0];

@@ -232,6 +232,16 @@ def test_de_boor_matches_scipy_bspline(orc):
 # oracle/wform_port.hpp restates the product's default kernel (lean team form).  The GPU tests pin the kernel to it bit
 # for bit; the tests below quantify, on the CPU, how that arithmetic relates to the REFERENCE-ORDER iterate.
 
+def test_kernel_schedule_of_the_recurrences_equals_the_stepwise_form(orc):
+    """The kernel runs the two 16-step triangular recurrences of the coefficient-space two-loop four steps per round of
+    shuffles (tp_lbfgs_warp.cuh: wf_coeffs); oracle/wform_port.hpp restates both that schedule (coeffs_blocked) and the
+    step-by-step form (coeffs, the one every solve of the restatement uses).  On 200,000 random Gram blocks — masked as the
+    Gram update leaves them or dense, with signed zeros, 1e300 / 1e-300, infinities and NaNs mixed in — the coefficients
+    and g.d must be equal bit for bit (two NaNs count as equal)."""
+    bad = sum(orc.lib().L.orc_wform_coeffs_schedules_check(seed, 50000) for seed in range(4))
+    assert bad == 0
+
+
 def test_fast_order_evaluation_and_direction_vs_reference_order(orc, sq_map, sq_omap, tp):
     """(1) cost and gradient of the lean form vs the reference-order restatement: <= 1e-10 relative per evaluation
     (north-star tolerance; measured ~1e-15).  (2) Every L-BFGS iteration of a lean-form solve: the Gram-form direction vs
